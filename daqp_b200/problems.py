@@ -1,0 +1,141 @@
+"""Synthetic QP workloads for tests and bench.
+
+G1 = batched port of the reference's test generator ``generate_test_QP(n, m, ms, nActive, kappa)``
+(reference: interfaces/daqp-julia/test/utils.jl:3-53; MATLAB twin interfaces/daqp-matlab/utils/generate_test_QP.m):
+an LDP with a chosen optimal active set and multipliers >= 0 is built first and transformed back to a QP, so the
+optimum ``xref`` and the optimal active set are known by construction.
+
+G0 = the probe distribution of BASELINE.md §2 (nearly fully active optima).
+
+Both are pure numpy (counter-based Philox stream: seed = 0x5EED0000 + config id) so the same arrays feed the
+oracle, the reference and the CUDA path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+SEED_BASE = 0x5EED0000
+
+
+@dataclass
+class QPBatch:
+    """Homogeneous batch in the packed layout of ``daqp_b200_solve_packed``: every array is C-contiguous,
+    leading dimension = problem index. ``A`` holds only the general rows (m - ms)."""
+
+    n: int
+    m: int
+    ms: int
+    H: np.ndarray       # [N, n, n]
+    f: np.ndarray       # [N, n]
+    A: np.ndarray       # [N, m-ms, n]
+    bupper: np.ndarray  # [N, m]
+    blower: np.ndarray  # [N, m]
+    sense: np.ndarray   # [N, m] int32
+    xref: np.ndarray | None = None      # [N, n] known optimum (G1 only)
+    active_ref: np.ndarray | None = None  # [N, m] int8: +1 active at upper, -1 at lower, 0 inactive (G1 only)
+
+    @property
+    def N(self) -> int:
+        return self.H.shape[0]
+
+    def astype(self, dtype) -> "QPBatch":
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dtype)
+        return QPBatch(self.n, self.m, self.ms, c(self.H), c(self.f), c(self.A), c(self.bupper), c(self.blower),
+                       self.sense.copy(), c(self.xref), self.active_ref)
+
+    def slice(self, lo: int, hi: int) -> "QPBatch":
+        s = lambda a: None if a is None else np.ascontiguousarray(a[lo:hi])
+        return QPBatch(self.n, self.m, self.ms, s(self.H), s(self.f), s(self.A), s(self.bupper), s(self.blower),
+                       s(self.sense), s(self.xref), s(self.active_ref))
+
+    def input_bytes(self) -> int:
+        return sum(a.nbytes for a in (self.H, self.f, self.A, self.bupper, self.blower, self.sense))
+
+
+def _rng(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.Philox(key=seed))
+
+
+def generate_g1(N: int, n: int, m: int, ms: int, n_active: int, kappa: float = 100.0, seed: int = SEED_BASE,
+                random_nactive: bool = False) -> QPBatch:
+    """Batched ``generate_test_QP`` (utils.jl:3-53). ``random_nactive`` draws nActive ~ U{0..n_active} per problem
+    (config C5: divergent iteration counts)."""
+    assert m >= ms and n >= 2 and n_active <= m
+    rng = _rng(seed)
+    eig = np.ones((N, n))
+    eig[:, 1] = kappa
+    if n > 2:
+        eig[:, 2:] = 1.0 + (kappa - 1.0) * rng.random((N, n - 2))
+    Q = np.linalg.qr(rng.standard_normal((N, n, n)))[0]
+    sq = np.sqrt(eig)
+    T = sq[:, :, None] * np.swapaxes(Q, 1, 2)          # diag(sqrt e) Q'
+    Tinv = Q * (1.0 / sq)[:, None, :]                   # Q diag(1/sqrt e)
+    H = np.swapaxes(T, 1, 2) @ T
+
+    M = np.empty((N, m, n))
+    M[:, :ms, :] = Tinv[:, :ms, :]
+    M[:, ms:, :] = rng.standard_normal((N, m - ms, n))
+
+    perm = np.argsort(rng.random((N, m)), axis=1)       # shuffle(1:m)
+    pos = np.empty_like(perm)
+    np.put_along_axis(pos, perm, np.broadcast_to(np.arange(m), (N, m)), axis=1)
+    nact = np.full(N, n_active) if not random_nactive else rng.integers(0, n_active + 1, N)
+    nau = (rng.random(N) * (nact + 1)).astype(np.int64)  # rand(0:nActive)
+    nau = np.minimum(nau, nact)
+    is_up = pos < nau[:, None]
+    is_lo = (pos >= nau[:, None]) & (pos < nact[:, None])
+    inactive = pos >= nact[:, None]
+    sgn = is_up.astype(np.float64) - is_lo.astype(np.float64)
+
+    lam = rng.random((N, m)) * (sgn != 0)
+    u = -np.einsum("bmn,bm->bn", M, sgn * lam)           # u = -Ma' lam
+    Mu = np.einsum("bmn,bn->bm", M, u)
+    g1 = 0.01 + rng.random((N, m))
+    g2 = 0.01 + rng.random((N, m))
+    dupper = np.where(is_up, Mu, np.where(is_lo, Mu + g1, Mu + g1))
+    dlower = np.where(is_lo, Mu, np.where(is_up, Mu - g1, Mu - g2))
+    del inactive
+
+    v = rng.standard_normal((N, n))
+    f = np.einsum("bij,bi->bj", T, v)                    # T' v
+    x = np.einsum("bij,bj->bi", Tinv, u - v)             # T \ (u - v)
+    A = M[:, ms:, :] @ T
+    Mv = np.einsum("bmn,bn->bm", M, v)
+    bupper = dupper - Mv
+    blower = dlower - Mv
+    c = np.ascontiguousarray
+    return QPBatch(n, m, ms, c(H), c(f), c(A), c(bupper), c(blower), np.zeros((N, m), dtype=np.int32), c(x),
+                   sgn.astype(np.int8))
+
+
+def generate_g0(N: int, n: int, m: int, seed: int = SEED_BASE + 100) -> QPBatch:
+    """Probe distribution of BASELINE.md §2: H = G'G/n + I, f ~ 3 N(0,1), A ~ N(0,1), b = A x0 +- (0.1 + U)."""
+    rng = _rng(seed)
+    G = rng.standard_normal((N, n, n))
+    H = np.swapaxes(G, 1, 2) @ G / n + np.eye(n)
+    f = 3.0 * rng.standard_normal((N, n))
+    A = rng.standard_normal((N, m, n))
+    x0 = 0.1 * rng.standard_normal((N, n))
+    Ax0 = np.einsum("bmn,bn->bm", A, x0)
+    bupper = Ax0 + 0.1 + rng.random((N, m))
+    blower = Ax0 - 0.1 - rng.random((N, m))
+    c = np.ascontiguousarray
+    return QPBatch(n, m, 0, c(H), c(f), c(A), c(bupper), c(blower), np.zeros((N, m), dtype=np.int32))
+
+
+# BASELINE.json configs. C4/C5 are widened rows (warm start / fp32 mixed sizes).
+CONFIGS = {
+    "C1": dict(n=10, m=20, ms=0, n_active=8, N=1),
+    "C2": dict(n=20, m=60, ms=0, n_active=16, N=10_000),
+    "C3": dict(n=50, m=150, ms=0, n_active=40, N=100_000),
+    "C4": dict(n=120, m=400, ms=120, n_active=96, N=50_000),
+}
+
+
+def generate_config(name: str, N: int | None = None, kappa: float = 100.0) -> QPBatch:
+    cfg = dict(CONFIGS[name])
+    n_default = cfg.pop("N")
+    seed = SEED_BASE + int(name[1:])
+    return generate_g1(N if N is not None else n_default, kappa=kappa, seed=seed, **cfg)

@@ -1,0 +1,89 @@
+/* oracle/daqp_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (own code, scalar C) of the reference's dual active-set hot path:
+ *   daqp_quadprog -> QP->LDP transform -> daqp_ldp loop -> ldp2qp_solution -> daqp_extract_result
+ * (reference: src/api.c:62-79, src/utils.c:58-687, src/daqp.c:6-139, src/auxiliary.c, src/factorization.c).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ * The product (daqp_b200/) never links or calls it.
+ *
+ * Parity pinning: tests/test_oracle.py checks this file against (1) the reference's known-answer tests,
+ * (2) the reference itself compiled from /root/reference into oracle/_ref (bit-exact against the
+ * -O2 -ffp-contract=off build), (3) committed golden vectors under tests/golden/.
+ *
+ * Compile with -DORC_SINGLE for the c_float=float variant (reference: include/types.h:8-12).
+ */
+#ifndef DAQP_ORACLE_H
+#define DAQP_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef ORC_SINGLE
+typedef float orc_real;
+#else
+typedef double orc_real;
+#endif
+
+/* Same field order / layout as DAQPProblem (include/types.h:32-49). */
+typedef struct {
+    int n, m, ms;
+    orc_real *H, *f, *A, *bupper, *blower;
+    int *sense;
+    int *break_points;
+    int nh;
+    int problem_type;
+} OrcProblem;
+
+/* Same layout as DAQPSettings (include/types.h:52-74). */
+typedef struct {
+    orc_real primal_tol, dual_tol, zero_tol, pivot_tol, progress_tol;
+    int cycle_tol, iter_limit;
+    orc_real fval_bound;
+    orc_real eps_prox, eta_prox;
+    orc_real rho_soft;
+    orc_real rel_subopt, abs_subopt;
+    orc_real sing_tol, refactor_tol, time_limit;
+} OrcSettings;
+
+/* Same layout as DAQPResult (include/api.h:15-27). */
+typedef struct {
+    orc_real *x, *lam;
+    orc_real fval, soft_slack;
+    int exitflag, iter, nodes;
+    orc_real solve_time, setup_time;
+} OrcResult;
+
+/* Extra observability the reference only exposes through its workspace: final working set + op counts. */
+typedef struct {
+    int n_active;     /* final |WS| */
+    int *ws;          /* caller buffer, >= n+ns+1 ints (may be NULL) */
+    int *sense_out;   /* caller buffer, m ints: final sense bits (may be NULL) */
+    int n_scan;       /* calls of the feasibility scan (daqp_add_infeasible)        */
+    int n_add;        /* LDL row appends (daqp_update_LDL_add)                        */
+    int n_remove;     /* LDL row deletions (daqp_update_LDL_remove incl. last-row)    */
+    int n_csp;        /* CSP solves                                                    */
+} OrcTrace;
+
+void orc_default_settings(OrcSettings *s);
+
+/* Drop-in equivalent of daqp_quadprog() restricted to the hot-path scope (dense H>0, no binaries/hierarchy/
+ * AVI/prox). Out-of-scope inputs return exitflag -8. trace may be NULL. */
+void orc_quadprog(OrcResult *res, const OrcProblem *qp, const OrcSettings *settings, OrcTrace *trace);
+
+/* Loop orc_quadprog over a strided homogeneous batch (same layout as daqp_b200_solve_packed); used by bench.py's
+ * cpu_baseline leg so the timed loop has no Python in it. nthreads>1 uses pthreads (dynamic chunks of 16 problems).
+ * sense may be NULL. x:[N][n] lam:[N][m] fval:[N] exitflag:[N] iter:[N]. Returns wall seconds. */
+double orc_solve_packed(int N, int n, int m, int ms,
+                        const orc_real *H, const orc_real *f, const orc_real *A,
+                        const orc_real *bupper, const orc_real *blower, const int *sense,
+                        const OrcSettings *settings,
+                        orc_real *x, orc_real *lam, orc_real *fval, int *exitflag, int *iter,
+                        int *trace_counts /* [N][4] scan,add,remove,csp or NULL */,
+                        int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

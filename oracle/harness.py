@@ -1,0 +1,218 @@
+"""oracle/harness.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes loaders for (a) the reference compiled from /root/reference into oracle/_ref/*.so and (b) this repo's scalar
+restatement oracle/libdaqp_oracle*.so. Imported only by tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+Struct layouts mirror the reference ABI (include/types.h:32-74,187-264, include/api.h:15-27).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+UPDATE_UNCONSTRAINED = 64
+UPDATE_ELIMINATE = 128
+
+
+def _structs(real):
+    P = C.POINTER
+
+    class Problem(C.Structure):
+        _fields_ = [("n", C.c_int), ("m", C.c_int), ("ms", C.c_int), ("H", P(real)), ("f", P(real)), ("A", P(real)),
+                    ("bupper", P(real)), ("blower", P(real)), ("sense", P(C.c_int)), ("break_points", P(C.c_int)),
+                    ("nh", C.c_int), ("problem_type", C.c_int)]
+
+    class Settings(C.Structure):
+        _fields_ = [("primal_tol", real), ("dual_tol", real), ("zero_tol", real), ("pivot_tol", real),
+                    ("progress_tol", real), ("cycle_tol", C.c_int), ("iter_limit", C.c_int), ("fval_bound", real),
+                    ("eps_prox", real), ("eta_prox", real), ("rho_soft", real), ("rel_subopt", real),
+                    ("abs_subopt", real), ("sing_tol", real), ("refactor_tol", real), ("time_limit", real)]
+
+    class Result(C.Structure):
+        _fields_ = [("x", P(real)), ("lam", P(real)), ("fval", real), ("soft_slack", real), ("exitflag", C.c_int),
+                    ("iter", C.c_int), ("nodes", C.c_int), ("solve_time", real), ("setup_time", real)]
+
+    class Workspace(C.Structure):  # include/types.h:187-264 (SOFT_WEIGHTS off)
+        _fields_ = [("qp", C.c_void_p), ("n", C.c_int), ("m", C.c_int), ("ms", C.c_int), ("M", P(real)),
+                    ("dupper", P(real)), ("dlower", P(real)), ("Rinv", P(real)), ("v", P(real)),
+                    ("sense", P(C.c_int)), ("scaling", P(real)), ("RinvD", P(real)), ("x", P(real)),
+                    ("xold", P(real)), ("lam", P(real)), ("lam_star", P(real)), ("u", P(real)), ("fval", real),
+                    ("L", P(real)), ("D", P(real)), ("xldl", P(real)), ("zldl", P(real)), ("reuse_ind", C.c_int),
+                    ("WS", P(C.c_int)), ("n_active", C.c_int), ("iterations", C.c_int), ("sing_ind", C.c_int),
+                    ("prox_mask", P(C.c_int)), ("n_prox", C.c_int), ("soft_slack", real), ("settings", C.c_void_p),
+                    ("bnb", C.c_void_p), ("nh", C.c_int), ("break_points", P(C.c_int)), ("avi", C.c_void_p),
+                    ("eq", C.c_void_p), ("timer", C.c_void_p), ("Mu", P(real))]
+
+    class Trace(C.Structure):
+        _fields_ = [("n_active", C.c_int), ("ws", P(C.c_int)), ("sense_out", P(C.c_int)), ("n_scan", C.c_int),
+                    ("n_add", C.c_int), ("n_remove", C.c_int), ("n_csp", C.c_int)]
+
+    return Problem, Settings, Result, Workspace, Trace
+
+
+_F64 = _structs(C.c_double)
+_F32 = _structs(C.c_float)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the oracle restatement, and the reference into oracle/_ref when /root/reference is present."""
+    targets = ["oracle"] + (["ref"] if ref and os.path.isdir("/root/reference/src") else [])
+    subprocess.run(["make", "-C", HERE, "CC=gcc"] + targets, check=True, capture_output=True)
+
+
+def have_ref(name: str = "libdaqp_ref.so") -> bool:
+    return os.path.exists(os.path.join(REF_DIR, name))
+
+
+@dataclass
+class Solution:
+    x: np.ndarray
+    lam: np.ndarray
+    fval: np.ndarray
+    exitflag: np.ndarray
+    iter: np.ndarray
+    ws: list | None = None        # per problem: working-set indices in factor order
+    sense: np.ndarray | None = None  # [N, m] final sense bits
+    counts: np.ndarray | None = None  # [N,4] scan, add, remove, csp (oracle only)
+    seconds: float = 0.0
+
+
+def default_settings(dtype=np.float64, **over):
+    S = (_F64 if dtype == np.float64 else _F32)[1]
+    s = S(1e-6, 1e-12, 1e-11, 1e-6, 1e-14, 10, 10000, 1e30, -1e-6, -1.0, 1e-6, 0, 0, 3.7e-11, 1e-9, 0)
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+def _ptr(a, real):
+    return None if a is None else a.ctypes.data_as(C.POINTER(real))
+
+
+class RefLib:
+    """The unmodified reference (daqp_quadprog & the workspace API), loaded from oracle/_ref."""
+
+    def __init__(self, name: str = "libdaqp_ref.so"):
+        self.single = "f32" in name
+        self.real = C.c_float if self.single else C.c_double
+        self.dtype = np.float32 if self.single else np.float64
+        self.Problem, self.Settings, self.Result, self.Workspace, _ = _F32 if self.single else _F64
+        self.lib = C.CDLL(os.path.join(REF_DIR, name))
+        self.lib.daqp_quadprog.restype = None
+        self.lib.setup_daqp_main.restype = C.c_int
+        self.lib.daqp_solve.restype = None
+
+    def _problem(self, b, p, sense):
+        real = self.real
+        mA = b.m - b.ms
+        return self.Problem(b.n, b.m, b.ms, _ptr(b.H[p], real), _ptr(b.f[p], real) if b.f is not None else None,
+                            _ptr(b.A[p], real) if mA > 0 else None, _ptr(b.bupper[p], real), _ptr(b.blower[p], real),
+                            sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)
+
+    def solve(self, b, settings=None, use_sense: bool | None = None, want_ws: bool = False) -> Solution:
+        """One daqp_quadprog call per problem (api.c:62-79). want_ws drives the same calls through
+        setup_daqp_main + daqp_solve so that the final working set can be read from the workspace."""
+        import time
+        N, n, m = b.N, b.n, b.m
+        b = b.astype(self.dtype)
+        x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
+        fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
+        ws = [] if want_ws else None
+        sense_out = np.zeros((N, m), np.int32) if want_ws else None
+        if use_sense is None:
+            use_sense = bool(np.any(b.sense))
+        sp = C.byref(settings) if settings is not None else None
+        t0 = time.perf_counter()
+        for p in range(N):
+            sense = b.sense[p].copy() if use_sense else None
+            qp = self._problem(b, p, sense)
+            res = self.Result(_ptr(x[p], self.real), _ptr(lam[p], self.real), 0, 0, 0, 0, 0, 0, 0)
+            if not want_ws:
+                self.lib.daqp_quadprog(C.byref(res), C.byref(qp), sp)
+            else:
+                work = self.Workspace()
+                work.settings = C.cast(sp, C.c_void_p) if sp is not None else None
+                st = self.real(0)
+                rc = self.lib.setup_daqp_main(C.byref(qp), C.byref(work), C.byref(st),
+                                              UPDATE_UNCONSTRAINED | UPDATE_ELIMINATE)
+                res.exitflag = rc
+                if rc >= 0:
+                    self.lib.daqp_solve(C.byref(res), C.byref(work))
+                    ws.append([work.WS[i] for i in range(work.n_active)])
+                    sense_out[p] = [work.sense[i] for i in range(m)]
+                    if sp is not None:
+                        work.settings = None
+                    self.lib.free_daqp_workspace(C.byref(work))
+                    self.lib.free_daqp_ldp(C.byref(work))
+                else:
+                    ws.append([])
+            fval[p], flag[p], it[p] = res.fval, res.exitflag, res.iter
+        return Solution(x, lam, fval, flag, it, ws, sense_out, None, time.perf_counter() - t0)
+
+
+class OracleLib:
+    """This repo's scalar restatement (oracle/daqp_oracle.c)."""
+
+    def __init__(self, single: bool = False):
+        self.single = single
+        self.real = C.c_float if single else C.c_double
+        self.dtype = np.float32 if single else np.float64
+        self.Problem, self.Settings, self.Result, _, self.Trace = _F32 if single else _F64
+        self.lib = C.CDLL(os.path.join(HERE, "libdaqp_oracle_f32.so" if single else "libdaqp_oracle.so"))
+        self.lib.orc_quadprog.restype = None
+        self.lib.orc_solve_packed.restype = C.c_double
+
+    def solve(self, b, settings=None, use_sense: bool | None = None) -> Solution:
+        import time
+        N, n, m = b.N, b.n, b.m
+        b = b.astype(self.dtype)
+        real = self.real
+        x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
+        fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
+        counts = np.zeros((N, 4), np.int32)
+        sense_out = np.zeros((N, m), np.int32)
+        ws = []
+        wsbuf = np.zeros(n + m + 2, np.int32)
+        if use_sense is None:
+            use_sense = bool(np.any(b.sense))
+        sp = C.byref(settings) if settings is not None else None
+        mA = m - b.ms
+        t0 = time.perf_counter()
+        for p in range(N):
+            sense = b.sense[p].copy() if use_sense else None
+            qp = self.Problem(n, m, b.ms, _ptr(b.H[p], real), _ptr(b.f[p], real) if b.f is not None else None,
+                              _ptr(b.A[p], real) if mA > 0 else None, _ptr(b.bupper[p], real),
+                              _ptr(b.blower[p], real),
+                              sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)
+            res = self.Result(_ptr(x[p], real), _ptr(lam[p], real), 0, 0, 0, 0, 0, 0, 0)
+            tr = self.Trace(0, wsbuf.ctypes.data_as(C.POINTER(C.c_int)),
+                            sense_out[p].ctypes.data_as(C.POINTER(C.c_int)), 0, 0, 0, 0)
+            self.lib.orc_quadprog(C.byref(res), C.byref(qp), sp, C.byref(tr))
+            fval[p], flag[p], it[p] = res.fval, res.exitflag, res.iter
+            counts[p] = (tr.n_scan, tr.n_add, tr.n_remove, tr.n_csp)
+            ws.append(wsbuf[:tr.n_active].tolist())
+        return Solution(x, lam, fval, flag, it, ws, sense_out, counts, time.perf_counter() - t0)
+
+    def solve_packed(self, b, settings=None, nthreads: int = 1, use_sense: bool | None = None) -> Solution:
+        """Whole batch inside C (no Python in the timed loop); returns wall seconds measured in C."""
+        N, n, m = b.N, b.n, b.m
+        b = b.astype(self.dtype)
+        real = self.real
+        x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
+        fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
+        counts = np.zeros((N, 4), np.int32)
+        if use_sense is None:
+            use_sense = bool(np.any(b.sense))
+        sp = C.byref(settings) if settings is not None else None
+        secs = self.lib.orc_solve_packed(
+            N, n, m, b.ms, _ptr(b.H, real), _ptr(b.f, real), _ptr(b.A, real), _ptr(b.bupper, real),
+            _ptr(b.blower, real), b.sense.ctypes.data_as(C.POINTER(C.c_int)) if use_sense else None, sp,
+            _ptr(x, real), _ptr(lam, real), _ptr(fval, real), flag.ctypes.data_as(C.POINTER(C.c_int)),
+            it.ctypes.data_as(C.POINTER(C.c_int)), counts.ctypes.data_as(C.POINTER(C.c_int)), nthreads)
+        return Solution(x, lam, fval, flag, it, None, None, counts, secs)
