@@ -1,0 +1,272 @@
+"""daqp_b200 -- B200-native batched dual active-set QP engine behind the DAQP C API.
+
+Host-side mirror of the reference's Python interface for the hot path (reference:
+interfaces/daqp-python/daqp.pyx:68-221 ``daqp.solve``), plus the batch entry points the reference lacks.
+Everything here calls the C ABI in ``libdaqp_b200.so`` (include/daqp_b200.h) through ctypes; there is no
+Python/CPU solve path -- if the CUDA library is missing or no GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdaqp_b200.so")
+
+DAQP_INF = 1e30
+EXIT_OPTIMAL, EXIT_SOFT_OPTIMAL = 1, 2
+EXIT_INFEASIBLE, EXIT_CYCLE, EXIT_UNBOUNDED, EXIT_ITERLIMIT = -1, -2, -3, -4
+EXIT_NONCONVEX, EXIT_OVERDETERMINED_INITIAL, EXIT_TIMELIMIT, EXIT_UNSUPPORTED = -5, -6, -7, -8
+ACTIVE, LOWER, IMMUTABLE, SOFT, BINARY = 1, 2, 4, 8, 16
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class DAQPProblem(C.Structure):  # include/daqp_b200.h == reference include/types.h:14-50
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("ms", C.c_int), ("H", _dp), ("f", _dp), ("A", _dp),
+                ("bupper", _dp), ("blower", _dp), ("sense", _ip), ("break_points", _ip), ("nh", C.c_int),
+                ("problem_type", C.c_int)]
+
+
+class DAQPSettings(C.Structure):  # reference include/types.h:52-74
+    _fields_ = [("primal_tol", C.c_double), ("dual_tol", C.c_double), ("zero_tol", C.c_double),
+                ("pivot_tol", C.c_double), ("progress_tol", C.c_double), ("cycle_tol", C.c_int),
+                ("iter_limit", C.c_int), ("fval_bound", C.c_double), ("eps_prox", C.c_double),
+                ("eta_prox", C.c_double), ("rho_soft", C.c_double), ("rel_subopt", C.c_double),
+                ("abs_subopt", C.c_double), ("sing_tol", C.c_double), ("refactor_tol", C.c_double),
+                ("time_limit", C.c_double)]
+
+
+class DAQPResult(C.Structure):  # reference include/api.h:15-27
+    _fields_ = [("x", _dp), ("lam", _dp), ("fval", C.c_double), ("soft_slack", C.c_double), ("exitflag", C.c_int),
+                ("iter", C.c_int), ("nodes", C.c_int), ("solve_time", C.c_double), ("setup_time", C.c_double)]
+
+
+class DAQPB200Diag(C.Structure):
+    _fields_ = [("n_active", _ip), ("ws", _ip), ("counts", _ip), ("sense", C.POINTER(C.c_ubyte))]
+
+
+class DAQPB200Stats(C.Structure):
+    _fields_ = [("setup_launches", C.c_int), ("solve_launches", C.c_int), ("setup_ms", C.c_double),
+                ("solve_ms", C.c_double), ("warps_per_sm", C.c_int), ("scratch_bytes", C.c_longlong)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library. Fails loudly: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m daqp_b200.build` "
+                               "(daqp_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.daqp_quadprog.restype = None
+        L.daqp_default_settings.restype = None
+        L.daqp_quadprog_batch.restype = C.c_int
+        L.daqp_b200_create.restype = C.c_int
+        L.daqp_b200_destroy.restype = None
+        L.daqp_b200_solve_packed.restype = C.c_int
+        L.daqp_b200_solve_device.restype = C.c_int
+        L.daqp_b200_get_stats.restype = C.c_int
+        L.daqp_b200_set_scratch_limit.restype = None
+        L.daqp_b200_set_scratch_limit.argtypes = [C.c_void_p, C.c_longlong]
+        L.daqp_b200_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"daqp_b200 error {rc}: {lib().daqp_b200_last_error().decode()}")
+
+
+def default_settings(**over) -> DAQPSettings:
+    s = DAQPSettings()
+    lib().daqp_default_settings(C.byref(s))
+    for k, v in over.items():
+        if not hasattr(s, k):
+            raise TypeError(f"unknown setting {k!r}")
+        setattr(s, k, v)
+    return s
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t=_dp):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def solve(H, f, A, bupper, blower=None, sense=None, **settings):
+    """Single QP through the drop-in ``daqp_quadprog`` symbol (same call shape and return value as the
+    reference's ``daqp.solve``: ``x, fval, exitflag, info``). bupper/blower longer than A's row count means the
+    leading entries are simple bounds (reference daqp.pyx:96-104)."""
+    A = _f64(A)
+    H = _f64(H); f = _f64(f); bupper = _f64(bupper)
+    mA, n = (A.shape if A is not None and A.size else (0, H.shape[0]))
+    m = bupper.shape[0]
+    blower = np.full(m, -DAQP_INF) if blower is None else _f64(blower)
+    sense = np.zeros(m, dtype=np.intc) if sense is None else np.ascontiguousarray(sense, dtype=np.intc)
+    x = np.empty(n); lam = np.empty(m)
+    qp = DAQPProblem(n, m, m - mA, _p(H), _p(f), _p(A) if mA else None, _p(bupper), _p(blower), _p(sense, _ip),
+                     None, 0, 0)
+    st = default_settings(**settings)
+    res = DAQPResult(_p(x), _p(lam) if m else None, 0, 0, 0, 0, 0, 0, 0)
+    lib().daqp_quadprog(C.byref(res), C.byref(qp), C.byref(st))
+    return x, res.fval, res.exitflag, {"solve_time": res.solve_time, "setup_time": res.setup_time,
+                                       "iterations": res.iter, "nodes": res.nodes, "lam": lam}
+
+
+class BatchResult:
+    __slots__ = ("x", "lam", "fval", "exitflag", "iter", "n_active", "ws", "counts", "sense")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+    def working_sets(self):
+        return [self.ws[p, : self.n_active[p]].tolist() for p in range(len(self.n_active))]
+
+
+class Engine:
+    """Owns one DAQPB200Handle (device scratch + streams)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        _check(lib().daqp_b200_create(C.byref(self._h), device))
+
+    def close(self):
+        if self._h:
+            lib().daqp_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_scratch_limit(self, nbytes: int):
+        lib().daqp_b200_set_scratch_limit(self._h, int(nbytes))
+
+    def stats(self, reset: bool = False) -> dict:
+        s = DAQPB200Stats()
+        _check(lib().daqp_b200_get_stats(self._h, C.byref(s), int(reset)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    # -- host arrays -----------------------------------------------------------------------------------------
+    def solve_batch(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, diag: bool = False,
+                    out: BatchResult | None = None, **settings) -> BatchResult:
+        """Homogeneous batch in host memory: H[N,n,n], f[N,n]|None, A[N,m-ms,n], bupper/blower[N,m],
+        sense[N,m]|None (``daqp_b200_solve_packed``). Pass pinned arrays for asynchronous copies."""
+        H = _f64(H); f = _f64(f); A = _f64(A); bupper = _f64(bupper); blower = _f64(blower)
+        N, n = H.shape[0], H.shape[1]
+        m = bupper.shape[1]
+        mA = A.shape[1] if A is not None and A.size else 0
+        ms = m - mA if ms is None else ms
+        if sense is not None:
+            sense = np.ascontiguousarray(sense, dtype=np.intc)
+        r = out or BatchResult(x=np.empty((N, n)), lam=np.empty((N, m)), fval=np.zeros(N),
+                               exitflag=np.empty(N, np.intc), iter=np.empty(N, np.intc))
+        d = None
+        if diag:
+            ldm = (max(m, 1) + 3) // 4 * 4
+            r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + 1), np.intc)
+            r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
+            d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
+                             r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        st = default_settings(**settings)
+        _check(lib().daqp_b200_solve_packed(self._h, N, n, m, ms, _p(H), _p(f), _p(A), _p(bupper), _p(blower),
+                                            _p(sense, _ip), C.byref(st), _p(r.x), _p(r.lam), _p(r.fval),
+                                            _p(r.exitflag, _ip), _p(r.iter, _ip), C.byref(d) if d else None))
+        if diag:
+            r.sense = r.sense[:, :m]
+        return r
+
+    # -- device arrays (torch CUDA tensors) -------------------------------------------------------------------
+    def solve_batch_device(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, out=None,
+                           diag=None, stream=None, **settings):
+        """Same on CUDA tensors (float64, contiguous); enqueues on the current torch stream and returns a dict of
+        output tensors without synchronising (``daqp_b200_solve_device``)."""
+        import torch
+        N, n = H.shape[0], H.shape[1]
+        m = bupper.shape[1]
+        mA = A.shape[1] if A is not None and A.numel() else 0
+        ms = m - mA if ms is None else ms
+        dev = H.device
+        for t in (H, f, A, bupper, blower):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        if sense is not None:
+            assert sense.is_cuda and sense.dtype == torch.int32 and sense.is_contiguous()
+        if out is None:
+            out = {"x": torch.empty((N, n), dtype=torch.float64, device=dev),
+                   "lam": torch.empty((N, m), dtype=torch.float64, device=dev),
+                   "fval": torch.zeros(N, dtype=torch.float64, device=dev),
+                   "exitflag": torch.empty(N, dtype=torch.int32, device=dev),
+                   "iter": torch.empty(N, dtype=torch.int32, device=dev)}
+        d = None
+        if diag is not None:
+            d = DAQPB200Diag(C.cast(diag["n_active"].data_ptr(), _ip), C.cast(diag["ws"].data_ptr(), _ip),
+                             C.cast(diag["counts"].data_ptr(), _ip),
+                             C.cast(diag["sense"].data_ptr(), C.POINTER(C.c_ubyte)))
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        ptr = lambda t, ty=_dp: None if t is None else C.cast(t.data_ptr(), ty)
+        st = default_settings(**settings)
+        _check(lib().daqp_b200_solve_device(self._h, N, n, m, ms, ptr(H), ptr(f), ptr(A), ptr(bupper), ptr(blower),
+                                            ptr(sense, _ip), C.byref(st), ptr(out["x"]), ptr(out["lam"]),
+                                            ptr(out["fval"]), ptr(out["exitflag"], _ip), ptr(out["iter"], _ip),
+                                            C.byref(d) if d else None, C.c_void_p(stream)))
+        return out
+
+    @staticmethod
+    def alloc_diag(N: int, n: int, m: int, device):
+        import torch
+        ldm = (max(m, 1) + 3) // 4 * 4
+        return {"n_active": torch.zeros(N, dtype=torch.int32, device=device),
+                "ws": torch.zeros((N, n + 1), dtype=torch.int32, device=device),
+                "counts": torch.zeros((N, 4), dtype=torch.int32, device=device),
+                "sense": torch.zeros((N, ldm), dtype=torch.uint8, device=device)}
+
+
+_default_engine = None
+
+
+def solve_batch(H, f, A, bupper, blower, sense=None, **kw) -> BatchResult:
+    """Module-level convenience: ``Engine().solve_batch`` on a process-wide engine."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine.solve_batch(H, f, A, bupper, blower, sense, **kw)
+
+
+def quadprog_batch(problems: list[dict], **settings):
+    """Array-of-struct batch through ``daqp_quadprog_batch``: a list of dicts with keys H, f, A, bupper, blower,
+    sense (the last three optional as in ``solve``); problems may differ in size. Returns a list of
+    ``(x, fval, exitflag, info)`` tuples."""
+    N = len(problems)
+    qps = (DAQPProblem * N)(); res = (DAQPResult * N)()
+    keep = []
+    for i, pr in enumerate(problems):
+        H = _f64(pr["H"]); f = _f64(pr.get("f")); A = _f64(pr.get("A")); bu = _f64(pr["bupper"])
+        m = bu.shape[0]
+        n = H.shape[0]
+        mA = A.shape[0] if A is not None and A.size else 0
+        bl = np.full(m, -DAQP_INF) if pr.get("blower") is None else _f64(pr["blower"])
+        se = None if pr.get("sense") is None else np.ascontiguousarray(pr["sense"], dtype=np.intc)
+        x = np.empty(n); lam = np.empty(m)
+        keep.append((H, f, A, bu, bl, se, x, lam))
+        qps[i] = DAQPProblem(n, m, m - mA, _p(H), _p(f), _p(A) if mA else None, _p(bu), _p(bl), _p(se, _ip), None, 0, 0)
+        res[i] = DAQPResult(_p(x), _p(lam) if m else None, 0, 0, 0, 0, 0, 0, 0)
+    st = default_settings(**settings)
+    _check(lib().daqp_quadprog_batch(N, qps, res, C.byref(st)))
+    return [(keep[i][6], res[i].fval, res[i].exitflag,
+             {"iterations": res[i].iter, "lam": keep[i][7], "solve_time": res[i].solve_time,
+              "setup_time": res[i].setup_time, "nodes": res[i].nodes}) for i in range(N)]

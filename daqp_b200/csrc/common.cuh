@@ -1,0 +1,87 @@
+// daqp_b200/csrc/common.cuh -- shared device helpers for the batched dual active-set QP engine (sm_100a).
+//
+// Execution model: ONE WARP PER PROBLEM for the whole solve. All control flow is warp-uniform (every lane
+// carries the same n_active / sing_ind / reuse_ind in registers); vectors and the LDL' factor live in shared
+// memory private to the warp; the constraint matrix is streamed from HBM/L2 with 128-bit loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dq {
+
+constexpr int EMPTY_IND = -1;
+constexpr unsigned FULL = 0xffffffffu;
+
+// sense bits: reference include/constants.h:64-96
+constexpr int B_ACTIVE = 1, B_LOWER = 2, B_IMMUTABLE = 4, B_SOFT = 8, B_BINARY = 16;
+
+// exit flags: reference include/constants.h:42-51
+constexpr int EXIT_SOFT_OPTIMAL = 2, EXIT_OPTIMAL = 1, EXIT_INFEASIBLE = -1, EXIT_CYCLE = -2, EXIT_UNBOUNDED = -3,
+              EXIT_ITERLIMIT = -4, EXIT_NONCONVEX = -5, EXIT_OVERDETERMINED_INITIAL = -6, EXIT_TIMELIMIT = -7,
+              EXIT_UNSUPPORTED = -8;
+
+// setup kernel -> solve kernel hand-over (per problem)
+constexpr int SETUP_SOLVE = 0;          // LDP formed, run the active-set loop
+constexpr int SETUP_SOLVE_ACTIVATE = 1; // same, but sense carries pre-activated rows (warm start / equalities)
+constexpr int SETUP_UNCONSTRAINED = 2;  // unconstrained optimum is feasible: x already final (utils.c:679-683)
+// negative values are final exit flags raised by the setup (api.c:69-72)
+
+template <typename T>
+struct DevSettings { // the DAQPSettings fields the hot path reads (include/types.h:52-74)
+    T primal_tol, dual_tol, zero_tol, pivot_tol, progress_tol, fval_bound, rho_soft, sing_tol, refactor_tol, eps_prox;
+    int cycle_tol, iter_limit;
+};
+
+template <typename T> struct VecOf;
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
+
+// 128-bit read-only global load
+template <typename T> __device__ __forceinline__ void ldg_vec(const T* p, T (&out)[VecOf<T>::N]);
+template <> __device__ __forceinline__ void ldg_vec<double>(const double* p, double (&out)[2]) {
+    double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    out[0] = v.x; out[1] = v.y;
+}
+template <> __device__ __forceinline__ void ldg_vec<float>(const float* p, float (&out)[4]) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <typename T> __device__ __forceinline__ void stg_vec(T* p, const T (&in)[VecOf<T>::N]);
+template <> __device__ __forceinline__ void stg_vec<double>(double* p, const double (&in)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(in[0], in[1]);
+}
+template <> __device__ __forceinline__ void stg_vec<float>(float* p, const float (&in)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+}
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Lexicographic (value, key) minimum over the warp. Reproduces a sequential "strict <, first index wins" scan
+// (reference auxiliary.c:112,118,139,145,293): the smallest value wins, ties go to the smallest key.
+// Lanes without a candidate pass key = INT_MAX. NaN never enters because candidates are admitted with '<'.
+template <typename T> __device__ __forceinline__ void warp_argmin(T& val, int& key) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T ov = __shfl_xor_sync(FULL, val, o);
+        int ok = __shfl_xor_sync(FULL, key, o);
+        if (ov < val || (ov == val && ok < key)) { val = ov; key = ok; }
+    }
+}
+
+template <typename T> __device__ __forceinline__ T rsqrt_exact(T x);
+template <> __device__ __forceinline__ double rsqrt_exact<double>(double x) { return 1.0 / sqrt(x); }
+template <> __device__ __forceinline__ float rsqrt_exact<float>(float x) { return 1.0f / sqrtf(x); }
+
+__host__ __device__ __forceinline__ int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// packed strict-lower storage of the unit-lower factor: row i holds L[i][0..i-1] at offset i(i-1)/2
+__host__ __device__ __forceinline__ int loff(int i) { return (i * (i - 1)) >> 1; }
+// packed upper-triangular (by rows) offset such that (R + roff(i,n))[j] is element (i,j), j >= i
+// (reference DAQP_R_OFFSET, include/constants.h:39)
+__host__ __device__ __forceinline__ int roff(int i, int n) { return ((2 * n - i - 1) * i) / 2; }
+
+} // namespace dq

@@ -1,0 +1,470 @@
+// daqp_b200/csrc/daqp_b200.cu -- host side of the C ABI declared in include/daqp_b200.h.
+//
+// Mirrors the reference's entry sequence for the hot path (src/api.c:62-79: setup_daqp_main -> daqp_solve ->
+// daqp_extract_result) as two kernel launches per chunk of problems:
+//   qp_setup_kernel  (QP -> LDP, setup_kernel.cuh)   then   ldp_solve_kernel (active-set loop + extraction).
+// There is no CPU solve path in this library: without a CUDA device every entry point reports an error.
+#include "../../include/daqp_b200.h"
+#include "ldp_kernel.cuh"
+#include "setup_kernel.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace dq;
+
+static thread_local std::string g_last_error;
+static int fail(const char* what, cudaError_t e, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "daqp_b200: %s failed at line %d: %s", what, line, cudaGetErrorString(e));
+    g_last_error = buf;
+    return -100 - (int)e;
+}
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return fail(#call, e_, __LINE__);       \
+    } while (0)
+
+extern "C" const char* daqp_b200_last_error(void) { return g_last_error.c_str(); }
+
+struct EventTriple { cudaEvent_t e0, e1, e2; };
+
+struct DAQPB200Handle {
+    int device = 0, num_sms = 0;
+    size_t smem_optin = 0;
+    cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+    long long scratch_limit = 24ll << 30;
+    std::vector<EventTriple> pending, free_events;
+    DAQPB200Stats stats{};
+    std::mutex mu;
+};
+
+extern "C" void daqp_default_settings(DAQPSettings* s) { // reference src/api.c:505-527, include/constants.h:15-29
+    s->primal_tol = 1e-6; s->dual_tol = 1e-12; s->zero_tol = 1e-11; s->pivot_tol = 1e-6;
+    s->progress_tol = 1e-14; s->cycle_tol = 10; s->iter_limit = 10000; s->fval_bound = DAQP_INF;
+    s->eps_prox = -1e-6; s->eta_prox = -1.0; s->rho_soft = 1e-6; s->rel_subopt = 0; s->abs_subopt = 0;
+    s->sing_tol = 3.7e-11; s->refactor_tol = 1e-9; s->time_limit = 0;
+}
+
+template <typename T>
+static DevSettings<T> to_dev_settings(const DAQPSettings* s) {
+    DAQPSettings d;
+    if (!s) { daqp_default_settings(&d); s = &d; }
+    DevSettings<T> o;
+    o.primal_tol = (T)s->primal_tol; o.dual_tol = (T)s->dual_tol; o.zero_tol = (T)s->zero_tol;
+    o.pivot_tol = (T)s->pivot_tol; o.progress_tol = (T)s->progress_tol; o.fval_bound = (T)s->fval_bound;
+    o.rho_soft = (T)s->rho_soft; o.sing_tol = (T)s->sing_tol; o.refactor_tol = (T)s->refactor_tol;
+    o.eps_prox = (T)s->eps_prox; o.cycle_tol = s->cycle_tol; o.iter_limit = s->iter_limit;
+    return o;
+}
+
+extern "C" int daqp_b200_create(DAQPB200Handle** out, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = "daqp_b200: no CUDA device available (this library has no CPU path)";
+        return -1;
+    }
+    if (device < 0) CK(cudaGetDevice(&device));
+    CK(cudaSetDevice(device));
+    DAQPB200Handle* h = new DAQPB200Handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    const char* lim = getenv("DAQP_B200_SCRATCH_GB");
+    if (lim) h->scratch_limit = (long long)(atof(lim) * (double)(1ll << 30));
+    *out = h;
+    return 0;
+}
+
+extern "C" void daqp_b200_destroy(DAQPB200Handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& t : h->pending) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+    for (auto& t : h->free_events) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+    if (h->arena) cudaFree(h->arena);
+    if (h->stage) cudaFree(h->stage);
+    cudaStreamDestroy(h->compute); cudaStreamDestroy(h->copy_in); cudaStreamDestroy(h->copy_out);
+    delete h;
+}
+
+extern "C" void daqp_b200_set_scratch_limit(DAQPB200Handle* h, long long bytes) { if (h) h->scratch_limit = bytes; }
+
+static std::mutex g_default_mu;
+static std::map<int, DAQPB200Handle*> g_default;
+static int default_handle(DAQPB200Handle** out) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        g_last_error = "daqp_b200: no CUDA device available (this library has no CPU path)";
+        return -1;
+    }
+    auto it = g_default.find(dev);
+    if (it == g_default.end()) {
+        DAQPB200Handle* h = nullptr;
+        int rc = daqp_b200_create(&h, dev);
+        if (rc) return rc;
+        g_default[dev] = h;
+        *out = h;
+    } else *out = it->second;
+    return 0;
+}
+
+static int drain_events(DAQPB200Handle* h) {
+    for (auto& t : h->pending) {
+        CK(cudaEventSynchronize(t.e2));
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, t.e0, t.e1));
+        CK(cudaEventElapsedTime(&b, t.e1, t.e2));
+        h->stats.setup_ms += a;
+        h->stats.solve_ms += b;
+        h->free_events.push_back(t);
+    }
+    h->pending.clear();
+    return 0;
+}
+
+extern "C" int daqp_b200_get_stats(DAQPB200Handle* h, DAQPB200Stats* out, int reset) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    h->stats.scratch_bytes = (long long)h->arena_bytes;
+    if (out) *out = h->stats;
+    if (reset) { int w = h->stats.warps_per_sm; h->stats = DAQPB200Stats{}; h->stats.warps_per_sm = w; }
+    return 0;
+}
+
+static int get_events(DAQPB200Handle* h, EventTriple* t) {
+    if (!h->free_events.empty()) { *t = h->free_events.back(); h->free_events.pop_back(); return 0; }
+    if (h->pending.size() > 4096) { int rc = drain_events(h); if (rc) return rc; return get_events(h, t); }
+    CK(cudaEventCreate(&t->e0)); CK(cudaEventCreate(&t->e1)); CK(cudaEventCreate(&t->e2));
+    return 0;
+}
+
+static int ensure(char** buf, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    if (*buf) { CK(cudaDeviceSynchronize()); CK(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+    CK(cudaMalloc((void**)buf, need));
+    *have = need;
+    return 0;
+}
+
+struct Carver {
+    char* p; size_t off = 0;
+    explicit Carver(char* base) : p(base) {}
+    template <typename U> U* take(size_t count) {
+        off = (off + 255) / 256 * 256;
+        U* r = reinterpret_cast<U*>(p + off);
+        off += count * sizeof(U);
+        return r;
+    }
+};
+
+template <typename T>
+static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
+    size_t e = (size_t)n * ldm + (size_t)m * ldn + 3 * (size_t)ldm + (size_t)n * (n + 1) / 2 + n;
+    return e * sizeof(T) + ldm + sizeof(int) + 64; // + sense bytes + setup flag + alignment slack
+}
+
+template <typename T, int NG>
+static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ldp_solve_kernel<T, NG><<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+template <typename T, int NGS>
+static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(qp_setup_kernel<T, NGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    qp_setup_kernel<T, NGS><<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// Device-resident batch: the core of every entry point.
+template <typename T>
+static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, const T* dH, const T* df, const T* dA,
+                             const T* dbu, const T* dbl, const int* dsense, const DAQPSettings* settings, T* dx,
+                             T* dlam, T* dfval, int* dflag, int* diter, const DAQPB200Diag* diag, cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
+    constexpr int V = VecOf<T>::N;
+    const int ldm = round_up(std::max(m, 1), 4), ldn = round_up(n, V), cap = n + 1, mA = m - ms;
+    const int ng = (ldn + 32 * V - 1) / (32 * V), ngs = (n + 31) / 32;
+    if (ng > 4 || ngs > 8) { g_last_error = "daqp_b200: n > 256 is not supported"; return -2; }
+
+    const size_t smem_solve_w = ldp_smem_per_warp<T>(n, m, cap), smem_setup_w = setup_smem_per_warp<T>(n);
+    const size_t budget = h->smem_optin;
+    int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
+    if (w_solve < 1 || w_setup < 1) { g_last_error = "daqp_b200: problem too large for shared memory"; return -2; }
+    if (const char* wenv = getenv("DAQP_B200_WARPS")) w_solve = std::max(1, std::min(w_solve, atoi(wenv))); // tuning knob
+    h->stats.warps_per_sm = w_solve;
+
+    const size_t per = scratch_per_problem<T>(n, m, ldm, ldn);
+    int chunk = (int)std::min<long long>(N, std::max<long long>(1, (h->scratch_limit - (8 << 20)) / (long long)per));
+    const int grid_max = h->num_sms;
+    const size_t pst = (size_t)grid_max * 16 * cap * (sizeof(int) + sizeof(T)) + 4096;
+    int rc = ensure(&h->arena, &h->arena_bytes, (size_t)chunk * per + pst + (1 << 20));
+    if (rc) return rc;
+
+    const DevSettings<T> st = to_dev_settings<T>(settings);
+    for (int p0 = 0; p0 < N; p0 += chunk) {
+        const int P = std::min(chunk, N - p0);
+        Carver cv(h->arena);
+        int* counters = cv.take<int>(64);
+        T* Mt = cv.take<T>((size_t)P * n * ldm);
+        T* Mr = cv.take<T>((size_t)P * m * ldn);
+        T* du = cv.take<T>((size_t)P * ldm);
+        T* dl = cv.take<T>((size_t)P * ldm);
+        T* sc = cv.take<T>((size_t)P * ldm);
+        T* Ri = cv.take<T>((size_t)P * n * (n + 1) / 2);
+        T* vv = cv.take<T>((size_t)P * n);
+        unsigned char* sense8 = cv.take<unsigned char>((size_t)P * ldm);
+        int* sflag = cv.take<int>(P);
+        int* pst_id = cv.take<int>((size_t)grid_max * 16 * cap);
+        T* pst_lam = cv.take<T>((size_t)grid_max * 16 * cap);
+
+        EventTriple ev;
+        rc = get_events(h, &ev);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
+        CK(cudaEventRecord(ev.e0, stream));
+
+        SetupArgs<T> sa;
+        sa.P = P; sa.n = n; sa.m = m; sa.ms = ms; sa.ldm = ldm; sa.ldn = ldn;
+        sa.H = dH + (size_t)p0 * n * n; sa.f = df ? df + (size_t)p0 * n : nullptr; sa.A = dA + (size_t)p0 * mA * n;
+        sa.bupper = dbu + (size_t)p0 * m; sa.blower = dbl + (size_t)p0 * m;
+        sa.sense_in = dsense ? dsense + (size_t)p0 * m : nullptr;
+        sa.Mt = Mt; sa.Mr = Mr; sa.dupper = du; sa.dlower = dl; sa.scaling = sc; sa.Rinv = Ri; sa.v = vv;
+        sa.sense = sense8; sa.setup_flag = sflag;
+        sa.x = dx + (size_t)p0 * n; sa.lam = dlam ? dlam + (size_t)p0 * m : nullptr; sa.fval = dfval + p0;
+        sa.exitflag = dflag + p0; sa.iter = diter + p0;
+        sa.work_counter = counters; sa.st = st;
+        {
+            const int grid = std::min(grid_max, (P + w_setup - 1) / w_setup);
+            const size_t smem = smem_setup_w * w_setup;
+            cudaError_t e = cudaErrorInvalidValue;
+            switch (ngs) {
+                case 1: e = launch_setup<T, 1>(sa, grid, 32 * w_setup, smem, stream); break;
+                case 2: e = launch_setup<T, 2>(sa, grid, 32 * w_setup, smem, stream); break;
+                case 3: e = launch_setup<T, 3>(sa, grid, 32 * w_setup, smem, stream); break;
+                case 4: e = launch_setup<T, 4>(sa, grid, 32 * w_setup, smem, stream); break;
+                default: e = launch_setup<T, 8>(sa, grid, 32 * w_setup, smem, stream); break;
+            }
+            if (e != cudaSuccess) return fail("qp_setup_kernel launch", e, __LINE__);
+            h->stats.setup_launches++;
+        }
+        CK(cudaEventRecord(ev.e1, stream));
+
+        LdpArgs<T> la;
+        la.P = P; la.n = n; la.m = m; la.ms = ms; la.ldm = ldm; la.ldn = ldn; la.cap = cap;
+        la.Mt = Mt; la.Mr = Mr; la.dupper = du; la.dlower = dl; la.scaling = sc; la.Rinv = Ri;
+        la.v = df ? vv : nullptr; la.sense = sense8; la.setup_flag = sflag;
+        la.x = sa.x; la.lam = sa.lam; la.fval = sa.fval; la.exitflag = sa.exitflag; la.iter = sa.iter;
+        la.ws_out = (diag && diag->ws) ? diag->ws + (size_t)p0 * cap : nullptr;
+        la.nact_out = (diag && diag->n_active) ? diag->n_active + p0 : nullptr;
+        la.counts_out = (diag && diag->counts) ? diag->counts + 4 * (size_t)p0 : nullptr;
+        la.sense_out = (diag && diag->sense) ? diag->sense + (size_t)p0 * ldm : nullptr;
+        la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
+        {
+            const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
+            const size_t smem = smem_solve_w * w_solve;
+            cudaError_t e = cudaErrorInvalidValue;
+            switch (ng) {
+                case 1: e = launch_solve<T, 1>(la, grid, 32 * w_solve, smem, stream); break;
+                case 2: e = launch_solve<T, 2>(la, grid, 32 * w_solve, smem, stream); break;
+                case 3: e = launch_solve<T, 3>(la, grid, 32 * w_solve, smem, stream); break;
+                default: e = launch_solve<T, 4>(la, grid, 32 * w_solve, smem, stream); break;
+            }
+            if (e != cudaSuccess) return fail("ldp_solve_kernel launch", e, __LINE__);
+            h->stats.solve_launches++;
+        }
+        CK(cudaEventRecord(ev.e2, stream));
+        h->pending.push_back(ev);
+    }
+    return 0;
+}
+
+extern "C" int daqp_b200_solve_device(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* dH,
+                                      const c_float* df, const c_float* dA, const c_float* dbupper,
+                                      const c_float* dblower, const int* dsense, const DAQPSettings* settings,
+                                      c_float* dx, c_float* dlam, c_float* dfval, int* dexitflag, int* diter,
+                                      const DAQPB200Diag* diag, void* stream) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->compute;
+    return solve_device_impl<double>(h, N, n, m, ms, dH, df, dA, dbupper, dblower, dsense, settings, dx, dlam, dfval,
+                                     dexitflag, diter, diag, s);
+}
+
+// Host arrays: chunks are copied in on one stream while the previous chunk is solved on another and the one before
+// that is copied out on a third (double-buffered device staging).
+extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* H,
+                                      const c_float* f, const c_float* A, const c_float* bupper, const c_float* blower,
+                                      const int* sense, const DAQPSettings* settings, c_float* x, c_float* lam,
+                                      c_float* fval, int* exitflag, int* iter, const DAQPB200Diag* diag) {
+    typedef c_float T;
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (N <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
+    const int mA = m - ms, cap = n + 1, ldm = round_up(std::max(m, 1), 4);
+    int chunk = 16384;
+    if (const char* c = getenv("DAQP_B200_HOST_CHUNK")) chunk = std::max(1, atoi(c));
+    chunk = std::min(chunk, N);
+    const size_t in_b = ((size_t)n * n + n + (size_t)mA * n + 2 * (size_t)m) * sizeof(T) + (size_t)m * sizeof(int);
+    const size_t out_b = ((size_t)n + m + 1) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
+    const size_t per_buf = (size_t)chunk * (in_b + out_b) + 16 * 256;
+    int rc = ensure(&h->stage, &h->stage_bytes, 2 * per_buf);
+    if (rc) return rc;
+
+    struct Buf { T *H, *f, *A, *bu, *bl; int* sense; T *x, *lam, *fval; int *flag, *iter, *nact, *ws, *counts; unsigned char* so; };
+    Buf b[2];
+    for (int i = 0; i < 2; i++) {
+        Carver cv(h->stage + i * per_buf);
+        b[i].H = cv.take<T>((size_t)chunk * n * n); b[i].f = cv.take<T>((size_t)chunk * n);
+        b[i].A = cv.take<T>((size_t)chunk * mA * n); b[i].bu = cv.take<T>((size_t)chunk * m);
+        b[i].bl = cv.take<T>((size_t)chunk * m); b[i].sense = cv.take<int>((size_t)chunk * m);
+        b[i].x = cv.take<T>((size_t)chunk * n); b[i].lam = cv.take<T>((size_t)chunk * m);
+        b[i].fval = cv.take<T>(chunk); b[i].flag = cv.take<int>(chunk); b[i].iter = cv.take<int>(chunk);
+        b[i].nact = cv.take<int>(chunk); b[i].ws = cv.take<int>((size_t)chunk * cap);
+        b[i].counts = cv.take<int>((size_t)chunk * 4); b[i].so = cv.take<unsigned char>((size_t)chunk * ldm);
+    }
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    int result = 0, c = 0;
+    for (int p0 = 0; p0 < N && result == 0; p0 += chunk, c++) {
+        const int P = std::min(chunk, N - p0), s = c & 1;
+        Buf& B = b[s];
+        // input buffers are free once the solve that read them (two chunks ago) has finished
+        if (c >= 2) CK(cudaStreamWaitEvent(h->copy_in, ev_done[s], 0));
+        CK(cudaMemcpyAsync(B.H, H + (size_t)p0 * n * n, (size_t)P * n * n * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+        if (f) CK(cudaMemcpyAsync(B.f, f + (size_t)p0 * n, (size_t)P * n * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+        if (mA > 0) CK(cudaMemcpyAsync(B.A, A + (size_t)p0 * mA * n, (size_t)P * mA * n * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+        if (m > 0) {
+            CK(cudaMemcpyAsync(B.bu, bupper + (size_t)p0 * m, (size_t)P * m * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+            CK(cudaMemcpyAsync(B.bl, blower + (size_t)p0 * m, (size_t)P * m * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
+            if (sense) CK(cudaMemcpyAsync(B.sense, sense + (size_t)p0 * m, (size_t)P * m * sizeof(int), cudaMemcpyHostToDevice, h->copy_in));
+        }
+        CK(cudaEventRecord(ev_in[s], h->copy_in));
+        CK(cudaStreamWaitEvent(h->compute, ev_in[s], 0));
+        if (c >= 2) CK(cudaStreamWaitEvent(h->compute, ev_out[s], 0)); // output buffers drained
+        DAQPB200Diag dd{};
+        if (diag) { dd.n_active = diag->n_active ? B.nact : nullptr; dd.ws = diag->ws ? B.ws : nullptr;
+                    dd.counts = diag->counts ? B.counts : nullptr; dd.sense = diag->sense ? B.so : nullptr; }
+        result = solve_device_impl<T>(h, P, n, m, ms, B.H, f ? B.f : nullptr, B.A, B.bu, B.bl, sense ? B.sense : nullptr,
+                                      settings, B.x, lam ? B.lam : nullptr, B.fval, B.flag, B.iter, diag ? &dd : nullptr,
+                                      h->compute);
+        if (result) break;
+        CK(cudaEventRecord(ev_done[s], h->compute));
+        CK(cudaStreamWaitEvent(h->copy_out, ev_done[s], 0));
+        CK(cudaMemcpyAsync(x + (size_t)p0 * n, B.x, (size_t)P * n * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
+        if (lam && m > 0) CK(cudaMemcpyAsync(lam + (size_t)p0 * m, B.lam, (size_t)P * m * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
+        if (fval) CK(cudaMemcpyAsync(fval + p0, B.fval, (size_t)P * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
+        CK(cudaMemcpyAsync(exitflag + p0, B.flag, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
+        if (iter) CK(cudaMemcpyAsync(iter + p0, B.iter, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
+        if (diag) {
+            if (diag->n_active) CK(cudaMemcpyAsync(diag->n_active + p0, B.nact, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
+            if (diag->ws) CK(cudaMemcpyAsync(diag->ws + (size_t)p0 * cap, B.ws, (size_t)P * cap * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
+            if (diag->counts) CK(cudaMemcpyAsync(diag->counts + (size_t)p0 * 4, B.counts, (size_t)P * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
+            if (diag->sense) CK(cudaMemcpyAsync(diag->sense + (size_t)p0 * ldm, B.so, (size_t)P * ldm, cudaMemcpyDeviceToHost, h->copy_out));
+        }
+        CK(cudaEventRecord(ev_out[s], h->copy_out));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->copy_in), e2 = cudaStreamSynchronize(h->compute), e3 = cudaStreamSynchronize(h->copy_out);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
+    if (result) return result;
+    if (e1 != cudaSuccess) return fail("copy_in stream", e1, __LINE__);
+    if (e2 != cudaSuccess) return fail("compute stream", e2, __LINE__);
+    if (e3 != cudaSuccess) return fail("copy_out stream", e3, __LINE__);
+    return 0;
+}
+
+// Array-of-struct batch: group by shape, pack, solve, scatter (identical in effect to N daqp_quadprog calls).
+extern "C" int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQPSettings* settings) {
+    if (N <= 0) return 0;
+    std::map<std::tuple<int, int, int, bool, bool>, std::vector<int>> groups;
+    for (int i = 0; i < N; i++) {
+        const DAQPProblem& q = qps[i];
+        res[i].nodes = 1; res[i].soft_slack = 0; res[i].solve_time = 0; res[i].setup_time = 0;
+        const bool bad = q.H == nullptr || q.nh > 1 || q.problem_type != 0 || q.n < 1 || q.m < q.ms || q.ms > q.n ||
+                         (q.m > q.ms && q.A == nullptr) || (q.m > 0 && (q.bupper == nullptr || q.blower == nullptr));
+        if (bad) { res[i].exitflag = DAQP_EXIT_UNSUPPORTED; res[i].iter = 0; continue; }
+        groups[std::make_tuple(q.n, q.m, q.ms, q.f != nullptr, q.sense != nullptr)].push_back(i);
+    }
+    DAQPB200Handle* h = nullptr;
+    int rc = default_handle(&h);
+    if (rc) return rc;
+    for (auto& kv : groups) {
+        const int n = std::get<0>(kv.first), m = std::get<1>(kv.first), ms = std::get<2>(kv.first), mA = m - ms;
+        const bool has_f = std::get<3>(kv.first), has_s = std::get<4>(kv.first);
+        const std::vector<int>& ids = kv.second;
+        const size_t G = ids.size();
+        std::vector<c_float> H(G * n * n), f(has_f ? G * n : 0), A(G * mA * n), bu(G * m), bl(G * m), x(G * n), lam(G * m), fv(G);
+        std::vector<int> se(has_s ? G * m : 0), flag(G), it(G);
+        for (size_t g = 0; g < G; g++) {
+            const DAQPProblem& q = qps[ids[g]];
+            memcpy(&H[g * n * n], q.H, sizeof(c_float) * n * n);
+            if (has_f) memcpy(&f[g * n], q.f, sizeof(c_float) * n);
+            if (mA > 0) memcpy(&A[g * mA * n], q.A, sizeof(c_float) * mA * n);
+            if (m > 0) { memcpy(&bu[g * m], q.bupper, sizeof(c_float) * m); memcpy(&bl[g * m], q.blower, sizeof(c_float) * m); }
+            if (has_s) memcpy(&se[g * m], q.sense, sizeof(int) * m);
+            fv[g] = res[ids[g]].fval; // reference leaves fval untouched when there is no linear term
+        }
+        DAQPB200Stats before{}, after{};
+        daqp_b200_get_stats(h, &before, 0);
+        rc = daqp_b200_solve_packed(h, (int)G, n, m, ms, H.data(), has_f ? f.data() : nullptr, A.data(), bu.data(),
+                                    bl.data(), has_s ? se.data() : nullptr, settings, x.data(), lam.data(), fv.data(),
+                                    flag.data(), it.data(), nullptr);
+        if (rc) return rc;
+        daqp_b200_get_stats(h, &after, 0);
+        for (size_t g = 0; g < G; g++) {
+            DAQPResult& r = res[ids[g]];
+            r.exitflag = flag[g];
+            r.setup_time = 1e-3 * (after.setup_ms - before.setup_ms);
+            r.solve_time = 1e-3 * (after.solve_ms - before.solve_ms);
+            // setup failures leave x untouched (api.c:69-72): exit flags -1/-5/-6/-8 raised before the solve
+            const bool solved = it[g] > 0;
+            r.iter = it[g];
+            if (!solved) continue;
+            memcpy(r.x, &x[g * n], sizeof(c_float) * n);
+            if (r.lam && m > 0) memcpy(r.lam, &lam[g * m], sizeof(c_float) * m);
+            if (has_f) r.fval = fv[g];
+        }
+    }
+    return 0;
+}
+
+extern "C" void daqp_quadprog(DAQPResult* res, DAQPProblem* qp, DAQPSettings* settings) {
+    int rc = daqp_quadprog_batch(1, qp, res, settings);
+    if (rc) {
+        fprintf(stderr, "%s\n", g_last_error.c_str());
+        res->exitflag = DAQP_EXIT_UNSUPPORTED;
+    }
+}

@@ -1,0 +1,358 @@
+// daqp_b200/csrc/setup_kernel.cuh -- batched QP -> LDP transform, one warp per problem.
+//
+// Covers SURVEY.md §8(a) rows a17..a19 exactly as daqp_quadprog() drives them (reference src/utils.c:58-221 with
+// mask = Rinv|M|v|d|sense|unconstrained, src/api.c:62-79,163-209):
+//   check_bounds (utils.c:546-567) -> symmetrise + Cholesky + triangular inverse (utils.c:223-391)
+//   -> v = R^-T f (utils.c:474-497) -> unconstrained-optimum shortcut (utils.c:618-687)
+//   -> M = A R^-1, row normalisation (utils.c:434-472,586-613) -> normalise simple-bound rows (utils.c:569-585)
+//   -> d (utils.c:151-158 after the shortcut, utils.c:499-544 otherwise).
+// Output is the device-side LDP the solve kernel consumes: the constraint matrix in BOTH layouts (column-major
+// Mt for the streaming scan, row-major Mr for active-row passes), bounds, scaling, packed R^-1, v, sense bytes.
+#pragma once
+#include "common.cuh"
+
+namespace dq {
+
+template <typename T>
+struct SetupArgs {
+    int P, n, m, ms, ldm, ldn;
+    const T *H, *f, *A, *bupper, *blower; // packed inputs; f may be nullptr
+    const int* sense_in;                  // [P][m] or nullptr
+    T *Mt, *Mr, *dupper, *dlower, *scaling, *Rinv, *v;
+    unsigned char* sense;                 // [P][ldm]
+    int* setup_flag;                      // [P]
+    T *x, *lam, *fval;                    // final outputs (written here only for problems finished by the setup)
+    int *exitflag, *iter;
+    int* work_counter;
+    DevSettings<T> st;
+};
+
+constexpr int SETUP_RB = 4; // rows of A processed together (one 32-byte sector of Mt per lane and column)
+
+template <typename T>
+__host__ __device__ inline size_t setup_smem_per_warp(int n) {
+    size_t e = (size_t)n * (n + 1) / 2 + (size_t)n * (2 + SETUP_RB);
+    return (e * sizeof(T) + 15) / 16 * 16;
+}
+
+template <typename T, int NGS>
+__global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = a.n, m = a.m, ms = a.ms, mA = a.m - a.ms, ldm = a.ldm, ldn = a.ldn;
+    const int ntri = n * (n + 1) / 2;
+    T* R = reinterpret_cast<T*>(smem_raw + setup_smem_per_warp<T>(n) * wib);
+    T* vv = R + ntri;          // f, then v = R^-T f
+    T* xu = vv + n;            // unconstrained optimum
+    T* arow = xu + n;          // SETUP_RB staged rows of A
+    const DevSettings<T>& st = a.st;
+
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(a.work_counter, 1);
+        p = __shfl_sync(FULL, p, 0);
+        if (p >= a.P) break;
+
+        const T* H = a.H + (size_t)p * n * n;
+        const T* f = a.f ? a.f + (size_t)p * n : nullptr;
+        const T* A = a.A + (size_t)p * mA * n;
+        const T* bu = a.bupper + (size_t)p * m;
+        const T* bl = a.blower + (size_t)p * m;
+        const int* sin = a.sense_in ? a.sense_in + (size_t)p * m : nullptr;
+        T* Mt = a.Mt + (size_t)p * n * ldm;
+        T* Mr = a.Mr + (size_t)p * m * ldn;
+        T* du = a.dupper + (size_t)p * ldm;
+        T* dl = a.dlower + (size_t)p * ldm;
+        T* sc = a.scaling + (size_t)p * ldm;
+        unsigned char* so = a.sense + (size_t)p * ldm;
+        T* Rg = a.Rinv + (size_t)p * ntri;
+        int flag = SETUP_SOLVE;
+
+        // ---- sense copy + check_bounds (utils.c:84-98, 546-567)
+        int any_fixed = 0, bad = 0, unsupported = 0;
+        for (int i = lane; i < ldm; i += 32) {
+            int s = 0;
+            if (i < m) {
+                s = sin ? sin[i] : 0;
+                if (s & (B_SOFT | B_BINARY) || (s & ~63)) unsupported = 1;
+                if (!(s & B_IMMUTABLE)) {
+                    const T diff = bu[i] - bl[i];
+                    if (diff < -st.primal_tol) bad = 1;
+                    else if (diff < st.zero_tol) s |= B_ACTIVE + B_IMMUTABLE;
+                }
+                if (s & (B_ACTIVE + B_IMMUTABLE)) any_fixed = 1;
+            }
+            so[i] = (unsigned char)s;
+        }
+        any_fixed = __any_sync(FULL, any_fixed);
+        if (__any_sync(FULL, unsupported)) flag = EXIT_UNSUPPORTED;
+        else if (__any_sync(FULL, bad)) flag = EXIT_INFEASIBLE;
+
+        // ---- Hessian factor (utils.c:223-391)
+        bool is_diag = true;
+        T hscale = 0;
+        if (flag >= 0) {
+            if (st.eps_prox > 0) flag = EXIT_UNSUPPORTED; // forced proximal mode is a different driver
+            int nd = 0;
+            for (int idx = lane; idx < n * n; idx += 32) {
+                const int i = idx / n, j = idx - i * n;
+                const T h = H[idx];
+                if (j > i && (h > st.zero_tol || h < -st.zero_tol)) nd = 1;
+                if (j == i) hscale = fmax(hscale, fabs(h));
+                if (j >= i) R[roff(i, n) + j] = (j == i) ? h : (T)0.5 * (h + H[(size_t)j * n + i]);
+            }
+            is_diag = !__any_sync(FULL, nd);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hscale = fmax(hscale, __shfl_xor_sync(FULL, hscale, o));
+            __syncwarp();
+        }
+        if (flag >= 0 && is_diag) { // utils.c:284-312
+            const T factor_tol = hscale > 0 ? st.zero_tol * hscale : st.zero_tol;
+            int prox = 0, nonconvex = 0;
+            for (int i = lane; i < n; i += 32) {
+                T Hi = R[roff(i, n) + i];
+                if (Hi <= factor_tol) {
+                    prox = 1;
+                    T eps = st.eps_prox < 0 ? -st.eps_prox : st.eps_prox;
+                    const T fl = sqrt(st.zero_tol) * hscale;
+                    if (eps > 0 && eps < fl) eps = fl;
+                    Hi += eps;
+                }
+                if (Hi <= st.zero_tol) nonconvex = 1;
+                Hi = sqrt(Hi);
+                T* Ri = R + roff(i, n);
+                for (int j = i + 1; j < n; j++) Ri[j] = 0;
+                Ri[i] = 1 / Hi;
+            }
+            if (__any_sync(FULL, nonconvex)) flag = EXIT_NONCONVEX;
+            else if (__any_sync(FULL, prox)) flag = EXIT_UNSUPPORTED; // reference hands over to daqp_prox
+            __syncwarp();
+        } else if (flag >= 0) {
+            // upper Cholesky by rows, 1/r_ii kept on the diagonal (utils.c:337-352)
+            T min_piv = (T)1e30, max_piv = 0;
+            bool singular = false;
+            for (int i = 0; i < n; i++) {
+                T* Ri = R + roff(i, n);
+                T part = 0;
+                for (int kk = lane; kk < i; kk += 32) { const T t = R[roff(kk, n) + i]; part += t * t; }
+                T di = Ri[i] - warp_sum(part);
+                if (di <= st.zero_tol) { singular = true; break; }
+                min_piv = fmin(min_piv, di);
+                max_piv = fmax(max_piv, di);
+                di = rsqrt_exact<T>(di);
+                for (int j = i + 1 + lane; j < n; j += 32) {
+                    T s = Ri[j];
+                    for (int kk = 0; kk < i; kk++) { const T* Rk = R + roff(kk, n); s -= Rk[i] * Rk[j]; }
+                    Ri[j] = s * di;
+                }
+                if (lane == 0) Ri[i] = di;
+                __syncwarp();
+            }
+            if (singular || min_piv <= st.zero_tol * max_piv) { // utils.c:356-377: shift + proximal driver
+                T eps = st.eps_prox < 0 ? -st.eps_prox : st.eps_prox;
+                flag = (eps <= 0) ? EXIT_NONCONVEX : EXIT_UNSUPPORTED;
+            } else {
+                // R -> R^-1 in place (utils.c:380-389). Row k of the inverse needs only row k and the ORIGINAL rows
+                // i > k, so all rows advance in lock-step over i: at step i rows k < i consume row i, then row i
+                // starts its own inversion (and is never read again).
+                for (int i = 0; i < n; i++) {
+                    const T* Ri = R + roff(i, n);
+                    const T rii = Ri[i];
+                    for (int k0 = lane; k0 < i; k0 += 32) {
+                        T* Rk = R + roff(k0, n);
+                        const T t = Rk[i] * rii;
+                        Rk[i] = t;
+                        for (int j = i + 1; j < n; j++) Rk[j] -= Ri[j] * t;
+                    }
+                    __syncwarp();
+                    for (int j = i + 1 + lane; j < n; j += 32) R[roff(i, n) + j] *= -rii;
+                    __syncwarp();
+                }
+            }
+        }
+
+        if (flag < 0) { // setup failure: exit flag only, x untouched (api.c:69-72)
+            if (lane == 0) { a.setup_flag[p] = flag; a.exitflag[p] = flag; a.iter[p] = 0; }
+            __syncwarp();
+            continue;
+        }
+
+        // ---- v = R^-T f (utils.c:474-497); zeros when f == NULL
+        for (int i = lane; i < n; i += 32) {
+            T s = 0;
+            if (f) {
+                s = R[roff(i, n) + i] * f[i];
+                for (int j = i - 1; j >= 0; j--) s += R[roff(j, n) + i] * f[j];
+            }
+            vv[i] = s;
+        }
+        __syncwarp();
+        T vnorm = 0;
+        for (int i = lane; i < n; i += 32) vnorm += vv[i] * vv[i];
+        vnorm = warp_sum(vnorm);
+        if (a.v) for (int i = lane; i < n; i += 32) a.v[(size_t)p * n + i] = vv[i];
+
+        // ---- unconstrained optimum x = -R^-1 v (utils.c:633-660), only when nothing is pre-activated/immutable
+        const bool unc = !any_fixed;
+        int infeasible_pt = 0;
+        if (unc) {
+            for (int i = lane; i < n; i += 32) {
+                const T* Ri = R + roff(i, n);
+                T s = 0;
+                for (int j = i; j < n; j++) s += Ri[j] * vv[j];
+                xu[i] = -s;
+            }
+            __syncwarp();
+        }
+
+        // ---- general rows: M = A R^-1, normalise, d (utils.c:434-472, 586-613, 663-678 / 499-544)
+        int zero_row_infeasible = 0;
+        for (int r0 = 0; r0 < mA; r0 += SETUP_RB) {
+            const int nr = min(SETUP_RB, mA - r0);
+            for (int idx = lane; idx < SETUP_RB * n; idx += 32) {
+                const int b = idx / n;
+                arow[idx] = (b < nr) ? A[(size_t)(r0 + b) * n + (idx - b * n)] : (T)0;
+            }
+            __syncwarp();
+            T acc[SETUP_RB][NGS];
+#pragma unroll
+            for (int b = 0; b < SETUP_RB; b++)
+#pragma unroll
+                for (int g = 0; g < NGS; g++) acc[b][g] = 0;
+            // M[r][c] = sum_{i<=c} A[r][i] Rinv[i][c], accumulated from i = c down to 0 as the reference does
+            for (int i = n - 1; i >= 0; i--) {
+                const T* Ri = R + roff(i, n);
+                T ai[SETUP_RB];
+#pragma unroll
+                for (int b = 0; b < SETUP_RB; b++) ai[b] = arow[b * n + i];
+#pragma unroll
+                for (int g = 0; g < NGS; g++) {
+                    const int c = lane + 32 * g;
+                    if (c >= i && c < n) {
+                        const T rv = Ri[c];
+#pragma unroll
+                        for (int b = 0; b < SETUP_RB; b++) acc[b][g] += rv * ai[b];
+                    }
+                }
+            }
+            T scal[SETUP_RB];
+#pragma unroll
+            for (int b = 0; b < SETUP_RB; b++) {
+                T nrm = 0, dotd = 0;
+#pragma unroll
+                for (int g = 0; g < NGS; g++) nrm += acc[b][g] * acc[b][g];
+                nrm = warp_sum(nrm);
+                const int row = ms + r0 + b; // constraint index
+                int sb = (b < nr) ? so[row] : 0;
+                T s = 1;
+                if (b < nr) {
+                    if (nrm < st.zero_tol) { // utils.c:595-606
+                        if ((bu[row] < -st.zero_tol || bl[row] > st.zero_tol) && !(sb & B_IMMUTABLE))
+                            zero_row_infeasible = 1;
+                        sb = B_IMMUTABLE;
+                    } else {
+                        s = rsqrt_exact<T>(nrm);
+#pragma unroll
+                        for (int g = 0; g < NGS; g++) acc[b][g] *= s;
+                    }
+                }
+                scal[b] = s;
+#pragma unroll
+                for (int g = 0; g < NGS; g++) {
+                    const int c = lane + 32 * g;
+                    if (c < n) dotd += unc ? arow[b * n + c] * xu[c] : acc[b][g] * vv[c];
+                }
+                dotd = warp_sum(dotd);
+                if (b < nr && lane == 0) {
+                    T u_ = bu[row], l_ = bl[row];
+                    if (unc) {
+                        u_ -= dotd; l_ -= dotd;
+                        if (u_ < -st.primal_tol || l_ > st.primal_tol) infeasible_pt = 1;
+                        u_ *= s; l_ *= s;
+                    } else {
+                        u_ = u_ * s + dotd; l_ = l_ * s + dotd;
+                    }
+                    du[row] = u_; dl[row] = l_; sc[row] = s; so[row] = (unsigned char)sb;
+                }
+            }
+            // row-major copy (coalesced), column-major copy (one 32-byte sector per lane and column)
+#pragma unroll
+            for (int g = 0; g < NGS; g++) {
+                const int c = lane + 32 * g;
+                if (c < ldn) {
+#pragma unroll
+                    for (int b = 0; b < SETUP_RB; b++)
+                        if (b < nr) Mr[(size_t)(ms + r0 + b) * ldn + c] = (c < n) ? acc[b][g] : (T)0;
+                }
+                if (c < n) {
+                    T* dst = Mt + (size_t)c * ldm + ms + r0;
+#pragma unroll
+                    for (int b = 0; b < SETUP_RB; b++)
+                        if (ms + r0 + b < ldm) dst[b] = (b < nr) ? acc[b][g] : (T)0;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- simple bounds: rows 0..ms-1 of R^-1, normalised (utils.c:569-585); identity rows for diagonal H
+        for (int i = 0; i < ms; i++) {
+            T* Ri = R + roff(i, n);
+            T s;
+            if (is_diag) { // utils.c:308-309: scaling = sqrt(H_ii), row = e_i
+                s = sqrt(H[(size_t)i * n + i]);
+                __syncwarp();
+                if (lane == 0) Ri[i] = 1;
+            } else {
+                T part = 0;
+                for (int j = i + lane; j < n; j += 32) part += Ri[j] * Ri[j];
+                s = rsqrt_exact<T>(warp_sum(part));
+                for (int j = i + lane; j < n; j += 32) Ri[j] *= s;
+            }
+            __syncwarp();
+            T dotd = 0;
+            if (!unc) { for (int j = i + lane; j < n; j += 32) dotd += Ri[j] * vv[j]; dotd = warp_sum(dotd); }
+            for (int c = lane; c < ldn; c += 32) {
+                const T val = (c >= i && c < n) ? Ri[c] : (T)0;
+                Mr[(size_t)i * ldn + c] = val;
+                if (c < n) Mt[(size_t)c * ldm + i] = val;
+            }
+            if (lane == 0) {
+                T u_ = bu[i], l_ = bl[i];
+                if (unc) {
+                    u_ -= xu[i]; l_ -= xu[i];
+                    if (u_ < -st.primal_tol || l_ > st.primal_tol) infeasible_pt = 1;
+                    u_ *= s; l_ *= s;
+                } else {
+                    u_ = u_ * s + dotd; l_ = l_ * s + dotd;
+                }
+                du[i] = u_; dl[i] = l_; sc[i] = s;
+            }
+        }
+        // pad rows m..ldm-1 of the column-major copy and of the per-row vectors
+        for (int c = lane; c < n; c += 32)
+            for (int r = m; r < ldm; r++) Mt[(size_t)c * ldm + r] = 0;
+        for (int r = m + lane; r < ldm; r += 32) { du[r] = 0; dl[r] = 0; sc[r] = 1; }
+        __syncwarp();
+        for (int idx = lane; idx < ntri; idx += 32) Rg[idx] = R[idx];
+
+        infeasible_pt = __shfl_sync(FULL, infeasible_pt, 0);
+        zero_row_infeasible = __shfl_sync(FULL, zero_row_infeasible, 0);
+        if (unc && !infeasible_pt) { // utils.c:679-683 + api.c:40-45,455-495: solve is skipped
+            for (int i = lane; i < n; i += 32) a.x[(size_t)p * n + i] = xu[i];
+            if (a.lam) for (int i = lane; i < m; i += 32) a.lam[(size_t)p * m + i] = 0;
+            if (lane == 0) {
+                if (f) a.fval[p] = (T)-0.5 * vnorm;
+                a.exitflag[p] = EXIT_OPTIMAL;
+                a.iter[p] = 1;
+                a.setup_flag[p] = SETUP_UNCONSTRAINED;
+            }
+        } else if (zero_row_infeasible) {
+            if (lane == 0) { a.setup_flag[p] = EXIT_INFEASIBLE; a.exitflag[p] = EXIT_INFEASIBLE; a.iter[p] = 0; }
+        } else {
+            if (lane == 0) a.setup_flag[p] = (sin != nullptr || any_fixed) ? SETUP_SOLVE_ACTIVATE : SETUP_SOLVE;
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace dq

@@ -139,3 +139,69 @@ def generate_config(name: str, N: int | None = None, kappa: float = 100.0) -> QP
     n_default = cfg.pop("N")
     seed = SEED_BASE + int(name[1:])
     return generate_g1(N if N is not None else n_default, kappa=kappa, seed=seed, **cfg)
+
+
+def generate_g1_torch(N: int, n: int, m: int, ms: int, n_active: int, kappa: float = 100.0, seed: int = SEED_BASE,
+                      device="cuda", chunk: int = 8192, random_nactive: bool = False):
+    """Same construction as ``generate_g1`` on a torch device (float64), for bench-size batches (100k problems take
+    about a second on the GPU instead of a minute in numpy). Returns a dict of contiguous tensors with the packed
+    layout of ``daqp_b200_solve_device`` plus ``xref`` / ``active_ref``. Different random stream than the numpy
+    generator (same distribution); determinism is per (seed, device type)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    mA = m - ms
+    out = {"H": torch.empty((N, n, n), dtype=f64, device=dev), "f": torch.empty((N, n), dtype=f64, device=dev),
+           "A": torch.empty((N, mA, n), dtype=f64, device=dev), "bupper": torch.empty((N, m), dtype=f64, device=dev),
+           "blower": torch.empty((N, m), dtype=f64, device=dev), "xref": torch.empty((N, n), dtype=f64, device=dev),
+           "active_ref": torch.empty((N, m), dtype=torch.int8, device=dev)}
+    for lo in range(0, N, chunk):
+        B = min(chunk, N - lo)
+        rnd = lambda *s: torch.rand(*s, dtype=f64, device=dev, generator=g)
+        rndn = lambda *s: torch.randn(*s, dtype=f64, device=dev, generator=g)
+        eig = torch.ones((B, n), dtype=f64, device=dev)
+        eig[:, 1] = kappa
+        if n > 2:
+            eig[:, 2:] = 1.0 + (kappa - 1.0) * rnd(B, n - 2)
+        Q = torch.linalg.qr(rndn(B, n, n))[0]
+        sq = eig.sqrt()
+        T = sq[:, :, None] * Q.transpose(1, 2)
+        Tinv = Q * (1.0 / sq)[:, None, :]
+        M = torch.empty((B, m, n), dtype=f64, device=dev)
+        M[:, :ms] = Tinv[:, :ms]
+        M[:, ms:] = rndn(B, mA, n)
+        pos = torch.argsort(torch.argsort(rnd(B, m), dim=1), dim=1)
+        nact = torch.full((B,), n_active, device=dev) if not random_nactive else \
+            torch.randint(0, n_active + 1, (B,), device=dev, generator=g)
+        nau = torch.minimum((rnd(B) * (nact + 1)).long(), nact)
+        is_up = pos < nau[:, None]
+        is_lo = (pos >= nau[:, None]) & (pos < nact[:, None])
+        sgn = is_up.to(f64) - is_lo.to(f64)
+        lam = rnd(B, m) * (sgn != 0)
+        u = -torch.einsum("bmn,bm->bn", M, sgn * lam)
+        Mu = torch.einsum("bmn,bn->bm", M, u)
+        g1 = 0.01 + rnd(B, m)
+        g2 = 0.01 + rnd(B, m)
+        dupper = torch.where(is_up, Mu, Mu + g1)
+        dlower = torch.where(is_lo, Mu, torch.where(is_up, Mu - g1, Mu - g2))
+        v = rndn(B, n)
+        Mv = torch.einsum("bmn,bn->bm", M, v)
+        sl = slice(lo, lo + B)
+        out["H"][sl] = T.transpose(1, 2) @ T
+        out["f"][sl] = torch.einsum("bij,bi->bj", T, v)
+        out["A"][sl] = M[:, ms:] @ T
+        out["bupper"][sl] = dupper - Mv
+        out["blower"][sl] = dlower - Mv
+        out["xref"][sl] = torch.einsum("bij,bj->bi", Tinv, u - v)
+        out["active_ref"][sl] = sgn.to(torch.int8)
+    return out
+
+
+def torch_to_batch(t: dict, n: int, m: int, ms: int, lo: int = 0, hi: int | None = None) -> QPBatch:
+    """Copy a slice of a torch workload to host as a QPBatch (used to hand the SAME problems to the CPU baseline)."""
+    hi = t["H"].shape[0] if hi is None else hi
+    c = lambda k: np.ascontiguousarray(t[k][lo:hi].cpu().numpy())
+    return QPBatch(n, m, ms, c("H"), c("f"), c("A"), c("bupper"), c("blower"), np.zeros((hi - lo, m), np.int32),
+                   c("xref"), c("active_ref"))

@@ -1,0 +1,170 @@
+/* include/daqp_b200.h -- C ABI of the B200-native batched dual active-set QP engine.
+ *
+ * Drop-in boundary. The three structs below have the SAME field order and layout as the reference
+ * (DAQPProblem: reference include/types.h:14-50, DAQPSettings: include/types.h:52-74, DAQPResult:
+ * include/api.h:15-27), so the reference's language interfaces (Cython daqp.pxd:50-88, Julia types.jl:46-177,
+ * Eigen daqp.cpp:111-112, MATLAB daqpmex.c) bind to this library unchanged for the calls listed here.
+ *
+ *   daqp_quadprog()          replaces reference include/api.h:30 / src/api.c:62-79 (runs a batch of one on the GPU)
+ *   daqp_default_settings()  replaces reference include/api.h:52 / src/api.c:505-527
+ *   daqp_quadprog_batch()    NEW: N independent daqp_quadprog() calls in one launch (the reference has no batch API)
+ *   daqp_b200_solve_packed() NEW: same for a homogeneous batch in strided host arrays (no per-problem pointers)
+ *   daqp_b200_solve_device() NEW: same with device-resident arrays, asynchronous on a caller stream
+ *
+ * Exit flags are the reference's (include/constants.h:42-51). Problems outside the hot-path scope (binary or soft
+ * constraints, hierarchies, AVI, H == NULL, singular H that needs the proximal-point driver) return
+ * DAQP_EXIT_UNSUPPORTED (-8); there is no CPU fallback inside this library.
+ *
+ * All arithmetic is fp64 (c_float = double), like the reference's default build.
+ */
+#ifndef DAQP_B200_H
+#define DAQP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double c_float;
+
+#define DAQP_INF ((c_float)1e30)
+
+/* exit flags -- reference include/constants.h:42-51 */
+#define DAQP_EXIT_SOFT_OPTIMAL 2
+#define DAQP_EXIT_OPTIMAL 1
+#define DAQP_EXIT_INFEASIBLE -1
+#define DAQP_EXIT_CYCLE -2
+#define DAQP_EXIT_UNBOUNDED -3
+#define DAQP_EXIT_ITERLIMIT -4
+#define DAQP_EXIT_NONCONVEX -5
+#define DAQP_EXIT_OVERDETERMINED_INITIAL -6
+#define DAQP_EXIT_TIMELIMIT -7
+#define DAQP_EXIT_UNSUPPORTED -8
+
+/* constraint sense bits -- reference include/constants.h:64-96 */
+#define DAQP_ACTIVE 1
+#define DAQP_LOWER 2
+#define DAQP_IMMUTABLE 4
+#define DAQP_SOFT 8
+#define DAQP_BINARY 16
+
+/* min 0.5 x'Hx + f'x  s.t.  blower <= [I(ms); A] x <= bupper  -- reference include/types.h:14-50 */
+typedef struct {
+    int n;  /* number of variables */
+    int m;  /* number of constraints, simple bounds first */
+    int ms; /* number of simple bounds */
+    c_float* H; /* n x n row-major */
+    c_float* f; /* n, may be NULL */
+    c_float* A; /* (m-ms) x n row-major */
+    c_float* bupper; /* m */
+    c_float* blower; /* m */
+    int* sense; /* m bit flags, may be NULL */
+    int* break_points; /* hierarchical QP: unsupported here */
+    int nh;
+    int problem_type; /* 0 QP; 1 AVI / 2 prefactored H: unsupported here */
+} DAQPProblem;
+
+/* reference include/types.h:52-74 */
+typedef struct {
+    c_float primal_tol;
+    c_float dual_tol;
+    c_float zero_tol;
+    c_float pivot_tol;
+    c_float progress_tol;
+    int cycle_tol;
+    int iter_limit;
+    c_float fval_bound;
+    c_float eps_prox;
+    c_float eta_prox;
+    c_float rho_soft;
+    c_float rel_subopt;
+    c_float abs_subopt;
+    c_float sing_tol;
+    c_float refactor_tol;
+    c_float time_limit; /* ignored by the batched path */
+} DAQPSettings;
+
+/* reference include/api.h:15-27 */
+typedef struct {
+    c_float* x;   /* n, caller-owned */
+    c_float* lam; /* m, caller-owned, may be NULL */
+    c_float fval;
+    c_float soft_slack;
+    int exitflag;
+    int iter;
+    int nodes;
+    c_float solve_time; /* seconds: device time of the batch this problem was part of */
+    c_float setup_time;
+} DAQPResult;
+
+/* ---- drop-in entry points ------------------------------------------------------------------------------- */
+
+/* reference include/api.h:30 (src/api.c:62-79). settings == NULL selects the defaults. */
+void daqp_quadprog(DAQPResult* res, DAQPProblem* qp, DAQPSettings* settings);
+
+/* reference include/api.h:52 (src/api.c:505-527) */
+void daqp_default_settings(DAQPSettings* settings);
+
+/* ---- batch entry points (new) --------------------------------------------------------------------------- */
+
+/* N independent problems, identical in effect to N calls of daqp_quadprog(&res[i], &qps[i], settings).
+ * Problems may differ in (n, m, ms); they are grouped by shape internally. Returns 0, or a negative CUDA-side
+ * error code (then no result field is valid). */
+int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQPSettings* settings);
+
+typedef struct DAQPB200Handle DAQPB200Handle;
+
+/* Engine bound to one CUDA device: owns streams and device scratch that is reused across calls.
+ * device < 0 selects the current device. Returns 0 on success. */
+int daqp_b200_create(DAQPB200Handle** out, int device);
+void daqp_b200_destroy(DAQPB200Handle* h);
+
+/* Optional per-problem diagnostics of the last solve (device pointers for solve_device, host for solve_packed).
+ * Any member may be NULL. */
+typedef struct {
+    int* n_active;  /* [N]          final size of the working set                         */
+    int* ws;        /* [N][n+1]     final working set in factor order                     */
+    int* counts;    /* [N][4]       feasibility scans, LDL adds, LDL removes, CSP solves  */
+    unsigned char* sense; /* [N][ldm], ldm = m rounded up to 4: final sense bits          */
+} DAQPB200Diag;
+
+/* Homogeneous batch, strided HOST arrays: H[N][n][n], f[N][n] (or NULL), A[N][m-ms][n], bupper/blower[N][m],
+ * sense[N][m] (or NULL); outputs x[N][n], lam[N][m] (or NULL), fval[N], exitflag[N], iter[N].
+ * Host<->device copies are pipelined with the solve in chunks; pinned host memory makes them asynchronous.
+ * h == NULL uses a process-wide default engine on the current device. Blocks until the results are in place. */
+int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, int ms,
+                           const c_float* H, const c_float* f, const c_float* A,
+                           const c_float* bupper, const c_float* blower, const int* sense,
+                           const DAQPSettings* settings,
+                           c_float* x, c_float* lam, c_float* fval, int* exitflag, int* iter,
+                           const DAQPB200Diag* diag);
+
+/* Same with DEVICE arrays; enqueues on `stream` (a cudaStream_t; NULL = the engine's own stream) and returns
+ * without synchronising. */
+int daqp_b200_solve_device(DAQPB200Handle* h, int N, int n, int m, int ms,
+                           const c_float* dH, const c_float* df, const c_float* dA,
+                           const c_float* dbupper, const c_float* dblower, const int* dsense,
+                           const DAQPSettings* settings,
+                           c_float* dx, c_float* dlam, c_float* dfval, int* dexitflag, int* diter,
+                           const DAQPB200Diag* diag, void* stream);
+
+/* Device-time accounting of the engine since the last reset (CUDA events on the launching stream). */
+typedef struct {
+    int setup_launches; /* qp_setup_kernel launches   */
+    int solve_launches; /* ldp_solve_kernel launches  */
+    double setup_ms;    /* summed device time of the setup kernels */
+    double solve_ms;    /* summed device time of the solve kernels */
+    int warps_per_sm;   /* resident problems per SM in the last solve launch */
+    long long scratch_bytes;
+} DAQPB200Stats;
+/* Synchronises the engine's streams, then reports and optionally clears the counters. */
+int daqp_b200_get_stats(DAQPB200Handle* h, DAQPB200Stats* out, int reset);
+
+/* Upper bound on device scratch per engine (bytes); batches that need more are processed in chunks. */
+void daqp_b200_set_scratch_limit(DAQPB200Handle* h, long long bytes);
+
+const char* daqp_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAQP_B200_H */

@@ -156,6 +156,30 @@ class RefLib:
         return Solution(x, lam, fval, flag, it, ws, sense_out, None, time.perf_counter() - t0)
 
 
+class RefDriver:
+    """pthread loop around the unmodified reference's daqp_quadprog (oracle/ref_driver.c -> oracle/_ref)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(REF_DIR, "libref_driver.so"))
+        self.lib.ref_solve_packed.restype = C.c_double
+        self.dtype = np.float64
+
+    def solve_packed(self, b, settings=None, nthreads: int = 1, use_sense: bool | None = None) -> "Solution":
+        N, n, m = b.N, b.n, b.m
+        real = C.c_double
+        x = np.zeros((N, n)); lam = np.zeros((N, m)); fval = np.zeros(N)
+        flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
+        if use_sense is None:
+            use_sense = bool(np.any(b.sense))
+        sp = C.byref(settings) if settings is not None else None
+        secs = self.lib.ref_solve_packed(
+            N, n, m, b.ms, _ptr(b.H, real), _ptr(b.f, real), _ptr(b.A, real), _ptr(b.bupper, real),
+            _ptr(b.blower, real), b.sense.ctypes.data_as(C.POINTER(C.c_int)) if use_sense else None, sp,
+            _ptr(x, real), _ptr(lam, real), _ptr(fval, real), flag.ctypes.data_as(C.POINTER(C.c_int)),
+            it.ctypes.data_as(C.POINTER(C.c_int)), nthreads)
+        return Solution(x, lam, fval, flag, it, None, None, None, secs)
+
+
 class OracleLib:
     """This repo's scalar restatement (oracle/daqp_oracle.c)."""
 

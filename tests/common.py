@@ -1,0 +1,59 @@
+"""Shared helpers for the parity tests.
+
+fp64 parity bar (SURVEY.md §8c / BASELINE.md §3.5): exit flag equal, iteration count equal, final working set equal
+(index + side), |x - x_ref|inf <= 1e-9 (1+|x_ref|inf), |fval - fval_ref| <= 1e-9 (1+|fval_ref|),
+|lam - lam_ref|inf <= 1e-7 (1+|lam_ref|inf).
+"""
+import glob
+import os
+
+import numpy as np
+
+from daqp_b200.problems import QPBatch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+X_TOL, F_TOL, L_TOL = 1e-9, 1e-9, 1e-7
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    b = QPBatch(int(d["n"]), int(d["m"]), int(d["ms"]), d["H"], d["f"], d["A"], d["bupper"], d["blower"],
+                d["sense"].astype(np.int32))
+    return b, d
+
+
+def assert_parity(ref_x, ref_lam, ref_fval, ref_flag, ref_iter, x, lam, fval, flag, it, what=""):
+    np.testing.assert_array_equal(flag, ref_flag, err_msg=f"{what}: exit flags differ")
+    np.testing.assert_array_equal(it, ref_iter, err_msg=f"{what}: iteration counts differ")
+    ok = ref_flag > 0
+    if not ok.any():
+        return
+    xs = 1 + np.abs(ref_x[ok]).max(axis=1, keepdims=True)
+    assert (np.abs(x[ok] - ref_x[ok]) <= X_TOL * xs).all(), f"{what}: x off by {np.abs(x[ok] - ref_x[ok]).max():.3e}"
+    ls = 1 + np.abs(ref_lam[ok]).max(axis=1, keepdims=True)
+    assert (np.abs(lam[ok] - ref_lam[ok]) <= L_TOL * ls).all(), \
+        f"{what}: lam off by {np.abs(lam[ok] - ref_lam[ok]).max():.3e}"
+    assert (np.abs(fval[ok] - ref_fval[ok]) <= F_TOL * (1 + np.abs(ref_fval[ok]))).all(), \
+        f"{what}: fval off by {np.abs(fval[ok] - ref_fval[ok]).max():.3e}"
+
+
+def ws_sets(ws, n_active):
+    return [sorted(int(i) for i in ws[p][: n_active[p]]) for p in range(len(n_active))]
+
+
+def kkt_residuals(b: QPBatch, x, lam):
+    """Solver-independent check in the spirit of the reference's Maros-Meszaros runner
+    (.github/benchmarks/maros_meszaros_runner.c:79-130): stationarity, primal feasibility, complementarity."""
+    N, n, m, ms = b.N, b.n, b.m, b.ms
+    Afull = np.zeros((N, m, n))
+    Afull[:, :ms, :] = np.eye(n)[None, :ms, :]
+    Afull[:, ms:, :] = b.A
+    Ax = np.einsum("bmn,bn->bm", Afull, x)
+    stat = np.einsum("bij,bj->bi", b.H, x) + b.f + np.einsum("bmn,bm->bn", Afull, lam)
+    pfeas = np.maximum(np.maximum(Ax - b.bupper, b.blower - Ax), 0)
+    comp = np.minimum(np.abs(lam), np.minimum(np.abs(Ax - b.bupper), np.abs(Ax - b.blower)))
+    return np.abs(stat).max(axis=1), pfeas.max(axis=1), comp.max(axis=1)

@@ -1,0 +1,205 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle and the committed golden vectors.
+
+fp64 tolerances are stated in tests/common.py (x 1e-9, fval 1e-9, lam 1e-7, relative); exit flags, iteration counts,
+final working sets and per-problem operation counts must be EQUAL.
+"""
+import numpy as np
+import pytest
+
+from common import assert_parity, golden_names, kkt_residuals, load_golden, ws_sets
+from daqp_b200.problems import generate_config, generate_g0, generate_g1
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(cuda_lib):
+    import daqp_b200
+    e = daqp_b200.Engine()
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def oracle(oracle_libs):
+    return oracle_libs.OracleLib()
+
+
+def run_gpu(engine, b, use_sense=None, **settings):
+    if use_sense is None:
+        use_sense = bool(b.sense.any())
+    return engine.solve_batch(b.H, b.f, b.A, b.bupper, b.blower, b.sense if use_sense else None, ms=b.ms, diag=True,
+                              **settings)
+
+
+def check_vs_oracle(engine, oracle, b, what, use_sense=None, settings=None):
+    from oracle import harness
+    settings = settings or {}
+    st = harness.default_settings(**settings) if settings else None
+    o = oracle.solve(b, settings=st, use_sense=use_sense)
+    r = run_gpu(engine, b, use_sense=use_sense, **settings)
+    assert_parity(o.x, o.lam, o.fval, o.exitflag, o.iter, r.x, r.lam, r.fval, r.exitflag, r.iter, what)
+    started = o.exitflag >= -4
+    got = r.working_sets()
+    for p in np.nonzero(started)[0]:
+        assert got[p] == list(o.ws[p]), f"{what}[{p}]: working set (factor order) differs"
+        assert (r.sense[p] & 3 == o.sense[p] & 3)[o.ws[p]].all(), f"{what}[{p}]: active side differs"
+    np.testing.assert_array_equal(r.counts[started], o.counts[started], err_msg=f"{what}: scan/add/remove counts")
+    return o, r
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_golden(engine, name):
+    """Outputs of the unmodified reference, generated in the build container (tests/golden/make_golden.py)."""
+    b, d = load_golden(name)
+    r = run_gpu(engine, b, use_sense=bool(d["use_sense"]))
+    assert_parity(d["x"], d["lam"], d["fval"], d["exitflag"], d["iter"], r.x, r.lam, r.fval, r.exitflag, r.iter, name)
+    want = ws_sets(d["ws"], d["n_active"])
+    got = [sorted(w) for w in r.working_sets()]
+    for p in np.nonzero(d["exitflag"] >= -4)[0]:
+        assert got[p] == want[p], f"{name}[{p}]: final active set differs from the reference"
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3"])
+def test_configs_vs_oracle(engine, oracle, cfg):
+    """BASELINE.json configs at sizes the scalar oracle finishes in seconds."""
+    N = {"C1": 1000, "C2": 3000, "C3": 1200}[cfg]
+    b = generate_config(cfg, N=N)
+    o, r = check_vs_oracle(engine, oracle, b, cfg)
+    assert (r.exitflag == 1).all()
+    assert np.abs(r.x - b.xref).max() < 1e-8  # construction-known optimum
+
+
+@pytest.mark.parametrize("shape", [(20, 60, 10, 16), (30, 80, 30, 20), (70, 200, 7, 50), (33, 95, 5, 25),
+                                   (64, 130, 0, 50), (65, 131, 1, 50), (120, 400, 120, 96)])
+def test_shapes_vs_oracle(engine, oracle, shape):
+    """Simple bounds, odd sizes (padding paths), n on both sides of a 64-column lane group, C4 shape."""
+    n, m, ms, na = shape
+    N = 150 if n >= 100 else 400
+    check_vs_oracle(engine, oracle, generate_g1(N, n, m, ms, na, seed=2000 + n + ms), f"G1{shape}")
+
+
+def test_g0_distribution(engine, oracle):
+    check_vs_oracle(engine, oracle, generate_g0(800, 50, 150), "G0 n50 m150")
+
+
+def test_degenerate_and_infeasible(engine, oracle):
+    check_vs_oracle(engine, oracle, generate_g1(600, 10, 40, 10, 10, seed=31), "vertex (nact = n)")
+    check_vs_oracle(engine, oracle, generate_g1(400, 20, 60, 5, 16, kappa=1e9, seed=32), "kappa 1e9")
+    b = generate_g1(400, 10, 30, 0, 8, seed=33)
+    b.A[:, 15:30] = b.A[:, 0:15]; b.bupper[:, 15:30] = b.bupper[:, 0:15]; b.blower[:, 15:30] = b.blower[:, 0:15]
+    check_vs_oracle(engine, oracle, b, "duplicate rows (singular steps)")
+    b = generate_g1(400, 10, 30, 0, 8, seed=34)
+    b.A[:, 1] = b.A[:, 0]; b.bupper[:, 1] = b.blower[:, 0] - 1.0; b.blower[:, 1] = b.blower[:, 0] - 2.0
+    o, r = check_vs_oracle(engine, oracle, b, "infeasible")
+    assert (r.exitflag == -1).all()
+    b = generate_g1(64, 10, 30, 0, 8, seed=35)
+    b.blower[::2, 3] = b.bupper[::2, 3] + 1  # every other problem trivially infeasible, the rest solvable
+    o, r = check_vs_oracle(engine, oracle, b, "mixed trivially infeasible")
+    assert (r.exitflag[::2] == -1).all() and (r.exitflag[1::2] == 1).all()
+
+
+def test_warm_start_and_equalities(engine, oracle):
+    b = generate_g1(300, 20, 60, 5, 16, seed=41)
+    o = oracle.solve(b)
+    b.sense[o.lam > 1e-12] = 1
+    b.sense[o.lam < -1e-12] = 3
+    o2, r2 = check_vs_oracle(engine, oracle, b, "warm start from the optimal active set", use_sense=True)
+    assert (r2.iter == 1).all()  # core_tests.jl:520-543
+    rng = np.random.default_rng(5)
+    b.sense[:] = np.where(rng.random(b.sense.shape) < 0.6, rng.choice([1, 3], b.sense.shape), 0)
+    check_vs_oracle(engine, oracle, b, "over-determined warm start", use_sense=True)
+    b = generate_g1(300, 20, 60, 0, 16, seed=42)
+    for p in range(b.N):
+        act = np.nonzero(b.active_ref[p])[0][:4]
+        b.sense[p, act] = 5
+    check_vs_oracle(engine, oracle, b, "equalities", use_sense=True)
+    b.sense[:] = 0
+    for p in range(b.N):
+        for i in np.nonzero(b.active_ref[p])[0][:4]:
+            if b.active_ref[p, i] > 0: b.blower[p, i] = b.bupper[p, i]
+            else: b.bupper[p, i] = b.blower[p, i]
+    check_vs_oracle(engine, oracle, b, "equalities via bl == bu", use_sense=False)
+
+
+def test_settings_and_limits(engine, oracle):
+    b = generate_g1(100, 20, 60, 0, 16, seed=51)
+    o, r = check_vs_oracle(engine, oracle, b, "iter_limit", settings={"iter_limit": 7})
+    assert (r.exitflag == -4).all() and (r.iter == 7).all()  # core_tests.jl:32-35 semantics
+    check_vs_oracle(engine, oracle, b, "loose primal_tol", settings={"primal_tol": 1e-3})
+    check_vs_oracle(engine, oracle, generate_g1(50, 10, 30, 0, 0, seed=52), "unconstrained optimum")
+    b = generate_g1(16, 8, 20, 0, 6, seed=53)
+    b.sense[:, 0] = 16
+    assert (run_gpu(engine, b, use_sense=True).exitflag == -8).all()  # binaries: out of scope, flagged
+    b = generate_g1(16, 8, 20, 0, 6, seed=54)
+    b.H[:, 0, :] = 0; b.H[:, :, 0] = 0
+    assert (run_gpu(engine, b).exitflag == -8).all()  # singular H needs the proximal driver: flagged
+
+
+def test_no_linear_term_and_diagonal_hessian(engine, oracle):
+    b = generate_g1(100, 12, 36, 4, 9, seed=61)
+    b.H[:] = (np.eye(12) * np.linspace(1, 5, 12))[None]
+    check_vs_oracle(engine, oracle, b, "diagonal H with simple bounds")
+
+
+def test_drop_in_entry_points(cuda_lib, oracle):
+    """daqp_quadprog (batch of one) and daqp_quadprog_batch (array of structs, mixed shapes)."""
+    import daqp_b200
+    for name, want in [("lit_model_qp", [-1, -1]), ("lit_model_qp_flipped", [1, 1]), ("lit_model_qp_half", [-0.5, -0.5]),
+                       ("lit_eigen_basic", [-1, -1])]:
+        b, d = load_golden(name)
+        x, fval, flag, info = daqp_b200.solve(b.H[0], b.f[0], b.A[0], b.bupper[0], b.blower[0], b.sense[0])
+        assert flag == 1 and info["iterations"] == int(d["iter"][0])
+        np.testing.assert_allclose(x, want, atol=1e-9)
+        np.testing.assert_allclose(fval, d["fval"][0], atol=1e-9)
+    mixed, refs = [], []
+    for seed, (n, m, ms, na) in enumerate([(10, 20, 0, 8), (20, 60, 10, 16), (10, 20, 0, 8), (7, 15, 3, 5)] * 3):
+        b = generate_g1(1, n, m, ms, na, seed=700 + seed)
+        o = oracle.solve(b)
+        mixed.append(dict(H=b.H[0], f=b.f[0], A=b.A[0], bupper=b.bupper[0], blower=b.blower[0]))
+        refs.append(o)
+    out = daqp_b200.quadprog_batch(mixed)
+    for (x, fval, flag, info), o in zip(out, refs):
+        assert flag == o.exitflag[0] and info["iterations"] == o.iter[0]
+        np.testing.assert_allclose(x, o.x[0], rtol=0, atol=1e-9 * (1 + np.abs(o.x[0]).max()))
+        np.testing.assert_allclose(info["lam"], o.lam[0], rtol=0, atol=1e-7 * (1 + np.abs(o.lam[0]).max()))
+
+
+def test_device_entry_point_and_chunking(engine, oracle):
+    """Device-pointer entry on the torch stream; a tiny scratch limit forces the multi-chunk path."""
+    import torch
+    import daqp_b200
+    b = generate_g1(700, 20, 60, 4, 16, seed=81)
+    o = oracle.solve_packed(b)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    eng = daqp_b200.Engine()
+    eng.set_scratch_limit(12 << 20)  # ~ 200 problems per chunk
+    out = eng.solve_batch_device(t(b.H), t(b.f), t(b.A), t(b.bupper), t(b.blower), None, ms=b.ms)
+    torch.cuda.synchronize()
+    st = eng.stats()
+    assert st["solve_launches"] >= 3
+    assert_parity(o.x, o.lam, o.fval, o.exitflag, o.iter, out["x"].cpu().numpy(), out["lam"].cpu().numpy(),
+                  out["fval"].cpu().numpy(), out["exitflag"].cpu().numpy(), out["iter"].cpu().numpy(), "device entry")
+    eng.close()
+
+
+def test_full_size_properties(engine):
+    """BASELINE.json C3 at a size the oracle cannot cover: size-independent properties only.
+    (1) every problem reports OPTIMAL, (2) x equals the construction-known optimum, (3) the active set equals the
+    constructed one, (4) KKT residuals vanish, (5) solving the same batch twice is bit-identical (idempotence /
+    no dependence on warp scheduling)."""
+    b = generate_config("C3", N=20000)
+    r = run_gpu(engine, b)
+    assert (r.exitflag == 1).all()
+    assert np.abs(r.x - b.xref).max() < 1e-8
+    assert (np.sign(r.lam) == b.active_ref).all()
+    stat, pf, comp = kkt_residuals(b, r.x, r.lam)
+    assert stat.max() < 1e-8 and pf.max() < 1e-8 and comp.max() < 1e-8
+    r2 = run_gpu(engine, b)
+    np.testing.assert_array_equal(r.x, r2.x)
+    np.testing.assert_array_equal(r.iter, r2.iter)
+    # a batch is a set of independent problems: permuting it permutes the answers
+    perm = np.random.default_rng(0).permutation(b.N)[:4000]
+    sub = engine.solve_batch(b.H[perm], b.f[perm], b.A[perm], b.bupper[perm], b.blower[perm], None, ms=b.ms)
+    np.testing.assert_array_equal(sub.x, r.x[perm])

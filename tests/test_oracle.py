@@ -1,0 +1,89 @@
+"""CPU suite: the oracle restatement against (1) golden vectors produced by the unmodified reference,
+(2) the reference itself when it is compiled here (oracle/_ref), (3) construction-known optima."""
+import numpy as np
+import pytest
+
+from common import assert_parity, golden_names, kkt_residuals, load_golden, ws_sets
+from daqp_b200.problems import generate_g0, generate_g1
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_golden(oracle_libs, name):
+    b, d = load_golden(name)
+    o = oracle_libs.OracleLib().solve(b, use_sense=bool(d["use_sense"]))
+    assert_parity(d["x"], d["lam"], d["fval"], d["exitflag"], d["iter"], o.x, o.lam, o.fval, o.exitflag, o.iter, name)
+    started = d["exitflag"] >= -4  # failures raised by the setup leave no working set
+    got = [sorted(w) for w in o.ws]
+    want = ws_sets(d["ws"], d["n_active"])
+    for p in np.nonzero(started)[0]:
+        assert got[p] == want[p], f"{name}[{p}]: working sets differ"
+
+
+def test_known_answers():
+    """Literals of the reference's own tests (example_test.py:175-237, 00_basic_qp.cpp:28)."""
+    for name, want in [("lit_model_qp", [-1, -1]), ("lit_model_qp_flipped", [1, 1]), ("lit_model_qp_half", [-0.5, -0.5]),
+                       ("lit_eigen_basic", [-1, -1])]:
+        _, d = load_golden(name)
+        assert d["exitflag"][0] == 1
+        np.testing.assert_allclose(d["x"][0], want, atol=1e-6)
+    assert load_golden("lit_python_demo")[1]["exitflag"][0] == 1
+    assert (load_golden("warm_exact")[1]["iter"] == 1).all()
+    assert (load_golden("trivially_infeasible")[1]["exitflag"] == -1).all()
+
+
+@pytest.mark.parametrize("shape", [(10, 20, 0, 8), (20, 60, 0, 16), (24, 70, 9, 18), (50, 150, 0, 40)])
+def test_oracle_recovers_constructed_optimum(oracle_libs, shape):
+    """generate_test_QP gives xref and the optimal active set by construction; the reference's own gate is
+    |x - xref| < 1e-4 (core_tests.jl:26-30)."""
+    n, m, ms, na = shape
+    b = generate_g1(40, n, m, ms, na, seed=900 + n)
+    o = oracle_libs.OracleLib().solve(b)
+    assert (o.exitflag == 1).all()
+    assert np.abs(o.x - b.xref).max() < 1e-8
+    for p in range(b.N):
+        assert sorted(o.ws[p]) == np.nonzero(b.active_ref[p])[0].tolist()
+        assert (np.sign(o.lam[p]) == b.active_ref[p]).all()
+    stat, pf, comp = kkt_residuals(b, o.x, o.lam)
+    assert stat.max() < 1e-8 and pf.max() < 1e-8 and comp.max() < 1e-8
+
+
+@pytest.mark.parametrize("libname", ["libdaqp_ref_strict.so", "libdaqp_ref.so"])
+def test_oracle_vs_live_reference(oracle_libs, libname):
+    """Against the reference compiled here from /root/reference. The -O2 -ffp-contract=off build must agree BIT FOR
+    BIT; the default fast-math build to the parity tolerances with identical iteration counts and working sets."""
+    if not oracle_libs.have_ref(libname):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    ref = oracle_libs.RefLib(libname)
+    orc = oracle_libs.OracleLib()
+    batches = [generate_g1(60, 10, 20, 0, 8, seed=1), generate_g1(60, 20, 60, 10, 16, seed=2),
+               generate_g1(20, 50, 150, 0, 40, seed=3), generate_g0(40, 20, 60, seed=4),
+               generate_g1(40, 20, 60, 5, 16, kappa=1e9, seed=5), generate_g1(60, 10, 40, 10, 10, seed=6)]
+    for b in batches:
+        r = ref.solve(b, want_ws=True)
+        o = orc.solve(b)
+        if "strict" in libname:
+            for a, c in ((r.x, o.x), (r.lam, o.lam), (r.fval, o.fval), (r.iter, o.iter), (r.exitflag, o.exitflag)):
+                np.testing.assert_array_equal(a, c)
+        else:
+            assert_parity(r.x, r.lam, r.fval, r.exitflag, r.iter, o.x, o.lam, o.fval, o.exitflag, o.iter, libname)
+        assert [list(w) for w in r.ws] == [list(w) for w in o.ws]
+
+
+def test_oracle_threads_and_packed_entry(oracle_libs):
+    b = generate_g1(64, 12, 30, 3, 9, seed=11)
+    orc = oracle_libs.OracleLib()
+    one = orc.solve(b)
+    for nt in (1, 3):
+        pk = orc.solve_packed(b, nthreads=nt)
+        np.testing.assert_array_equal(one.x, pk.x)
+        np.testing.assert_array_equal(one.iter, pk.iter)
+        np.testing.assert_array_equal(one.counts, pk.counts)
+
+
+def test_oracle_out_of_scope_flags(oracle_libs):
+    b = generate_g1(4, 8, 20, 0, 6, seed=12)
+    b.sense[:, 0] = 16  # binary
+    assert (oracle_libs.OracleLib().solve(b, use_sense=True).exitflag == -8).all()
+    b = generate_g1(4, 8, 20, 0, 6, seed=13)
+    b.H[:, 0, :] = 0; b.H[:, :, 0] = 0  # singular H -> proximal driver in the reference
+    assert (oracle_libs.OracleLib().solve(b).exitflag == -8).all()
