@@ -218,6 +218,8 @@ class Engine:
                              C.cast(diag["sense"].data_ptr(), C.POINTER(C.c_ubyte)))
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
+        if stream == 0:
+            stream = 1  # cudaStreamLegacy: name torch's default stream explicitly (NULL means "the engine's own")
         ptr = lambda t, ty=_dp: None if t is None else C.cast(t.data_ptr(), ty)
         st = default_settings(**settings)
         _check(lib().daqp_b200_solve_device(self._h, N, n, m, ms, ptr(H), ptr(f), ptr(A), ptr(bupper), ptr(blower),

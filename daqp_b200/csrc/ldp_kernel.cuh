@@ -623,7 +623,13 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const LdpArgs<T> a) {
         p = __shfl_sync(FULL, p, 0);
         if (p >= a.P) break;
         const int sflag = a.setup_flag[p];
-        if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) continue; // finished by the setup kernel
+        if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) { // finished by the setup kernel
+            if (a.nact_out && lane == 0) a.nact_out[p] = 0;
+            if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = 0;
+            if (a.sense_out)
+                for (int i = lane; i < a.m; i += 32) a.sense_out[(size_t)p * a.ldm + i] = a.sense[(size_t)p * a.ldm + i];
+            continue;
+        }
 
         w.Mt = a.Mt + (size_t)p * a.n * a.ldm;
         w.Mr = a.Mr + (size_t)p * a.m * a.ldn;
