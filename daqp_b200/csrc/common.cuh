@@ -46,6 +46,27 @@ template <> __device__ __forceinline__ void ldg_vec<float>(const float* p, float
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
 }
+// L2 eviction policies (createpolicy + ld.global.nc.L2::cache_hint): the streamed column-major matrix is marked
+// evict_first so that it does not push the small, re-read set of active rows (marked evict_last) out of L2.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <typename T> __device__ __forceinline__ void ldg_vec_hint(const T* p, T (&out)[VecOf<T>::N], uint64_t pol);
+template <> __device__ __forceinline__ void ldg_vec_hint<double>(const double* p, double (&out)[2], uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(out[0]), "=d"(out[1]) : "l"(p), "l"(pol));
+}
+template <> __device__ __forceinline__ void ldg_vec_hint<float>(const float* p, float (&out)[4], uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "l"(p), "l"(pol));
+}
 template <typename T> __device__ __forceinline__ void stg_vec(T* p, const T (&in)[VecOf<T>::N]);
 template <> __device__ __forceinline__ void stg_vec<double>(double* p, const double (&in)[2]) {
     *reinterpret_cast<double2*>(p) = make_double2(in[0], in[1]);
@@ -58,6 +79,35 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
+}
+
+// Sum B per-lane values across the warp with a transposed butterfly: B/2 + B/4 + ... + 1 exchanges replace B full
+// 5-step reductions. Returns the warp total of value number multi_index<B>(lane); the 32/B lanes that share the
+// top log2(B) lane bits all return the same total.
+template <int B, typename T> __device__ __forceinline__ T warp_sum_multi(T (&v)[B], int lane) {
+    static_assert(B == 1 || B == 2 || B == 4 || B == 8 || B == 16, "B must be a power of two <= 16");
+    int bit = 16;
+#pragma unroll
+    for (int half = B / 2; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = lane & bit;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            const T send = up ? v[i] : v[i + half];
+            const T keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, bit);
+        }
+    }
+    T r = v[0];
+#pragma unroll
+    for (int o = 16 / B; o >= 1; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+    return r;
+}
+// which of the B values a lane ends up holding after warp_sum_multi<B>
+template <int B> __device__ __forceinline__ int multi_index(int lane) {
+    int idx = 0, bit = 16;
+#pragma unroll
+    for (int half = B / 2; half >= 1; half >>= 1, bit >>= 1) idx += (lane & bit) ? half : 0;
+    return idx;
 }
 
 // Lexicographic (value, key) minimum over the warp. Reproduces a sequential "strict <, first index wins" scan

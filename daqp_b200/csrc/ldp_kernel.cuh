@@ -56,6 +56,8 @@ __host__ __device__ inline size_t ldp_smem_per_warp(int n, int m, int cap) {
 template <typename T, int NG>
 struct Warp {
     static constexpr int V = VecOf<T>::N;
+    static constexpr int ROWB = (NG == 1) ? 8 : (NG == 2 ? 4 : 2); // active rows fetched per batch
+    uint64_t pol_keep, pol_stream; // L2 policies: active rows are re-read every iteration, the scan is a pure stream
     // shared memory
     T *L, *D, *lam, *lams, *xl, *zl, *u;
     int* WS;
@@ -85,7 +87,7 @@ struct Warp {
             const int c = V * (lane + 32 * g);
 #pragma unroll
             for (int e = 0; e < V; e++) mi[g][e] = 0;
-            if (c < ldn) ldg_vec<T>(rowi + c, mi[g]);
+            if (c < ldn) ldg_vec_hint<T>(rowi + c, mi[g], pol_keep);
 #pragma unroll
             for (int e = 0; e < V; e++) part += mi[g][e] * mi[g][e];
         }
@@ -93,23 +95,34 @@ struct Warp {
         const int kk = k;
         T* Lk = L + loff(kk);
         if (kk > 0) {
-            // l_j = M_{WS[j]} . m_add   (each row read once, 128-bit coalesced; warp reduction per row)
-#pragma unroll 4
-            for (int j = 0; j < kk; j++) {
-                const T* rowj = Mr + (size_t)WS[j] * ldn;
-                T pj = 0;
+            // l_j = M_{WS[j]} . m_add : ROWB rows per batch -> ROWB*NG independent 128-bit loads in flight, then one
+            // transposed butterfly sums all ROWB dot products at once
+            for (int j0 = 0; j0 < kk; j0 += ROWB) {
+                T tv[ROWB][NG][V];
 #pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    const int c = V * (lane + 32 * g);
-                    if (c < ldn) {
-                        T t[V];
-                        ldg_vec<T>(rowj + c, t);
+                for (int b = 0; b < ROWB; b++) {
+                    const int j = min(j0 + b, kk - 1); // clamp keeps the address valid; surplus results are dropped
+                    const T* rowj = Mr + (size_t)WS[j] * ldn;
 #pragma unroll
-                        for (int e = 0; e < V; e++) pj += t[e] * mi[g][e];
+                    for (int g = 0; g < NG; g++) {
+                        const int c = V * (lane + 32 * g);
+#pragma unroll
+                        for (int e = 0; e < V; e++) tv[b][g][e] = 0;
+                        if (c < ldn) ldg_vec_hint<T>(rowj + c, tv[b][g], pol_keep);
                     }
                 }
-                pj = warp_sum(pj);
-                if (lane == 0) Lk[j] = pj;
+                T pv[ROWB];
+#pragma unroll
+                for (int b = 0; b < ROWB; b++) {
+                    pv[b] = 0;
+#pragma unroll
+                    for (int g = 0; g < NG; g++)
+#pragma unroll
+                        for (int e = 0; e < V; e++) pv[b] += tv[b][g][e] * mi[g][e];
+                }
+                const T tot = warp_sum_multi<ROWB>(pv, lane);
+                const int j = j0 + multi_index<ROWB>(lane);
+                if ((lane & (32 / ROWB - 1)) == 0 && j < kk) Lk[j] = tot;
             }
             __syncwarp();
             // l <- L^-1 l : column sweep, one broadcast + one FMA per step
@@ -303,20 +316,28 @@ struct Warp {
         for (int g = 0; g < NG; g++)
 #pragma unroll
             for (int e = 0; e < V; e++) acc[g][e] = 0;
-#pragma unroll 4
-        for (int i = 0; i < k; i++) {
-            const T* row = Mr + (size_t)WS[i] * ldn;
-            const T li = lams[i];
+        for (int i0 = 0; i0 < k; i0 += ROWB) { // ROWB rows per batch: all loads first, then the FMAs in index order
+            T tv[ROWB][NG][V];
+            T li[ROWB];
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                const int c = V * (lane + 32 * g);
-                if (c < ldn) {
-                    T t[V];
-                    ldg_vec<T>(row + c, t);
+            for (int b = 0; b < ROWB; b++) {
+                const int i = i0 + b;
+                const T* row = Mr + (size_t)WS[min(i, k - 1)] * ldn;
+                li[b] = (i < k) ? lams[i] : (T)0;
 #pragma unroll
-                    for (int e = 0; e < V; e++) acc[g][e] -= t[e] * li;
+                for (int g = 0; g < NG; g++) {
+                    const int c = V * (lane + 32 * g);
+#pragma unroll
+                    for (int e = 0; e < V; e++) tv[b][g][e] = 0;
+                    if (c < ldn && i < k) ldg_vec_hint<T>(row + c, tv[b][g], pol_keep);
                 }
             }
+#pragma unroll
+            for (int b = 0; b < ROWB; b++)
+#pragma unroll
+                for (int g = 0; g < NG; g++)
+#pragma unroll
+                    for (int e = 0; e < V; e++) acc[g][e] -= tv[b][g][e] * li[b];
         }
         T part = 0;
 #pragma unroll
@@ -335,33 +356,40 @@ struct Warp {
     // ---- a8: Mu = M u for all rows, most-violated inactive row (auxiliary.c:89-198). Returns 1 if a row was added.
     __device__ int add_infeasible() {
         n_scan++;
-        constexpr int RB = 2 * 32 * V; // rows per block: two 128-bit loads per lane per column
+        constexpr int SG = 4;            // row groups per pass: up to SG 128-bit loads per lane and column
+        constexpr int GR = 32 * V;       // rows per group
         T best = 0;
         int key = INT_MAX;
         const T ep = -st->primal_tol;
-        for (int base = 0; base < m; base += RB) {
-            const int r0 = base + V * lane, r1 = r0 + 32 * V;
-            const bool ok0 = r0 < ldm, ok1 = r1 < ldm;
-            T a0[V], a1[V];
+        for (int base = 0; base < m; base += SG * GR) {
+            const int r0 = base + V * lane;
+            const int ngrp = min(SG, (ldm - base + GR - 1) / GR); // warp-uniform
+            T acc[SG][V];
 #pragma unroll
-            for (int e = 0; e < V; e++) { a0[e] = 0; a1[e] = 0; }
+            for (int g = 0; g < SG; g++)
+#pragma unroll
+                for (int e = 0; e < V; e++) acc[g][e] = 0;
             const T* col = Mt + r0;
-#pragma unroll 5
+#pragma unroll 4
             for (int c = 0; c < n; c++) {
                 const T uc = u[c];
-                T t0[V], t1[V];
+                T t[SG][V];
 #pragma unroll
-                for (int e = 0; e < V; e++) { t0[e] = 0; t1[e] = 0; }
-                if (ok0) ldg_vec<T>(col, t0);
-                if (ok1) ldg_vec<T>(col + 32 * V, t1);
+                for (int g = 0; g < SG; g++) {
 #pragma unroll
-                for (int e = 0; e < V; e++) { a0[e] += t0[e] * uc; a1[e] += t1[e] * uc; }
+                    for (int e = 0; e < V; e++) t[g][e] = 0;
+                    if (g < ngrp && r0 + g * GR < ldm) ldg_vec_hint<T>(col + g * GR, t[g], pol_stream);
+                }
+#pragma unroll
+                for (int g = 0; g < SG; g++)
+#pragma unroll
+                    for (int e = 0; e < V; e++) acc[g][e] += t[g][e] * uc;
                 col += ldm;
             }
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int rr = h ? r1 : r0;
-                if (rr < m) { // ldm is a multiple of V: the whole vector is addressable
+            for (int g = 0; g < SG; g++) {
+                const int rr = r0 + g * GR;
+                if (g < ngrp && rr < m) { // ldm is a multiple of V: the whole vector is addressable
                     T bu[V], bl[V], bs[V];
                     ldg_vec<T>(du + rr, bu);
                     ldg_vec<T>(dl + rr, bl);
@@ -371,7 +399,7 @@ struct Warp {
                         const int row = rr + e;
                         if (row >= m) continue;
                         if (sense[row] & (B_ACTIVE + B_IMMUTABLE)) continue;
-                        const T mu = h ? a1[e] : a0[e];
+                        const T mu = acc[g][e];
                         const T bound = ep * bs[e];
                         T cand = bu[e] - mu;
                         if (cand < best && cand < bound) { best = cand; key = 2 * row; }
@@ -601,6 +629,8 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const LdpArgs<T> a) {
 
     Warp<T, NG> w;
     w.lane = lane;
+    w.pol_keep = policy_evict_last();
+    w.pol_stream = policy_evict_first();
     w.n = a.n; w.m = a.m; w.ldm = a.ldm; w.ldn = a.ldn; w.cap = a.cap;
     w.st = &a.st;
     T* fp = reinterpret_cast<T*>(base);
