@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdaqp_b200.so")
+LIB_PATH = os.environ.get("DAQP_B200_LIB", os.path.join(_HERE, "libdaqp_b200.so"))
 
 DAQP_INF = 1e30
 EXIT_OPTIMAL, EXIT_SOFT_OPTIMAL = 1, 2

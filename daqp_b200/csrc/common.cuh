@@ -60,10 +60,26 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 }
 template <typename T> __device__ __forceinline__ void ldg_vec_hint(const T* p, T (&out)[VecOf<T>::N], uint64_t pol);
 template <> __device__ __forceinline__ void ldg_vec_hint<double>(const double* p, double (&out)[2], uint64_t pol) {
-    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
                  : "=d"(out[0]), "=d"(out[1]) : "l"(p), "l"(pol));
 }
 template <> __device__ __forceinline__ void ldg_vec_hint<float>(const float* p, float (&out)[4], uint64_t pol) {
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "l"(p), "l"(pol));
+}
+// One-instruction bulk prefetch of a contiguous global range into L2 (TMA bulk prefetch, no registers, no smem).
+// bytes must be a multiple of 16 and p 16-byte aligned. Issued by one lane.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// Same loads, but "volatile": the compiler keeps them in program order, which is what pins the depth of a
+// hand-written software pipeline (a slot is refilled right after it has been consumed).
+template <typename T> __device__ __forceinline__ void ldg_vec_hint_ordered(const T* p, T (&out)[VecOf<T>::N], uint64_t pol);
+template <> __device__ __forceinline__ void ldg_vec_hint_ordered<double>(const double* p, double (&out)[2], uint64_t pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(out[0]), "=d"(out[1]) : "l"(p), "l"(pol));
+}
+template <> __device__ __forceinline__ void ldg_vec_hint_ordered<float>(const float* p, float (&out)[4], uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "l"(p), "l"(pol));
 }

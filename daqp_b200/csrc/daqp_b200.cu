@@ -186,11 +186,11 @@ static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
     return e * sizeof(T) + ldm + sizeof(int) + 64; // + sense bytes + setup flag + alignment slack
 }
 
-template <typename T, int NG>
+template <typename T, int NV>
 static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ldp_solve_kernel<T, NG><<<grid, block, smem, s>>>(a);
+    ldp_solve_kernel<T, NV><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
 }
 template <typename T, int NGS>
@@ -210,10 +210,13 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
     constexpr int V = VecOf<T>::N;
     const int ldm = round_up(std::max(m, 1), 4), ldn = round_up(n, V), cap = n + 1, mA = m - ms;
-    const int ng = (ldn + 32 * V - 1) / (32 * V), ngs = (n + 31) / 32;
-    if (ng > 4 || ngs > 8) { g_last_error = "daqp_b200: n > 256 is not supported"; return -2; }
+    const int nv = (cap + 31) / 32, ngs = (n + 31) / 32; // register segments of a length-cap vector / of a row
+    if (nv > 8 || ngs > 8) { g_last_error = "daqp_b200: n > 255 is not supported"; return -2; }
 
-    const size_t smem_solve_w = ldp_smem_per_warp<T>(n, m, cap), smem_setup_w = setup_smem_per_warp<T>(n);
+    LdpArgs<T> la;
+    memset(&la, 0, sizeof(la));
+    la.n = n; la.m = m; la.ms = ms; la.ldm = ldm; la.ldn = ldn; la.cap = cap;
+    const size_t smem_solve_w = ldp_layout<T>(la), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
     int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
     if (w_solve < 1 || w_setup < 1) { g_last_error = "daqp_b200: problem too large for shared memory"; return -2; }
@@ -276,8 +279,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         }
         CK(cudaEventRecord(ev.e1, stream));
 
-        LdpArgs<T> la;
-        la.P = P; la.n = n; la.m = m; la.ms = ms; la.ldm = ldm; la.ldn = ldn; la.cap = cap;
+        la.P = P;
         la.Mt = Mt; la.Mr = Mr; la.dupper = du; la.dlower = dl; la.scaling = sc; la.Rinv = Ri;
         la.v = df ? vv : nullptr; la.sense = sense8; la.setup_flag = sflag;
         la.x = sa.x; la.lam = sa.lam; la.fval = sa.fval; la.exitflag = sa.exitflag; la.iter = sa.iter;
@@ -286,15 +288,21 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.counts_out = (diag && diag->counts) ? diag->counts + 4 * (size_t)p0 : nullptr;
         la.sense_out = (diag && diag->sense) ? diag->sense + (size_t)p0 * ldm : nullptr;
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
+        la.tune = 0; // experiment knob: 1 = bulk L2 prefetch of the streamed matrix ahead of the scan
+        if (const char* tenv = getenv("DAQP_B200_TUNE")) la.tune = atoi(tenv);
         {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
             const size_t smem = smem_solve_w * w_solve;
             cudaError_t e = cudaErrorInvalidValue;
-            switch (ng) {
+            switch (nv) {
                 case 1: e = launch_solve<T, 1>(la, grid, 32 * w_solve, smem, stream); break;
                 case 2: e = launch_solve<T, 2>(la, grid, 32 * w_solve, smem, stream); break;
                 case 3: e = launch_solve<T, 3>(la, grid, 32 * w_solve, smem, stream); break;
-                default: e = launch_solve<T, 4>(la, grid, 32 * w_solve, smem, stream); break;
+                case 4: e = launch_solve<T, 4>(la, grid, 32 * w_solve, smem, stream); break;
+                case 5: e = launch_solve<T, 5>(la, grid, 32 * w_solve, smem, stream); break;
+                case 6: e = launch_solve<T, 6>(la, grid, 32 * w_solve, smem, stream); break;
+                case 7: e = launch_solve<T, 7>(la, grid, 32 * w_solve, smem, stream); break;
+                default: e = launch_solve<T, 8>(la, grid, 32 * w_solve, smem, stream); break;
             }
             if (e != cudaSuccess) return fail("ldp_solve_kernel launch", e, __LINE__);
             h->stats.solve_launches++;
