@@ -136,105 +136,39 @@ struct Warp {
 
     __device__ __forceinline__ void reset() { sing = EMPTY_IND; k = 0; reuse = 0; } // daqp.c:142-146
 
-    // ---- register-resident vectors: element i = lane + 32 q of a length <= cap vector sits in x[q]
-    __device__ __forceinline__ void vload(T (&x)[NV], const T* src, int len) {
-#pragma unroll
-        for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; x[q] = (i < len) ? src[i] : (T)0; }
-    }
-    __device__ __forceinline__ void vstore(const T (&x)[NV], T* dst, int lo, int len) {
-#pragma unroll
-        for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; if (i >= lo && i < len) dst[i] = x[q]; }
-    }
-    __device__ __forceinline__ T vsel(const T (&x)[NV], int q) { // q is warp-uniform
-        T r = x[0];
-#pragma unroll
-        for (int b = 1; b < NV; b++) if (q == b) r = x[b];
-        return r;
-    }
+    // ---- triangular sweeps on a vector held in shared memory. Deliberately the most compact form (one broadcast
+    // load + one FMA per pivot, ~15 instructions of loop body): with sixteen warps in sixteen different phases the
+    // instruction cache, not the length of the dependency chain, decides the speed of these loops. (A
+    // register-resident variant that advances four pivots per shuffle round is kept under experiments/; it halves
+    // the chain but quadruples the code and lost 25% end to end.)
 
-    // Triangular sweeps. FOUR pivots advance per step: their current values are broadcast with four independent
-    // shuffles, every lane solves the 4x4 diagonal block redundantly (6 uniform loads, 3 dependent FMAs), then applies
-    // the four columns to its own rows. Per element the subtractions happen in exactly the order of the one-pivot
-    // recurrence, so the arithmetic equals the scalar substitution; only the shuffle->FMA chain is 4x shorter.
-    // Blocks are 4-aligned and 32 is a multiple of 4, so a block never straddles two register segments.
-
-    // x <- L^-1 x restricted to rows >= rlo (rows < rlo already hold the solution); ascending pivots
-    // (reference forward substitutions: factorization.c:86-92, auxiliary.c:334-337).
-    __device__ __forceinline__ void forward_sweep(T (&x)[NV], int rlo, int len) {
+    // x <- L^-1 x restricted to rows >= rlo (rows < rlo already hold the solution); ascending pivots, the order of
+    // the reference's forward substitutions (factorization.c:86-92, auxiliary.c:334-337).
+    __device__ __forceinline__ void forward_sweep(T* x, int rlo, int len) {
         const T* Lp = L();
-        const T* Lrow[NV]; // start of this lane's rows
-#pragma unroll
-        for (int q = 0; q < NV; q++) Lrow[q] = Lp + loff(lane + 32 * q);
-        int j = 0;
-        for (; j + 3 < len; j += 4) {
-            const int l0 = j & 31;
-            const T* R1 = Lp + loff(j + 1); // rows j+1..j+3 of the factor (diagonal block)
-            const T xs = vsel(x, j >> 5);
-            const T a0 = __shfl_sync(FULL, xs, l0), a1 = __shfl_sync(FULL, xs, l0 + 1);
-            const T a2 = __shfl_sync(FULL, xs, l0 + 2), a3 = __shfl_sync(FULL, xs, l0 + 3);
-            const T* R2 = R1 + (j + 1);
-            const T* R3 = R2 + (j + 2);
-            const T y0 = a0;
-            const T y1 = (j + 1 >= rlo) ? a1 - R1[j] * y0 : a1;
-            const T y2 = (j + 2 >= rlo) ? (a2 - R2[j] * y0) - R2[j + 1] * y1 : a2;
-            const T y3 = (j + 3 >= rlo) ? ((a3 - R3[j] * y0) - R3[j + 1] * y1) - R3[j + 2] * y2 : a3;
-            const int dl0 = lane - l0;
-            const T mine = dl0 == 1 ? y1 : (dl0 == 2 ? y2 : y3);
-            const bool owner = dl0 >= 1 && dl0 <= 3;
-#pragma unroll
-            for (int q2 = 0; q2 < NV; q2++) {
-                const int i = lane + 32 * q2;
-                if (owner && q2 == (j >> 5)) x[q2] = mine;
-                if (i > j + 3 && i >= rlo && i < len) {
-                    const T* Li = Lrow[q2] + j;
-                    x[q2] = (((x[q2] - Li[0] * y0) - Li[1] * y1) - Li[2] * y2) - Li[3] * y3;
-                }
+        if (rlo > 0) { // rows >= rlo first absorb the solved prefix: independent per row
+            for (int i = rlo + lane; i < len; i += 32) {
+                const T* Li = Lp + loff(i);
+                T s = x[i];
+                for (int j = 0; j < rlo; j++) s -= Li[j] * x[j];
+                x[i] = s;
             }
+            __syncwarp();
         }
-        for (; j < len - 1; j++) {
-            const T xj = __shfl_sync(FULL, vsel(x, j >> 5), j & 31);
-#pragma unroll
-            for (int q2 = 0; q2 < NV; q2++) {
-                const int i = lane + 32 * q2;
-                if (i > j && i >= rlo && i < len) x[q2] -= Lrow[q2][j] * xj;
-            }
+        for (int j = rlo; j < len - 1; j++) {
+            const T xj = x[j];
+            for (int i = j + 1 + lane; i < len; i += 32) x[i] -= Lp[loff(i) + j] * xj;
+            __syncwarp();
         }
     }
     // x <- L^-T x ; descending pivots (auxiliary.c:343-352, 363-370). Row j of the packed factor is contiguous.
-    __device__ __forceinline__ void backward_sweep(T (&x)[NV], int len) {
-        const T* Lp = L();
-        int j = len - 1;
-        for (; j >= 1 && (j & 3) != 3; j--) { // peel down to a 4-aligned block boundary
-            const T xj = __shfl_sync(FULL, vsel(x, j >> 5), j & 31);
-            const T* Lj = Lp + loff(j);
-#pragma unroll
-            for (int q2 = 0; q2 < NV; q2++) {
-                const int i = lane + 32 * q2;
-                if (i < j) x[q2] -= Lj[i] * xj;
-            }
-        }
-        for (; j >= 3; j -= 4) { // rows j, j-1, j-2, j-3
-            const int l0 = j & 31;
-            const T xs = vsel(x, j >> 5);
-            const T a0 = __shfl_sync(FULL, xs, l0), a1 = __shfl_sync(FULL, xs, l0 - 1);
-            const T a2 = __shfl_sync(FULL, xs, l0 - 2), a3 = __shfl_sync(FULL, xs, l0 - 3);
-            const T* R0 = Lp + loff(j);
-            const T* R1 = R0 - (j - 1);
-            const T* R2 = R1 - (j - 2);
-            const T* R3 = R2 - (j - 3);
-            const T y0 = a0;
-            const T y1 = a1 - R0[j - 1] * y0;
-            const T y2 = (a2 - R0[j - 2] * y0) - R1[j - 2] * y1;
-            const T y3 = ((a3 - R0[j - 3] * y0) - R1[j - 3] * y1) - R2[j - 3] * y2;
-            const int dl0 = l0 - lane;
-            const T mine = dl0 == 1 ? y1 : (dl0 == 2 ? y2 : y3);
-            const bool owner = dl0 >= 1 && dl0 <= 3;
-#pragma unroll
-            for (int q2 = 0; q2 < NV; q2++) {
-                const int i = lane + 32 * q2;
-                if (owner && q2 == (j >> 5)) x[q2] = mine;
-                if (i < j - 3) x[q2] = (((x[q2] - R0[i] * y0) - R1[i] * y1) - R2[i] * y2) - R3[i] * y3;
-            }
+    __device__ __forceinline__ void backward_sweep(T* x, int len) {
+        const T* Lj = L() + loff(len - 1);
+        for (int j = len - 1; j > 0; j--) {
+            const T xj = x[j];
+            for (int i = lane; i < j; i += 32) x[i] -= Lj[i] * xj;
+            __syncwarp();
+            Lj -= j - 1; // loff(j-1) = loff(j) - (j-1)
         }
     }
 
@@ -294,21 +228,15 @@ struct Warp {
                 if ((lane & (32 / ROWB - 1)) == 0 && j < kk) Lk[j] = tot;
             }
             __syncwarp();
-            // l <- L^-1 l in registers, then l <- D^-1 l ; d -= l' D l
-            T lv[NV];
-            vload(lv, Lk, kk);
-            forward_sweep(lv, 0, kk);
+            // l <- L^-1 l, then l <- D^-1 l ; d -= l' D l
+            forward_sweep(Lk, 0, kk);
             const T* Dp = D();
             T acc = 0;
-#pragma unroll
-            for (int q = 0; q < NV; q++) {
-                const int i = lane + 32 * q;
-                if (i < kk) {
-                    const T t = lv[q];
-                    const T qd = t / Dp[i];
-                    Lk[i] = qd;
-                    acc += t * qd;
-                }
+            for (int i = lane; i < kk; i += 32) {
+                const T t = Lk[i];
+                const T qd = t / Dp[i];
+                Lk[i] = qd;
+                acc += t * qd;
             }
             d -= warp_sum(acc);
             if (d < a.st.sing_tol || kk >= a.n) { // ns_active == 0 on this path (soft constraints not in kernel yet)
@@ -426,7 +354,6 @@ struct Warp {
         const int kk = k, r = reuse;
         T* xp = xl();
         const T* da = dact();
-        T xv[NV];
         if (kk - r <= 2) {
             // one or two new rows (the common case after an add): one warp-wide dot product per row
             for (int i = r; i < kk; i++) {
@@ -437,32 +364,22 @@ struct Warp {
                 if (lane == 0) xp[i] = -da[i] - acc;
                 __syncwarp();
             }
-            vload(xv, xp, kk);
         } else {
-#pragma unroll
-            for (int q = 0; q < NV; q++) {
-                const int i = lane + 32 * q;
-                xv[q] = (i < kk) ? (i >= r ? -da[i] : xp[i]) : (T)0;
-            }
-            forward_sweep(xv, r, kk);
-            vstore(xv, xp, r, kk);
+            for (int i = r + lane; i < kk; i += 32) xp[i] = -da[i];
+            __syncwarp();
+            forward_sweep(xp, r, kk);
         }
-        // z = D^-1 x (kept in zldl for rows >= r as the reference does), then lam* <- L^-T z in registers
+        // z = D^-1 x (kept in zldl for rows >= r as the reference does), then lam* <- L^-T z
         T* z = zl();
+        T* ls = lams();
         const T* Dp = D();
-        T zv[NV];
-#pragma unroll
-        for (int q = 0; q < NV; q++) {
-            const int i = lane + 32 * q;
-            zv[q] = 0;
-            if (i < kk) {
-                if (i >= r) { zv[q] = xv[q] / Dp[i]; z[i] = zv[q]; }
-                else zv[q] = z[i];
-            }
+        for (int i = lane; i < kk; i += 32) {
+            T zi;
+            if (i >= r) { zi = xp[i] / Dp[i]; z[i] = zi; } else zi = z[i];
+            ls[i] = zi;
         }
-        backward_sweep(zv, kk);
-        vstore(zv, lams(), 0, kk);
         __syncwarp();
+        backward_sweep(ls, kk);
         reuse = kk;
     }
 
@@ -470,16 +387,14 @@ struct Warp {
     __device__ __forceinline__ void singular_direction() {
         const int s = sing;
         const T* Ls = L() + loff(s);
-        T pv[NV];
-#pragma unroll
-        for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; pv[q] = (i < s) ? -Ls[i] : (T)0; }
-        backward_sweep(pv, s);
-        const bool flip = sense()[WS()[s]] & B_LOWER;
         T* ls = lams();
-#pragma unroll
-        for (int q = 0; q < NV; q++) {
-            const int i = lane + 32 * q;
-            if (i <= s) { const T val = (i == s) ? (T)1 : pv[q]; ls[i] = flip ? -val : val; }
+        for (int i = lane; i < s; i += 32) ls[i] = -Ls[i];
+        __syncwarp();
+        backward_sweep(ls, s);
+        const bool flip = sense()[WS()[s]] & B_LOWER;
+        for (int i = lane; i <= s; i += 32) {
+            const T val = (i == s) ? (T)1 : ls[i];
+            ls[i] = flip ? -val : val;
         }
         __syncwarp();
     }
@@ -726,19 +641,10 @@ struct Warp {
             if (lane == 0) xp[i] = part - dact()[i];
         }
         __syncwarp();
-        {
-            T rv[NV];
-            vload(rv, xp, kk);
-            forward_sweep(rv, 0, kk);
-#pragma unroll
-            for (int q = 0; q < NV; q++) {
-                const int i = lane + 32 * q;
-                if (i < kk) { rv[q] = rv[q] / D()[i]; zl()[i] = rv[q]; }
-            }
-            backward_sweep(rv, kk);
-            vstore(rv, xp, 0, kk);
-            __syncwarp();
-        }
+        forward_sweep(xp, 0, kk);
+        for (int i = lane; i < kk; i += 32) { const T zi = xp[i] / D()[i]; zl()[i] = zi; xp[i] = zi; }
+        __syncwarp();
+        backward_sweep(xp, kk);
         for (int i = lane; i < kk; i += 32) lams()[i] += xp[i];
         T acc[NG][V];
 #pragma unroll
