@@ -1,0 +1,85 @@
+"""Batch sharding across GPUs.
+
+Problems are independent, so the data path has NO collective: every rank solves a contiguous block of the batch on
+its own GPU. torch.distributed is used only as transport around the solve -- scatter of the packed problem slabs
+from the rank that owns the host data, gather of the small result arrays back to it. With ``backend="nccl"`` the
+buffers are device tensors (NVLink / NVSwitch); with ``backend="gloo"`` the same code runs on CPU tensors, which is
+how the partitioning and the scatter / gather plumbing are tested without GPUs (tests/test_sharding.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import numpy as np
+
+
+def partition(N: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous, balanced blocks: the first ``N % world`` ranks get one extra problem."""
+    base, extra = divmod(N, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def partition_by_cost(costs: Sequence[float], world: int) -> list[np.ndarray]:
+    """Mixed-size batches: longest-processing-time-first on an estimated cost (e.g. n^2 m) so that every rank gets
+    the same mix. Returns, per rank, the indices it owns (ascending)."""
+    order = np.argsort(-np.asarray(costs, dtype=np.float64), kind="stable")
+    load = np.zeros(world)
+    owner = np.empty(len(costs), dtype=np.int64)
+    for i in order:
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += costs[i]
+    return [np.nonzero(owner == r)[0] for r in range(world)]
+
+
+def scatter_solve_gather(arrays: dict | None, n: int, m: int, ms: int, solve_local: Callable[[dict], dict], src: int = 0,
+                         device=None) -> dict | None:
+    """Rank ``src`` holds the whole batch (dict of torch tensors H, f, A, bupper, blower with leading dim N); every
+    rank receives its block, runs ``solve_local`` on it and the results (x, lam, fval, exitflag, iter) are gathered
+    back on ``src``. Other ranks pass ``arrays=None`` and get ``None`` back."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    meta = [None]
+    if rank == src:
+        meta = [(int(arrays["H"].shape[0]), str(arrays["H"].dtype))]
+    dist.broadcast_object_list(meta, src=src)
+    N = meta[0][0]
+    blocks = partition(N, world)
+    lo, hi = blocks[rank]
+    dev = device if device is not None else (arrays["H"].device if rank == src else torch.device("cpu"))
+    mA = m - ms
+    shapes = {"H": (n, n), "f": (n,), "A": (mA, n), "bupper": (m,), "blower": (m,)}
+    local = {}
+    for key, shp in shapes.items():
+        recv = torch.empty((hi - lo,) + shp, dtype=torch.float64, device=dev)
+        if rank == src:
+            chunks = [arrays[key][a:b].contiguous().to(dev) for a, b in blocks]
+            # scatter needs equally sized chunks: pad the short ones, receivers trim
+            width = max(b - a for a, b in blocks)
+            padded = [torch.cat([c, c.new_zeros((width - c.shape[0],) + shp)]) if c.shape[0] < width else c for c in chunks]
+            buf = torch.empty((width,) + shp, dtype=torch.float64, device=dev)
+            dist.scatter(buf, padded, src=src)
+        else:
+            width = max(b - a for a, b in blocks)
+            buf = torch.empty((width,) + shp, dtype=torch.float64, device=dev)
+            dist.scatter(buf, None, src=src)
+        recv.copy_(buf[: hi - lo])
+        local[key] = recv
+    res = solve_local(local)
+    out = {} if rank == src else None
+    width = max(b - a for a, b in blocks)
+    for key in ("x", "lam", "fval", "exitflag", "iter"):
+        t = res[key]
+        pad = t.new_zeros((width,) + tuple(t.shape[1:]))
+        pad[: t.shape[0]] = t
+        gathered = [torch.empty_like(pad) for _ in range(world)] if rank == src else None
+        dist.gather(pad, gathered, dst=src)
+        if rank == src:
+            out[key] = torch.cat([g[: b - a] for g, (a, b) in zip(gathered, blocks)])
+    return out
