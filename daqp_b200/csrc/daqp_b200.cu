@@ -183,7 +183,7 @@ struct Carver {
 template <typename T>
 static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
     size_t e = (size_t)n * ldm + (size_t)m * ldn + 3 * (size_t)ldm + (size_t)n * (n + 1) / 2 + n;
-    return e * sizeof(T) + ldm + sizeof(int) + 64; // + sense bytes + setup flag + alignment slack
+    return e * sizeof(T) + (size_t)n * ldm * sizeof(float) + ldm + sizeof(int) + 64; // + fp32 Mt + sense + flag + slack
 }
 
 template <typename T, int NV>
@@ -231,12 +231,16 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     if (rc) return rc;
 
     const DevSettings<T> st = to_dev_settings<T>(settings);
+    int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
+    if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
+    const bool screening = sizeof(T) == 8 && !(tune & 2) && ldm <= 256;
     for (int p0 = 0; p0 < N; p0 += chunk) {
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);
         int* counters = cv.take<int>(64);
         T* Mt = cv.take<T>((size_t)P * n * ldm);
         T* Mr = cv.take<T>((size_t)P * m * ldn);
+        float* Mt32 = screening ? cv.take<float>((size_t)P * n * ldm) : nullptr;
         T* du = cv.take<T>((size_t)P * ldm);
         T* dl = cv.take<T>((size_t)P * ldm);
         T* sc = cv.take<T>((size_t)P * ldm);
@@ -258,7 +262,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         sa.H = dH + (size_t)p0 * n * n; sa.f = df ? df + (size_t)p0 * n : nullptr; sa.A = dA + (size_t)p0 * mA * n;
         sa.bupper = dbu + (size_t)p0 * m; sa.blower = dbl + (size_t)p0 * m;
         sa.sense_in = dsense ? dsense + (size_t)p0 * m : nullptr;
-        sa.Mt = Mt; sa.Mr = Mr; sa.dupper = du; sa.dlower = dl; sa.scaling = sc; sa.Rinv = Ri; sa.v = vv;
+        sa.Mt = Mt; sa.Mr = Mr; sa.Mt32 = Mt32; sa.dupper = du; sa.dlower = dl; sa.scaling = sc; sa.Rinv = Ri; sa.v = vv;
         sa.sense = sense8; sa.setup_flag = sflag;
         sa.x = dx + (size_t)p0 * n; sa.lam = dlam ? dlam + (size_t)p0 * m : nullptr; sa.fval = dfval + p0;
         sa.exitflag = dflag + p0; sa.iter = diter + p0;
@@ -280,7 +284,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         CK(cudaEventRecord(ev.e1, stream));
 
         la.P = P;
-        la.Mt = Mt; la.Mr = Mr; la.dupper = du; la.dlower = dl; la.scaling = sc; la.Rinv = Ri;
+        la.Mt = Mt; la.Mr = Mr; la.Mt32 = Mt32; la.dupper = du; la.dlower = dl; la.scaling = sc; la.Rinv = Ri;
         la.v = df ? vv : nullptr; la.sense = sense8; la.setup_flag = sflag;
         la.x = sa.x; la.lam = sa.lam; la.fval = sa.fval; la.exitflag = sa.exitflag; la.iter = sa.iter;
         la.ws_out = (diag && diag->ws) ? diag->ws + (size_t)p0 * cap : nullptr;
@@ -288,8 +292,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.counts_out = (diag && diag->counts) ? diag->counts + 4 * (size_t)p0 : nullptr;
         la.sense_out = (diag && diag->sense) ? diag->sense + (size_t)p0 * ldm : nullptr;
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
-        la.tune = 0; // experiment knob: 1 = bulk L2 prefetch of the streamed matrix ahead of the scan
-        if (const char* tenv = getenv("DAQP_B200_TUNE")) la.tune = atoi(tenv);
+        la.tune = tune;
         {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
             const size_t smem = smem_solve_w * w_solve;

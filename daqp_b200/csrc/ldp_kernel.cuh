@@ -33,11 +33,13 @@ struct LdpArgs {
     int P, n, m, ms, ldm, ldn, cap;
     // shared-memory layout of one warp, in elements of T from the warp's base (host-computed, see ldp_layout)
     int oD, olamA, olamB, oxl, ozl, odact, ou, oWS /* in ints */, osense /* in bytes */, ocnt /* in ints */;
+    int ou32; /* float copy of u for the screening scan, in floats from the warp's base */
     unsigned per_warp_bytes;
     // per-problem byte strides of the global arrays
-    unsigned sMt, sMr, sVec, sRinv, sv;
+    unsigned sMt, sMr, sVec, sRinv, sv, sMt32;
     const T* Mt;              // [P][n][ldm]
     const T* Mr;              // [P][m][ldn]
+    const float* Mt32;        // [P][n][ldm] fp32 copy of Mt for the screening scan (nullptr: always scan in T)
     const T* dupper;          // [P][ldm]
     const T* dlower;          // [P][ldm]
     const T* scaling;         // [P][ldm]
@@ -77,6 +79,8 @@ inline size_t ldp_layout(LdpArgs<T>& a) {
     a.oWS = (int)(bytes / sizeof(int)); bytes += (size_t)cap * sizeof(int);
     a.ocnt = (int)(bytes / sizeof(int)); bytes += 4 * sizeof(int);
     a.osense = (int)bytes; bytes += (size_t)round_up(a.m, 4);
+    bytes = (bytes + 3) / 4 * 4;
+    a.ou32 = (int)(bytes / sizeof(float)); bytes += (size_t)(round_up(a.n, 4) + U_PAD) * sizeof(float);
     bytes = (bytes + 15) / 16 * 16;
     a.per_warp_bytes = (unsigned)bytes;
     a.sMt = (unsigned)((size_t)a.n * a.ldm * sizeof(T));
@@ -84,6 +88,7 @@ inline size_t ldp_layout(LdpArgs<T>& a) {
     a.sVec = (unsigned)((size_t)a.ldm * sizeof(T));
     a.sRinv = (unsigned)((size_t)a.n * (a.n + 1) / 2 * sizeof(T));
     a.sv = (unsigned)((size_t)a.n * sizeof(T));
+    a.sMt32 = (unsigned)((size_t)a.n * a.ldm * sizeof(float));
     return bytes;
 }
 
@@ -124,6 +129,7 @@ struct Warp {
     __device__ __forceinline__ T* zl() const { return S + a.ozl; }
     __device__ __forceinline__ T* dact() const { return S + a.odact; }
     __device__ __forceinline__ T* u() const { return S + a.ou; }
+    __device__ __forceinline__ float* u32() const { return reinterpret_cast<float*>(S) + a.ou32; }
     __device__ __forceinline__ int* WS() const { return reinterpret_cast<int*>(S) + a.oWS; }
     __device__ __forceinline__ int* cnt() const { return reinterpret_cast<int*>(S) + a.ocnt; }
     __device__ __forceinline__ unsigned char* sense() const { return reinterpret_cast<unsigned char*>(S) + a.osense; }
@@ -136,38 +142,57 @@ struct Warp {
 
     __device__ __forceinline__ void reset() { sing = EMPTY_IND; k = 0; reuse = 0; } // daqp.c:142-146
 
-    // ---- triangular sweeps on a vector held in shared memory. Deliberately the most compact form (one broadcast
-    // load + one FMA per pivot, ~15 instructions of loop body): with sixteen warps in sixteen different phases the
-    // instruction cache, not the length of the dependency chain, decides the speed of these loops. (A
-    // register-resident variant that advances four pivots per shuffle round is kept under experiments/; it halves
-    // the chain but quadruples the code and lost 25% end to end.)
+    // ---- triangular sweeps. The vector lives in NV registers per lane (element i = lane + 32 q in x[q]); one pivot
+    // per step: shuffle-broadcast the pivot value, one predicated FMA per register. No shared-memory round trip and
+    // no __syncwarp inside the recurrence; the loop bodies are branch-free and ~17 instructions (NV = 2), which
+    // matters twice: fewer issue slots, and a hot footprint that stays inside the instruction cache.
+    // Loads of L are unconditional (a lane outside the triangle reads a neighbouring, valid shared-memory word and
+    // discards it through the select), so the compiler emits no divergence bookkeeping.
+    __device__ __forceinline__ void vload(T (&x)[NV], const T* src, int len) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; x[q] = (i < len) ? src[i] : (T)0; }
+    }
+    __device__ __forceinline__ void vstore(const T (&x)[NV], T* dst, int lo, int len) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; if (i >= lo && i < len) dst[i] = x[q]; }
+    }
+    __device__ __forceinline__ T pivot_value(const T (&x)[NV], int j) { // j is warp-uniform
+        T src = x[0];
+#pragma unroll
+        for (int b = 1; b < NV; b++) src = sel((j >> 5) == b, x[b], src);
+        return __shfl_sync(FULL, src, j & 31);
+    }
 
     // x <- L^-1 x restricted to rows >= rlo (rows < rlo already hold the solution); ascending pivots, the order of
     // the reference's forward substitutions (factorization.c:86-92, auxiliary.c:334-337).
-    __device__ __forceinline__ void forward_sweep(T* x, int rlo, int len) {
-        const T* Lp = L();
-        if (rlo > 0) { // rows >= rlo first absorb the solved prefix: independent per row
-            for (int i = rlo + lane; i < len; i += 32) {
-                const T* Li = Lp + loff(i);
-                T s = x[i];
-                for (int j = 0; j < rlo; j++) s -= Li[j] * x[j];
-                x[i] = s;
-            }
-            __syncwarp();
+    __device__ __forceinline__ void forward_sweep(T (&x)[NV], int rlo, int len) {
+        const T* col[NV]; // &L[i][0] for this lane's rows; advanced by one column per step
+        bool valid[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const int i = lane + 32 * q;
+            valid[q] = i >= rlo && i < len;
+            col[q] = L() + loff(min(i, a.cap - 1)); // clamp: lanes without a row still read inside the factor
         }
-        for (int j = rlo; j < len - 1; j++) {
-            const T xj = x[j];
-            for (int i = j + 1 + lane; i < len; i += 32) x[i] -= Lp[loff(i) + j] * xj;
-            __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < len - 1; j++) {
+            const T xj = pivot_value(x, j);
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const T lij = *col[q];
+                col[q]++;
+                x[q] = sel(valid[q] && lane + 32 * q > j, x[q] - lij * xj, x[q]);
+            }
         }
     }
     // x <- L^-T x ; descending pivots (auxiliary.c:343-352, 363-370). Row j of the packed factor is contiguous.
-    __device__ __forceinline__ void backward_sweep(T* x, int len) {
-        const T* Lj = L() + loff(len - 1);
+    __device__ __forceinline__ void backward_sweep(T (&x)[NV], int len) {
+        const T* Lj = L() + loff(len - 1) + lane;
+#pragma unroll 1
         for (int j = len - 1; j > 0; j--) {
-            const T xj = x[j];
-            for (int i = lane; i < j; i += 32) x[i] -= Lj[i] * xj;
-            __syncwarp();
+            const T xj = pivot_value(x, j);
+#pragma unroll
+            for (int q = 0; q < NV; q++) x[q] = sel(lane + 32 * q < j, x[q] - Lj[32 * q] * xj, x[q]);
             Lj -= j - 1; // loff(j-1) = loff(j) - (j-1)
         }
     }
@@ -228,15 +253,21 @@ struct Warp {
                 if ((lane & (32 / ROWB - 1)) == 0 && j < kk) Lk[j] = tot;
             }
             __syncwarp();
-            // l <- L^-1 l, then l <- D^-1 l ; d -= l' D l
-            forward_sweep(Lk, 0, kk);
+            // l <- L^-1 l in registers, then l <- D^-1 l ; d -= l' D l
+            T lv[NV];
+            vload(lv, Lk, kk);
+            forward_sweep(lv, 0, kk);
             const T* Dp = D();
             T acc = 0;
-            for (int i = lane; i < kk; i += 32) {
-                const T t = Lk[i];
-                const T qd = t / Dp[i];
-                Lk[i] = qd;
-                acc += t * qd;
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const int i = lane + 32 * q;
+                if (i < kk) {
+                    const T t = lv[q];
+                    const T qd = t / Dp[i];
+                    Lk[i] = qd;
+                    acc += t * qd;
+                }
             }
             d -= warp_sum(acc);
             if (d < a.st.sing_tol || kk >= a.n) { // ns_active == 0 on this path (soft constraints not in kernel yet)
@@ -354,6 +385,7 @@ struct Warp {
         const int kk = k, r = reuse;
         T* xp = xl();
         const T* da = dact();
+        T xv[NV];
         if (kk - r <= 2) {
             // one or two new rows (the common case after an add): one warp-wide dot product per row
             for (int i = r; i < kk; i++) {
@@ -364,22 +396,32 @@ struct Warp {
                 if (lane == 0) xp[i] = -da[i] - acc;
                 __syncwarp();
             }
+            vload(xv, xp, kk);
         } else {
-            for (int i = r + lane; i < kk; i += 32) xp[i] = -da[i];
-            __syncwarp();
-            forward_sweep(xp, r, kk);
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const int i = lane + 32 * q;
+                xv[q] = (i < kk) ? (i >= r ? -da[i] : xp[i]) : (T)0;
+            }
+            forward_sweep(xv, r, kk);
+            vstore(xv, xp, r, kk);
         }
         // z = D^-1 x (kept in zldl for rows >= r as the reference does), then lam* <- L^-T z
         T* z = zl();
-        T* ls = lams();
         const T* Dp = D();
-        for (int i = lane; i < kk; i += 32) {
-            T zi;
-            if (i >= r) { zi = xp[i] / Dp[i]; z[i] = zi; } else zi = z[i];
-            ls[i] = zi;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const int i = lane + 32 * q;
+            T zi = 0;
+            if (i < kk) {
+                if (i >= r) { zi = xv[q] / Dp[i]; z[i] = zi; }
+                else zi = z[i];
+            }
+            xv[q] = zi;
         }
+        backward_sweep(xv, kk);
+        vstore(xv, lams(), 0, kk);
         __syncwarp();
-        backward_sweep(ls, kk);
         reuse = kk;
     }
 
@@ -387,14 +429,16 @@ struct Warp {
     __device__ __forceinline__ void singular_direction() {
         const int s = sing;
         const T* Ls = L() + loff(s);
-        T* ls = lams();
-        for (int i = lane; i < s; i += 32) ls[i] = -Ls[i];
-        __syncwarp();
-        backward_sweep(ls, s);
+        T pv[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; pv[q] = (i < s) ? -Ls[i] : (T)0; }
+        backward_sweep(pv, s);
         const bool flip = sense()[WS()[s]] & B_LOWER;
-        for (int i = lane; i <= s; i += 32) {
-            const T val = (i == s) ? (T)1 : ls[i];
-            ls[i] = flip ? -val : val;
+        T* ls = lams();
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const int i = lane + 32 * q;
+            if (i <= s) { const T val = (i == s) ? (T)1 : pv[q]; ls[i] = flip ? -val : val; }
         }
         __syncwarp();
     }
@@ -472,7 +516,7 @@ struct Warp {
             const int c = V * (lane + 32 * g);
             if (c < a.ldn) {
 #pragma unroll
-                for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; part += acc[g][e] * acc[g][e]; }
+                for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
             }
         }
         fval = warp_sum(part); // soft_slack == 0 on this path
@@ -556,10 +600,117 @@ struct Warp {
         }
     }
 
+    // ---- fp32 SCREENING of the feasibility scan (T = double only).
+    // The scan only has to name the most violated row, not its value. A float copy of the matrix (half the bytes, and
+    // small enough that the resident problems' copies fit L2) gives every slack with a rigorous error bound
+    //   |s32 - s64| <= delta = 1.01 (n+3) 2^-24 |u|_2        (rows are normalised to unit 2-norm; Cauchy-Schwarz)
+    // so: a row whose s32 - delta >= threshold cannot be a candidate; if exactly one candidate lies within 2 delta of
+    // the smallest s32 and it is below the threshold by more than delta, it IS the fp64 argmin. Anything ambiguous
+    // (near-ties, rows within delta of the threshold that could win) returns -2 and the caller runs the fp64 scan, so
+    // the selected row is always the one the fp64 scan selects.
+    template <int SG, int UN>
+    __device__ __forceinline__ int scan_screen() {
+        constexpr int GR = 128; // rows per group: one float4 per lane
+        const uint64_t pol = (a.tune & 4) ? policy_evict_first() : policy_evict_last();
+        const int r0 = 4 * lane;
+        float acc[SG][4];
+        bool own[SG];
+#pragma unroll
+        for (int g = 0; g < SG; g++) {
+            own[g] = r0 + g * GR < a.ldm;
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[g][e] = 0.f;
+        }
+        float buf[UN][SG][4];
+        const char* col0 = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + (size_t)r0 * sizeof(float);
+        const unsigned cstride = (unsigned)a.ldm * (unsigned)sizeof(float), clast = (unsigned)(a.n - 1) * cstride;
+        unsigned coff = 0;
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+#pragma unroll
+            for (int g = 0; g < SG; g++) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) buf[i][g][e] = 0.f;
+                if (own[g]) ldg_vec_hint_ordered<float>(reinterpret_cast<const float*>(col0 + coff) + g * GR, buf[i][g], pol);
+            }
+            coff = min(coff + cstride, clast);
+        }
+        const float* up = u32();
+        for (int c = 0; c < a.n; c += UN) {
+#pragma unroll
+            for (int i = 0; i < UN; i++) {
+                const float uc = up[c + i]; // zero for c + i >= n
+                const float* cp = reinterpret_cast<const float*>(col0 + coff);
+#pragma unroll
+                for (int g = 0; g < SG; g++) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[g][e] += buf[i][g][e] * uc;
+                    if (own[g]) ldg_vec_hint_ordered<float>(cp + g * GR, buf[i][g], pol);
+                }
+                coff = min(coff + cstride, clast);
+            }
+        }
+        // candidates in double from the float products; track the best and the runner-up among "possible" candidates
+        const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * sqrt((double)fval);
+        const double ep = -(double)a.st.primal_tol;
+        const uint64_t polk = policy_evict_last();
+        const unsigned char* se = sense();
+        double best = 1e300, second = 1e300;
+        int key = INT_MAX;
+        bool best_sure = false;
+#pragma unroll
+        for (int g = 0; g < SG; g++) {
+            const int rr = r0 + g * GR;
+            if (rr < a.m) {
+                double bu[4], bl[4], bs[4];
+#pragma unroll
+                for (int h = 0; h < 2; h++) { // two 128-bit loads per vector of four doubles
+                    double t2[2];
+                    ldg_vec_hint<double>(reinterpret_cast<const double*>(du()) + rr + 2 * h, t2, polk); bu[2 * h] = t2[0]; bu[2 * h + 1] = t2[1];
+                    ldg_vec_hint<double>(reinterpret_cast<const double*>(dl()) + rr + 2 * h, t2, polk); bl[2 * h] = t2[0]; bl[2 * h + 1] = t2[1];
+                    ldg_vec_hint<double>(reinterpret_cast<const double*>(sc()) + rr + 2 * h, t2, polk); bs[2 * h] = t2[0]; bs[2 * h + 1] = t2[1];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int row = rr + e;
+                    if (row >= a.m) continue;
+                    if (se[row] & (B_ACTIVE + B_IMMUTABLE)) continue;
+                    const double mu = (double)acc[g][e];
+                    const double bound = ep * bs[e];
+#pragma unroll
+                    for (int side = 0; side < 2; side++) {
+                        const double cand = side ? mu - bl[e] : bu[e] - mu;
+                        if (cand - delta < bound) { // possibly a candidate
+                            if (cand < best) { second = best; best = cand; key = 2 * row + side; best_sure = cand + delta < bound; }
+                            else if (cand < second) second = cand;
+                        }
+                    }
+                }
+            }
+        }
+        // warp: argmin of (best, key); runner-up = smallest value that is not the winner
+        double wbest = best;
+        int wkey = key;
+        warp_argmin(wbest, wkey);
+        if (wkey == INT_MAX) return -1; // no row can be violated beyond the tolerance: certain
+        double other = (key == wkey) ? second : best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) other = fmin(other, __shfl_xor_sync(FULL, other, o));
+        const bool sure = __any_sync(FULL, key == wkey && best_sure);
+        if (sure && other - wbest > 2.0 * delta) return wkey;
+        return -2; // ambiguous: decide in fp64
+    }
+
     // ---- a8: Mu = M u for all rows, most-violated inactive row (auxiliary.c:89-152).
     // Returns 2*row + (1 if violated at the lower bound), or -1 when every inactive row is feasible.
     __device__ __forceinline__ int scan_infeasible() {
         count(0);
+        if constexpr (sizeof(T) == 8) {
+            if (a.Mt32 != nullptr && a.ldm <= 256) { // screening in fp32 (two row groups of 128)
+                const int r = scan_screen<2, 6>();
+                if (r != -2) return r;
+            }
+        }
         constexpr int GR = 32 * V; // rows per group (one 128-bit load per lane)
         T best = 0;
         int key = INT_MAX;
@@ -641,10 +792,19 @@ struct Warp {
             if (lane == 0) xp[i] = part - dact()[i];
         }
         __syncwarp();
-        forward_sweep(xp, 0, kk);
-        for (int i = lane; i < kk; i += 32) { const T zi = xp[i] / D()[i]; zl()[i] = zi; xp[i] = zi; }
-        __syncwarp();
-        backward_sweep(xp, kk);
+        {
+            T rv[NV];
+            vload(rv, xp, kk);
+            forward_sweep(rv, 0, kk);
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const int i = lane + 32 * q;
+                if (i < kk) { rv[q] = rv[q] / D()[i]; zl()[i] = rv[q]; }
+            }
+            backward_sweep(rv, kk);
+            vstore(rv, xp, 0, kk);
+            __syncwarp();
+        }
         for (int i = lane; i < kk; i += 32) lams()[i] += xp[i];
         T acc[NG][V];
 #pragma unroll
@@ -804,6 +964,8 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             T* up = w.u();
             for (int i = lane; i < round_up(a.n, VecOf<T>::N) + U_PAD; i += 32) up[i] = 0;
             if (lane < 4) w.cnt()[lane] = 0;
+            float* u32p = w.u32();
+            for (int i = lane; i < round_up(a.n, 4) + U_PAD; i += 32) u32p[i] = 0.f;
         }
         __syncwarp();
         w.reset();
