@@ -100,11 +100,15 @@ __device__ __forceinline__ float sel(bool c, float a, float b) {
     return r;
 }
 
-template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+// The reductions and the fp64 division are deliberately NOT inlined in the solve kernel: each expands to 20-30
+// instructions and is used at a dozen sites; one shared copy keeps the hot code inside the instruction cache.
+template <typename T> __device__ __noinline__ T warp_sum(T v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+__device__ __noinline__ double fdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 
 // Sum B per-lane values across the warp with a transposed butterfly: B/2 + B/4 + ... + 1 exchanges replace B full
 // 5-step reductions. Returns the warp total of value number multi_index<B>(lane); the 32/B lanes that share the
@@ -138,7 +142,7 @@ template <int B> __device__ __forceinline__ int multi_index(int lane) {
 // Lexicographic (value, key) minimum over the warp. Reproduces a sequential "strict <, first index wins" scan
 // (reference auxiliary.c:112,118,139,145,293): the smallest value wins, ties go to the smallest key.
 // Lanes without a candidate pass key = INT_MAX. NaN never enters because candidates are admitted with '<'.
-template <typename T> __device__ __forceinline__ void warp_argmin(T& val, int& key) {
+template <typename T> __device__ __noinline__ void warp_argmin(T& val, int& key) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         T ov = __shfl_xor_sync(FULL, val, o);

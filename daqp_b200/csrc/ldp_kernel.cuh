@@ -117,6 +117,10 @@ struct Warp {
     int lsw;             // which of the two lambda buffers currently is `lam` (the reference swaps pointers)
     T fval;
     int* pst_id; T* pst_lam;
+    // daqp_ldp loop state (daqp.c:7-10), kept across step() calls
+    int iter, tried_repair, cycle_counter;
+    bool do_activate;
+    T best_fval;
 
     __device__ __forceinline__ Warp(const LdpArgs<T>& args) : a(args) {}
 
@@ -264,7 +268,7 @@ struct Warp {
                 const int i = lane + 32 * q;
                 if (i < kk) {
                     const T t = lv[q];
-                    const T qd = t / Dp[i];
+                    const T qd = fdiv(t, Dp[i]);
                     Lk[i] = qd;
                     acc += t * qd;
                 }
@@ -309,8 +313,8 @@ struct Warp {
                 const T pv = z[c];
                 const T Dold = Dp[c + 1];
                 const T dbar = Dold + alpha * pv * pv;
-                const T beta = pv * alpha / dbar;
-                alpha = Dold * alpha / dbar;
+                const T beta = fdiv(pv * alpha, dbar);
+                alpha = fdiv(Dold * alpha, dbar);
                 if (lane == 0) Dp[c] = dbar; // D[c] was consumed one step earlier, before that step's __syncwarp
                 for (int s = t + 1 + lane; s < nu; s += 32) {
                     T* Lrc = Lp + loff(r + s) + c;
@@ -414,7 +418,7 @@ struct Warp {
             const int i = lane + 32 * q;
             T zi = 0;
             if (i < kk) {
-                if (i >= r) { zi = xv[q] / Dp[i]; z[i] = zi; }
+                if (i >= r) { zi = fdiv(xv[q], Dp[i]); z[i] = zi; }
                 else zi = z[i];
             }
             xv[q] = zi;
@@ -459,7 +463,7 @@ struct Warp {
             if (sb & B_LOWER) { if (s < dual_tol) continue; }
             else if (s > -dual_tol) continue;
             const T l = lm[i];
-            const T ac = (sing == EMPTY_IND) ? -l / (s - l) : -l / s;
+            const T ac = fdiv(-l, (sing == EMPTY_IND) ? s - l : s);
             if (ac < best) { best = ac; key = i; }
         }
         warp_argmin(best, key);
@@ -673,18 +677,19 @@ struct Warp {
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int row = rr + e;
-                    if (row >= a.m) continue;
-                    if (se[row] & (B_ACTIVE + B_IMMUTABLE)) continue;
+                    // at most one side of a row can be violated beyond the tolerance (check_bounds guarantees
+                    // bupper >= blower - tol), so the row's candidate is its more violated side
                     const double mu = (double)acc[g][e];
+                    const double cu = bu[e] - mu, cl = mu - bl[e];
+                    const bool lower = cl < cu;
+                    const double cand = lower ? cl : cu;
                     const double bound = ep * bs[e];
-#pragma unroll
-                    for (int side = 0; side < 2; side++) {
-                        const double cand = side ? mu - bl[e] : bu[e] - mu;
-                        if (cand - delta < bound) { // possibly a candidate
-                            if (cand < best) { second = best; best = cand; key = 2 * row + side; best_sure = cand + delta < bound; }
-                            else if (cand < second) second = cand;
-                        }
-                    }
+                    const bool possible = row < a.m && !(se[row] & (B_ACTIVE + B_IMMUTABLE)) && cand - delta < bound;
+                    const bool nb = possible && cand < best;
+                    second = nb ? best : ((possible && cand < second) ? cand : second);
+                    best_sure = nb ? (cand + delta < bound) : best_sure;
+                    key = nb ? 2 * row + (int)lower : key;
+                    best = nb ? cand : best;
                 }
             }
         }
@@ -841,93 +846,95 @@ struct Warp {
     }
 
     // ---- a11: the daqp_ldp state machine (daqp.c:6-108), preceded by the activation daqp_update_ldp runs for a warm
-    // start (utils.c:199-211). Same decisions in the same order as the reference; control flow is arranged so that
-    // the direction solve, the ratio test, the scan and the working-set modification each appear once.
-    // Returns the exit flag (negative setup flag with *iters = 0 when the initial activation fails).
-    __device__ __forceinline__ int solve(bool activate_first, int* iters) {
-        int exitflag = EXIT_ITERLIMIT, iter = 0;
-        int tried_repair = 0, cycle_counter = 0;
-        T best_fval = -1;
+    // start (utils.c:199-211). Same decisions in the same order as the reference, but RESUMABLE: step() executes
+    // exactly one pass of the reference's for-loop and returns, so that the kernel can line all warps of a CTA up at
+    // the top of every iteration (see ldp_solve_kernel). Control flow is arranged so that the direction solve, the
+    // ratio test, the scan and the working-set modification each appear once.
+    static constexpr int RUNNING = 0x7fffffff;
+    __device__ __forceinline__ void begin(bool activate_first) {
+        iter = 0; tried_repair = 0; cycle_counter = 0; best_fval = -1; do_activate = activate_first;
+    }
+    // Returns RUNNING, or the exit flag when the solve is over (iter holds the iteration count; iter == 0 means the
+    // initial activation failed, which the reference reports as a setup failure).
+    __device__ __forceinline__ int step() {
         const T fval_bound = 2 * a.st.fval_bound;
-        bool do_activate = activate_first;
-        for (;;) {
-            if (do_activate) { // end of the previous iteration's refactor / cycle repair, or the warm start
-                do_activate = false;
-                if (iter > 0) reset();
-                const int aflag = activate_constraints();
-                if (iter == 0 && aflag < 0) { *iters = 0; return aflag; }
-            }
-            if (++iter >= a.st.iter_limit) break; // for(iter=1; iter < iter_limit; ++iter)
-            const bool was_singular = sing != EMPTY_IND;
-            if (!was_singular) compute_csp(); else singular_direction();
-            int op = OP_REMOVE, arg = find_blocking();
-            T lamval = 0;
-            bool refined = false, done = false;
-            if (arg < 0) { // no blocking constraint: dual feasible (or, in singular mode, primal infeasible)
-                if (was_singular) { exitflag = EXIT_INFEASIBLE; break; } // daqp.c:88-93
-                compute_primal();
-                if (fval > fval_bound) { exitflag = EXIT_INFEASIBLE; break; }
-                for (;;) {
-                    const int key = scan_infeasible();
-                    if (key >= 0) {
-                        arg = key >> 1;
-                        const int lower = key & 1;
-                        if (lane == 0) { if (lower) sense()[arg] |= B_LOWER; else sense()[arg] &= ~B_LOWER; }
-                        lsw ^= 1; // lam <- lam* : the reference swaps the two pointers (auxiliary.c:159-160)
-                        __syncwarp();
-                        op = OP_ADD;
-                        lamval = lower ? (T)-1 : (T)1;
-                        break;
-                    }
-                    // primal feasible: KKT point unless the factor is ill-conditioned (daqp.c:28-63)
-                    T min_D = (T)1e30;
-                    for (int i = lane; i < k; i += 32) min_D = fmin(min_D, D()[i]);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) min_D = fmin(min_D, __shfl_xor_sync(FULL, min_D, o));
-                    if (k > 2 && tried_repair != 1 && min_D < a.st.refactor_tol) {
-                        tried_repair = 1;
-                        for (int i = lane; i < k; i += 32) {
-                            const int id = WS()[i];
-                            if (lam()[i] >= 0) sense()[id] &= ~B_LOWER; else sense()[id] |= B_LOWER;
-                        }
-                        __syncwarp();
-                        do_activate = true;
-                        break;
-                    }
-                    if (!refined && k > 0 && min_D < a.st.pivot_tol) {
-                        refine_active();
-                        refined = true;
-                        continue; // daqp.c:52-56: scan again after the refinement
-                    }
-                    exitflag = EXIT_OPTIMAL; // soft_slack == 0 on this path, so never SOFT_OPTIMAL
-                    done = true;
+        if (do_activate) { // end of the previous iteration's refactor / cycle repair, or the warm start
+            do_activate = false;
+            if (iter > 0) reset();
+            const int aflag = activate_constraints();
+            if (iter == 0 && aflag < 0) return aflag;
+        }
+        if (++iter >= a.st.iter_limit) return EXIT_ITERLIMIT; // for(iter=1; iter < iter_limit; ++iter)
+        const bool was_singular = sing != EMPTY_IND;
+        if (!was_singular) compute_csp(); else singular_direction();
+        int op = OP_REMOVE, arg = find_blocking();
+        T lamval = 0;
+        bool refined = false;
+        if (arg < 0) { // no blocking constraint: dual feasible (or, in singular mode, primal infeasible)
+            if (was_singular) return EXIT_INFEASIBLE; // daqp.c:88-93
+            compute_primal();
+            if (fval > fval_bound) return EXIT_INFEASIBLE;
+            for (;;) {
+                const int key = scan_infeasible();
+                if (key >= 0) {
+                    arg = key >> 1;
+                    const int lower = key & 1;
+                    if (lane == 0) { if (lower) sense()[arg] |= B_LOWER; else sense()[arg] &= ~B_LOWER; }
+                    lsw ^= 1; // lam <- lam* : the reference swaps the two pointers (auxiliary.c:159-160)
+                    __syncwarp();
+                    op = OP_ADD;
+                    lamval = lower ? (T)-1 : (T)1;
                     break;
                 }
-                if (done) break;
-                if (arg < 0) continue; // refactor requested: handled at the top of the next pass
-            }
-            modify(op, arg, lamval); // the ONE place where the working set changes inside the loop
-            if (op == OP_ADD && !refined) { // cycle guard, daqp.c:67-85 (skipped on the refine path, daqp.c:54-55)
-                if (fval - best_fval < a.st.progress_tol) {
-                    if (cycle_counter++ > a.st.cycle_tol) {
-                        if (tried_repair == 1) { exitflag = EXIT_CYCLE; break; }
-                        tried_repair = 1;
-                        do_activate = true;
-                        cycle_counter = 0;
-                        best_fval = -1;
+                // primal feasible: KKT point unless the factor is ill-conditioned (daqp.c:28-63)
+                T min_D = (T)1e30;
+                for (int i = lane; i < k; i += 32) min_D = fmin(min_D, D()[i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) min_D = fmin(min_D, __shfl_xor_sync(FULL, min_D, o));
+                if (k > 2 && tried_repair != 1 && min_D < a.st.refactor_tol) {
+                    tried_repair = 1;
+                    for (int i = lane; i < k; i += 32) {
+                        const int id = WS()[i];
+                        if (lam()[i] >= 0) sense()[id] &= ~B_LOWER; else sense()[id] |= B_LOWER;
                     }
-                } else {
-                    best_fval = fval;
-                    cycle_counter = 0;
+                    __syncwarp();
+                    do_activate = true; // refactor: handled at the top of the next step
+                    return RUNNING;
                 }
+                if (!refined && k > 0 && min_D < a.st.pivot_tol) {
+                    refine_active();
+                    refined = true;
+                    continue; // daqp.c:52-56: scan again after the refinement
+                }
+                return EXIT_OPTIMAL; // soft_slack == 0 on this path, so never SOFT_OPTIMAL
             }
         }
-        *iters = iter;
-        return exitflag;
+        modify(op, arg, lamval); // the ONE place where the working set changes inside the loop
+        if (op == OP_ADD && !refined) { // cycle guard, daqp.c:67-85 (skipped on the refine path, daqp.c:54-55)
+            if (fval - best_fval < a.st.progress_tol) {
+                if (cycle_counter++ > a.st.cycle_tol) {
+                    if (tried_repair == 1) return EXIT_CYCLE;
+                    tried_repair = 1;
+                    do_activate = true;
+                    cycle_counter = 0;
+                    best_fval = -1;
+                }
+            } else {
+                best_fval = fval;
+                cycle_counter = 0;
+            }
+        }
+        return RUNNING;
     }
 };
 
 // One warp per problem, persistent CTAs pulling problem indices from an atomic queue (iteration counts diverge).
+//
+// Phase alignment: all warps of the CTA meet at ONE block barrier per active-set iteration and then run the same
+// sequence (direction solve -> ratio test -> remove | primal -> scan -> add). Without it sixteen warps sit in sixteen
+// different routines and the SM's instruction cache thrashes (measured: 24 % of all stall samples were
+// "no instruction", icc hit rate 75 %); with it the instruction working set at any moment is one routine. The
+// barrier carries no data -- problems stay independent -- it only keeps the instruction streams together.
 template <typename T, int NV>
 __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant__ LdpArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -940,24 +947,25 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
     w.pst_id = a.pst_id + (size_t)gw * a.cap;
     w.pst_lam = a.pst_lam + (size_t)gw * a.cap;
 
+    bool have = false, exhausted = false;
     for (;;) {
-        int p = 0;
-        if (lane == 0) p = atomicAdd(a.work_counter, 1);
-        p = __shfl_sync(FULL, p, 0);
-        if (p >= a.P) break;
-        w.p = p;
-        const int sflag = a.setup_flag[p];
-        if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) { // finished by the setup kernel
-            if (a.nact_out && lane == 0) a.nact_out[p] = 0;
-            if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = 0;
-            if (a.sense_out)
-                for (int i = lane; i < a.m; i += 32) a.sense_out[(size_t)p * a.ldm + i] = a.sense[(size_t)p * a.ldm + i];
-            continue;
-        }
-
-        w.lsw = 0;
-        w.fval = 0;
-        {
+        // ---- take the next problem off the queue (problems finished by the setup kernel are only passed through)
+        while (!have && !exhausted) {
+            int p = 0;
+            if (lane == 0) p = atomicAdd(a.work_counter, 1);
+            p = __shfl_sync(FULL, p, 0);
+            if (p >= a.P) { exhausted = true; break; }
+            w.p = p;
+            const int sflag = a.setup_flag[p];
+            if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) {
+                if (a.nact_out && lane == 0) a.nact_out[p] = 0;
+                if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = 0;
+                if (a.sense_out)
+                    for (int i = lane; i < a.m; i += 32) a.sense_out[(size_t)p * a.ldm + i] = a.sense[(size_t)p * a.ldm + i];
+                continue;
+            }
+            w.lsw = 0;
+            w.fval = 0;
             const unsigned char* sin = a.sense + (size_t)p * a.ldm;
             unsigned char* se = w.sense();
             for (int i = lane; i < a.m; i += 32) se[i] = sin[i];
@@ -966,13 +974,22 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             if (lane < 4) w.cnt()[lane] = 0;
             float* u32p = w.u32();
             for (int i = lane; i < round_up(a.n, 4) + U_PAD; i += 32) u32p[i] = 0.f;
+            __syncwarp();
+            w.reset();
+            w.begin(sflag == SETUP_SOLVE_ACTIVATE);
+            have = true;
         }
-        __syncwarp();
-        w.reset();
+        // ---- the alignment point; also the termination test (every warp calls it the same number of times)
+        if (a.tune & 8) { // experiment: one block barrier per iteration (phase alignment)
+            if (!__syncthreads_or(have)) break;
+            if (!have) continue;
+        } else if (!have) break;
 
-        int iters = 0;
-        const int exitflag = w.solve(sflag == SETUP_SOLVE_ACTIVATE, &iters);
-        if (iters == 0) {
+        const int exitflag = w.step();
+        if (exitflag == Warp<T, NV>::RUNNING) continue;
+        have = false;
+        const int p = w.p;
+        if (w.iter == 0) {
             // the initial activation failed (utils.c:209-210 -> api.c:69-72): flag only, x untouched
             if (lane == 0) { a.exitflag[p] = exitflag; a.iter[p] = 0; }
         } else {
@@ -1009,7 +1026,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             if (lane == 0) {
                 if (vv) a.fval[p] = (T)0.5 * (w.fval - vnorm);
                 a.exitflag[p] = exitflag;
-                a.iter[p] = iters;
+                a.iter[p] = w.iter;
             }
         }
         if (a.nact_out && lane == 0) a.nact_out[p] = w.k;
