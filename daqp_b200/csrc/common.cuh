@@ -100,6 +100,34 @@ __device__ __forceinline__ float sel(bool c, float a, float b) {
     return r;
 }
 
+// ---- asynchronous global -> shared copies (cp.async / LDGSTS), 16 bytes per lane, lane-private ring slots ----------
+// Every lane copies, and later reads back, only its own 16-byte chunk of a matrix row / column, so the ring needs no
+// barrier at all: cp.async.wait_group is a per-thread wait. The data never occupies registers while in flight, which
+// is what lets a rolled, 30-instruction loop keep 8 columns (or rows) in flight.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// src_bytes = 16 copies, src_bytes = 0 writes zeros without touching global memory
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int src_bytes, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <typename T> __device__ __forceinline__ void lds_vec(unsigned addr, T (&out)[VecOf<T>::N]);
+template <> __device__ __forceinline__ void lds_vec<double>(unsigned addr, double (&out)[2]) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[1]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_vec<float>(unsigned addr, float (&out)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "r"(addr));
+}
+
+// x = (i < j) ? x - l * y : x   as ONE compare plus ONE predicated FMA (the C++ form costs a compare, an FMA and a
+// two-instruction select per double)
+__device__ __forceinline__ void fms_if_lt(double& x, double l, double y, int i, int j) {
+    asm("{\n .reg .pred q;\n setp.lt.s32 q, %3, %4;\n @q fma.rn.f64 %0, %1, %2, %0;\n}" : "+d"(x) : "d"(-l), "d"(y), "r"(i), "r"(j));
+}
+__device__ __forceinline__ void fms_if_lt(float& x, float l, float y, int i, int j) {
+    asm("{\n .reg .pred q;\n setp.lt.s32 q, %3, %4;\n @q fma.rn.f32 %0, %1, %2, %0;\n}" : "+f"(x) : "f"(-l), "f"(y), "r"(i), "r"(j));
+}
+
 // The reductions and the fp64 division are deliberately NOT inlined in the solve kernel: each expands to 20-30
 // instructions and is used at a dozen sites; one shared copy keeps the hot code inside the instruction cache.
 template <typename T> __device__ __noinline__ T warp_sum(T v) {

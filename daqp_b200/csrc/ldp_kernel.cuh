@@ -27,6 +27,7 @@
 namespace dq {
 
 constexpr int U_PAD = 16; // zero entries behind u so that the scan pipeline can run past column n-1
+constexpr int RING = 8;   // depth of the cp.async staging rings (columns of the scan, rows of the active-row passes)
 
 template <typename T>
 struct LdpArgs {
@@ -34,6 +35,7 @@ struct LdpArgs {
     // shared-memory layout of one warp, in elements of T from the warp's base (host-computed, see ldp_layout)
     int oD, olamA, olamB, oxl, ozl, odact, ou, oWS /* in ints */, osense /* in bytes */, ocnt /* in ints */;
     int ou32; /* float copy of u for the screening scan, in floats from the warp's base */
+    int oarena, oscratch; /* byte offsets: cp.async staging ring / reduction scratch (see RING) */
     unsigned per_warp_bytes;
     // per-problem byte strides of the global arrays
     unsigned sMt, sMr, sVec, sRinv, sv, sMt32;
@@ -81,6 +83,14 @@ inline size_t ldp_layout(LdpArgs<T>& a) {
     a.osense = (int)bytes; bytes += (size_t)round_up(a.m, 4);
     bytes = (bytes + 3) / 4 * 4;
     a.ou32 = (int)(bytes / sizeof(float)); bytes += (size_t)(round_up(a.n, 4) + U_PAD) * sizeof(float);
+    bytes = (bytes + 15) / 16 * 16;
+    // staging ring: RING columns of the fp32 matrix (screening scan) or RING rows of the row-major matrix plus the
+    // scratch of the dot-product reduction, whichever is larger
+    a.oarena = (int)bytes;
+    const size_t colb = (size_t)a.ldm * sizeof(float), rowb = (size_t)a.ldn * sizeof(T);
+    const size_t rows_need = RING * rowb + 8 * 33 * sizeof(T);
+    a.oscratch = (int)(bytes + RING * rowb);
+    bytes += (a.ldm <= 256 && RING * colb > rows_need) ? RING * colb : rows_need;
     bytes = (bytes + 15) / 16 * 16;
     a.per_warp_bytes = (unsigned)bytes;
     a.sMt = (unsigned)((size_t)a.n * a.ldm * sizeof(T));
@@ -160,44 +170,46 @@ struct Warp {
 #pragma unroll
         for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; if (i >= lo && i < len) dst[i] = x[q]; }
     }
-    __device__ __forceinline__ T pivot_value(const T (&x)[NV], int j) { // j is warp-uniform
-        T src = x[0];
-#pragma unroll
-        for (int b = 1; b < NV; b++) src = sel((j >> 5) == b, x[b], src);
-        return __shfl_sync(FULL, src, j & 31);
-    }
-
     // x <- L^-1 x restricted to rows >= rlo (rows < rlo already hold the solution); ascending pivots, the order of
-    // the reference's forward substitutions (factorization.c:86-92, auxiliary.c:334-337).
+    // the reference's forward substitutions (factorization.c:86-92, auxiliary.c:334-337). One loop per register
+    // segment of the pivot (so the shuffle source is a fixed register); body = 2 shuffles + per register one shared
+    // load, one compare and one predicated FMA.
     __device__ __forceinline__ void forward_sweep(T (&x)[NV], int rlo, int len) {
-        const T* col[NV]; // &L[i][0] for this lane's rows; advanced by one column per step
-        bool valid[NV];
+        const T* col[NV]; // &L[i][j] for this lane's rows; advanced by one column per step
+        int lim[NV];      // row index, or a value no pivot exceeds for rows that must not be touched
 #pragma unroll
         for (int q = 0; q < NV; q++) {
             const int i = lane + 32 * q;
-            valid[q] = i >= rlo && i < len;
+            lim[q] = (i >= rlo && i < len) ? i : -1;
             col[q] = L() + loff(min(i, a.cap - 1)); // clamp: lanes without a row still read inside the factor
         }
-#pragma unroll 1
-        for (int j = 0; j < len - 1; j++) {
-            const T xj = pivot_value(x, j);
 #pragma unroll
-            for (int q = 0; q < NV; q++) {
-                const T lij = *col[q];
-                col[q]++;
-                x[q] = sel(valid[q] && lane + 32 * q > j, x[q] - lij * xj, x[q]);
+        for (int qp = 0; qp < NV; qp++) {
+            const int jend = min(len - 1, 32 * qp + 32);
+#pragma unroll 1
+            for (int j = 32 * qp; j < jend; j++) {
+                const T xj = __shfl_sync(FULL, x[qp], j & 31);
+#pragma unroll
+                for (int q = qp; q < NV; q++) { // rows above the pivot's segment are already final
+                    fms_if_lt(x[q], *col[q], xj, j, lim[q]);
+                    col[q]++;
+                }
             }
         }
     }
     // x <- L^-T x ; descending pivots (auxiliary.c:343-352, 363-370). Row j of the packed factor is contiguous.
     __device__ __forceinline__ void backward_sweep(T (&x)[NV], int len) {
         const T* Lj = L() + loff(len - 1) + lane;
-#pragma unroll 1
-        for (int j = len - 1; j > 0; j--) {
-            const T xj = pivot_value(x, j);
 #pragma unroll
-            for (int q = 0; q < NV; q++) x[q] = sel(lane + 32 * q < j, x[q] - Lj[32 * q] * xj, x[q]);
-            Lj -= j - 1; // loff(j-1) = loff(j) - (j-1)
+        for (int qp = NV - 1; qp >= 0; qp--) {
+            const int jlo = max(1, 32 * qp);
+#pragma unroll 1
+            for (int j = min(len - 1, 32 * qp + 31); j >= jlo; j--) {
+                const T xj = __shfl_sync(FULL, x[qp], j & 31);
+#pragma unroll
+                for (int q = 0; q <= qp; q++) fms_if_lt(x[q], Lj[32 * q], xj, lane + 32 * q, j);
+                Lj -= j - 1; // loff(j-1) = loff(j) - (j-1)
+            }
         }
     }
 
@@ -227,35 +239,58 @@ struct Warp {
         const int kk = k;
         T* Lk = L() + loff(kk);
         if (kk > 0) {
-            // l_j = M_{WS[j]} . m_add : ROWB rows per batch -> ROWB*NG independent 128-bit loads in flight, then one
-            // transposed butterfly sums all ROWB dot products at once
+            // l_j = M_{WS[j]} . m_add. The active rows stream through the lane-private cp.async ring (RING rows in
+            // flight, rolled loop); per-lane partial products of 8 rows are parked in scratch and summed with a
+            // transposed read (lane = (row, quarter)) instead of 8 full shuffle reductions.
             const int* ws = WS();
-            for (int j0 = 0; j0 < kk; j0 += ROWB) {
-                T tv[ROWB][NG][V];
+            const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + RING * rstride;
+            T* scr = reinterpret_cast<T*>(reinterpret_cast<char*>(S) + a.oscratch);
+            bool okg[NG];
 #pragma unroll
-                for (int b = 0; b < ROWB; b++) {
-                    const int j = min(j0 + b, kk - 1); // clamp keeps the address valid; surplus results are dropped
-                    const T* rowj = reinterpret_cast<const T*>(M + (size_t)ws[j] * rstride);
+            for (int g = 0; g < NG; g++) okg[g] = V * (lane + 32 * g) < a.ldn;
+#pragma unroll 1
+            for (int sl = 0; sl < RING; sl++) {
+                const bool ok = sl < kk;
+                const char* src = M + (size_t)(ok ? ws[sl] : 0) * rstride;
 #pragma unroll
-                    for (int g = 0; g < NG; g++) {
+                for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(ring0 + sl * rstride + 512 * g, src + 512 * g, 16, pol);
+                cp_async_commit();
+            }
+            unsigned slot = ring0;
+#pragma unroll 1
+            for (int j = 0; j < kk; j++) {
+                cp_async_wait<RING - 1>();
+                T pj = 0;
 #pragma unroll
-                        for (int e = 0; e < V; e++) tv[b][g][e] = 0;
-                        if (V * (lane + 32 * g) < a.ldn) ldg_vec_hint<T>(rowj + 32 * V * g, tv[b][g], pol);
+                for (int g = 0; g < NG; g++) {
+                    if (okg[g]) { // a lane without columns in this group has no chunk in the slot
+                        T t[V];
+                        lds_vec<T>(slot + 512 * g, t);
+#pragma unroll
+                        for (int e = 0; e < V; e++) pj += t[e] * mi[g][e];
                     }
                 }
-                T pv[ROWB];
+                scr[(j & 7) * 33 + lane] = pj;
+                const bool ok = j + RING < kk;
+                const char* src = M + (size_t)(ok ? ws[j + RING] : 0) * rstride;
 #pragma unroll
-                for (int b = 0; b < ROWB; b++) {
-                    pv[b] = 0;
-#pragma unroll
-                    for (int g = 0; g < NG; g++)
-#pragma unroll
-                        for (int e = 0; e < V; e++) pv[b] += tv[b][g][e] * mi[g][e];
+                for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(slot + 512 * g, src + 512 * g, 16, pol);
+                cp_async_commit();
+                slot += rstride;
+                if (slot == ring_end) slot = ring0;
+                if ((j & 7) == 7 || j == kk - 1) { // sum the parked partials of rows j0..j
+                    __syncwarp();
+                    const int r8 = lane >> 2, q4 = lane & 3;
+                    const T* pr = scr + r8 * 33 + 8 * q4;
+                    T sum = ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+                    sum += __shfl_xor_sync(FULL, sum, 1);
+                    sum += __shfl_xor_sync(FULL, sum, 2);
+                    const int jr = (j & ~7) + r8;
+                    if (q4 == 0 && jr <= j) Lk[jr] = sum;
+                    __syncwarp();
                 }
-                const T tot = warp_sum_multi<ROWB>(pv, lane);
-                const int j = j0 + multi_index<ROWB>(lane);
-                if ((lane & (32 / ROWB - 1)) == 0 && j < kk) Lk[j] = tot;
             }
+            cp_async_wait<0>();
             __syncwarp();
             // l <- L^-1 l in registers, then l <- D^-1 l ; d -= l' D l
             T lv[NV];
@@ -313,8 +348,9 @@ struct Warp {
                 const T pv = z[c];
                 const T Dold = Dp[c + 1];
                 const T dbar = Dold + alpha * pv * pv;
-                const T beta = fdiv(pv * alpha, dbar);
-                alpha = fdiv(Dold * alpha, dbar);
+                const T rdb = fdiv((T)1, dbar); // one reciprocal for the two quotients of the reference
+                const T beta = pv * alpha * rdb;
+                alpha = Dold * alpha * rdb;
                 if (lane == 0) Dp[c] = dbar; // D[c] was consumed one step earlier, before that step's __syncwarp
                 for (int s = t + 1 + lane; s < nu; s += 32) {
                     T* Lrc = Lp + loff(r + s) + c;
@@ -487,32 +523,48 @@ struct Warp {
         const int* ws = WS();
         const T* ls = lams();
         T acc[NG][V];
+        bool okg[NG];
 #pragma unroll
-        for (int g = 0; g < NG; g++)
+        for (int g = 0; g < NG; g++) {
+            okg[g] = V * (lane + 32 * g) < a.ldn;
 #pragma unroll
             for (int e = 0; e < V; e++) acc[g][e] = 0;
-        for (int i0 = 0; i0 < k; i0 += ROWB) { // ROWB rows per batch: all loads first, then the FMAs in index order
-            T tv[ROWB][NG][V];
-            T li[ROWB];
+        }
+        // active rows stream through the lane-private cp.async ring: RING rows in flight, rolled loop, FMAs in index
+        // order (the order of the reference's accumulation, auxiliary.c:54-68)
+        const int kk = k;
+        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + RING * rstride;
+#pragma unroll 1
+        for (int sl = 0; sl < RING; sl++) {
+            const bool ok = sl < kk;
+            const char* src = M + (size_t)(ok ? ws[sl] : 0) * rstride;
 #pragma unroll
-            for (int b = 0; b < ROWB; b++) {
-                const int i = i0 + b;
-                const T* row = reinterpret_cast<const T*>(M + (size_t)ws[min(i, k - 1)] * rstride);
-                li[b] = (i < k) ? ls[i] : (T)0;
+            for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(ring0 + sl * rstride + 512 * g, src + 512 * g, 16, pol);
+            cp_async_commit();
+        }
+        unsigned slot = ring0;
+#pragma unroll 1
+        for (int i = 0; i < kk; i++) {
+            cp_async_wait<RING - 1>();
+            const T li = ls[i];
 #pragma unroll
-                for (int g = 0; g < NG; g++) {
+            for (int g = 0; g < NG; g++) {
+                if (okg[g]) {
+                    T t[V];
+                    lds_vec<T>(slot + 512 * g, t);
 #pragma unroll
-                    for (int e = 0; e < V; e++) tv[b][g][e] = 0;
-                    if (V * (lane + 32 * g) < a.ldn) ldg_vec_hint<T>(row + 32 * V * g, tv[b][g], pol);
+                    for (int e = 0; e < V; e++) acc[g][e] -= t[e] * li;
                 }
             }
+            const bool ok = i + RING < kk;
+            const char* src = M + (size_t)(ok ? ws[i + RING] : 0) * rstride;
 #pragma unroll
-            for (int b = 0; b < ROWB; b++)
-#pragma unroll
-                for (int g = 0; g < NG; g++)
-#pragma unroll
-                    for (int e = 0; e < V; e++) acc[g][e] -= tv[b][g][e] * li[b];
+            for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(slot + 512 * g, src + 512 * g, 16, pol);
+            cp_async_commit();
+            slot += rstride;
+            if (slot == ring_end) slot = ring0;
         }
+        cp_async_wait<0>();
         T* up = u();
         T part = 0;
 #pragma unroll
@@ -612,7 +664,7 @@ struct Warp {
     // the smallest s32 and it is below the threshold by more than delta, it IS the fp64 argmin. Anything ambiguous
     // (near-ties, rows within delta of the threshold that could win) returns -2 and the caller runs the fp64 scan, so
     // the selected row is always the one the fp64 scan selects.
-    template <int SG, int UN>
+    template <int SG>
     __device__ __forceinline__ int scan_screen() {
         constexpr int GR = 128; // rows per group: one float4 per lane
         const uint64_t pol = (a.tune & 4) ? policy_evict_first() : policy_evict_last();
@@ -625,37 +677,49 @@ struct Warp {
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[g][e] = 0.f;
         }
-        float buf[UN][SG][4];
-        const char* col0 = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + (size_t)r0 * sizeof(float);
-        const unsigned cstride = (unsigned)a.ldm * (unsigned)sizeof(float), clast = (unsigned)(a.n - 1) * cstride;
-        unsigned coff = 0;
+        // columns stream through the lane-private cp.async ring: RING columns in flight, rolled loop
+        const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + 16 * lane;
+        const unsigned colb = (unsigned)a.ldm * (unsigned)sizeof(float);
+        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + RING * colb;
+        const int nn = a.n;
+#pragma unroll 1
+        for (int sl = 0; sl < RING; sl++) {
+            const bool ok = sl < nn;
+            const char* sc_ = ok ? src + (size_t)sl * colb : src;
 #pragma unroll
-        for (int i = 0; i < UN; i++) {
-#pragma unroll
-            for (int g = 0; g < SG; g++) {
-#pragma unroll
-                for (int e = 0; e < 4; e++) buf[i][g][e] = 0.f;
-                if (own[g]) ldg_vec_hint_ordered<float>(reinterpret_cast<const float*>(col0 + coff) + g * GR, buf[i][g], pol);
-            }
-            coff = min(coff + cstride, clast);
+            for (int g = 0; g < SG; g++) if (ok && own[g]) cp_async16(ring0 + sl * colb + 512 * g, sc_ + 512 * g, 16, pol);
+            cp_async_commit();
         }
         const float* up = u32();
-        for (int c = 0; c < a.n; c += UN) {
+        unsigned slot = ring0;
+        const char* nxt = src + (size_t)RING * colb;
+#pragma unroll 1
+        for (int c = 0; c < nn; c++) {
+            cp_async_wait<RING - 1>();
+            const float uc = up[c];
 #pragma unroll
-            for (int i = 0; i < UN; i++) {
-                const float uc = up[c + i]; // zero for c + i >= n
-                const float* cp = reinterpret_cast<const float*>(col0 + coff);
+            for (int g = 0; g < SG; g++) {
+                if (own[g]) {
+                    float t[4];
+                    lds_vec<float>(slot + 512 * g, t);
 #pragma unroll
-                for (int g = 0; g < SG; g++) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) acc[g][e] += buf[i][g][e] * uc;
-                    if (own[g]) ldg_vec_hint_ordered<float>(cp + g * GR, buf[i][g], pol);
+                    for (int e = 0; e < 4; e++) acc[g][e] += t[e] * uc;
                 }
-                coff = min(coff + cstride, clast);
             }
+            const bool ok = c + RING < nn;
+            const char* sc_ = ok ? nxt : src;
+#pragma unroll
+            for (int g = 0; g < SG; g++) if (ok && own[g]) cp_async16(slot + 512 * g, sc_ + 512 * g, 16, pol);
+            cp_async_commit();
+            nxt += colb;
+            slot += colb;
+            if (slot == ring_end) slot = ring0;
         }
+        cp_async_wait<0>();
         // candidates in double from the float products; track the best and the runner-up among "possible" candidates
-        const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * sqrt((double)fval);
+        // |u|_2 from a float square root, rounded up (the bound only has to be an upper bound; + covers underflow)
+        const double unorm = (double)sqrtf((float)fval) * 1.0001 + 1e-22;
+        const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * unorm;
         const double ep = -(double)a.st.primal_tol;
         const uint64_t polk = policy_evict_last();
         const unsigned char* se = sense();
@@ -712,7 +776,7 @@ struct Warp {
         count(0);
         if constexpr (sizeof(T) == 8) {
             if (a.Mt32 != nullptr && a.ldm <= 256) { // screening in fp32 (two row groups of 128)
-                const int r = scan_screen<2, 6>();
+                const int r = scan_screen<2>();
                 if (r != -2) return r;
             }
         }
