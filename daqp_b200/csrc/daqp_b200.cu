@@ -183,7 +183,7 @@ struct Carver {
 template <typename T>
 static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
     size_t e = (size_t)n * ldm + (size_t)m * ldn + 3 * (size_t)ldm + (size_t)n * (n + 1) / 2 + n;
-    return e * sizeof(T) + (size_t)n * ldm * sizeof(float) + ldm + sizeof(int) + 64; // + fp32 Mt + sense + flag + slack
+    return e * sizeof(T) + (size_t)((n + 3) / 4) * m * 16 + ldm + sizeof(int) + 64; // + fp32 quad copy + sense + flag + slack
 }
 
 template <typename T, int NV>
@@ -233,14 +233,14 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     const DevSettings<T> st = to_dev_settings<T>(settings);
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
-    const bool screening = sizeof(T) == 8 && !(tune & 2) && ldm <= 256;
+    const bool screening = sizeof(T) == 8 && !(tune & 2) && m <= 256;
     for (int p0 = 0; p0 < N; p0 += chunk) {
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);
         int* counters = cv.take<int>(64);
         T* Mt = cv.take<T>((size_t)P * n * ldm);
         T* Mr = cv.take<T>((size_t)P * m * ldn);
-        float* Mt32 = screening ? cv.take<float>((size_t)P * n * ldm) : nullptr;
+        float* Mt32 = screening ? cv.take<float>((size_t)P * ((n + 3) / 4) * m * 4) : nullptr;
         T* du = cv.take<T>((size_t)P * ldm);
         T* dl = cv.take<T>((size_t)P * ldm);
         T* sc = cv.take<T>((size_t)P * ldm);

@@ -27,7 +27,8 @@
 namespace dq {
 
 constexpr int U_PAD = 16; // zero entries behind u so that the scan pipeline can run past column n-1
-constexpr int RING = 8;   // depth of the cp.async staging rings (columns of the scan, rows of the active-row passes)
+constexpr int RING = 8;   // depth of the cp.async staging ring of the active-row passes (rows in flight)
+constexpr int QRING = 3;  // depth of the screening scan's ring (quads of columns in flight)
 
 template <typename T>
 struct LdpArgs {
@@ -41,7 +42,7 @@ struct LdpArgs {
     unsigned sMt, sMr, sVec, sRinv, sv, sMt32;
     const T* Mt;              // [P][n][ldm]
     const T* Mr;              // [P][m][ldn]
-    const float* Mt32;        // [P][n][ldm] fp32 copy of Mt for the screening scan (nullptr: always scan in T)
+    const float* Mt32;        // [P][ceil(n/4)][m][4] fp32 copy of M in quad layout for the screening scan (nullptr: scan in T)
     const T* dupper;          // [P][ldm]
     const T* dlower;          // [P][ldm]
     const T* scaling;         // [P][ldm]
@@ -81,16 +82,16 @@ inline size_t ldp_layout(LdpArgs<T>& a) {
     a.oWS = (int)(bytes / sizeof(int)); bytes += (size_t)cap * sizeof(int);
     a.ocnt = (int)(bytes / sizeof(int)); bytes += 4 * sizeof(int);
     a.osense = (int)bytes; bytes += (size_t)round_up(a.m, 4);
-    bytes = (bytes + 3) / 4 * 4;
+    bytes = (bytes + 15) / 16 * 16; // the screening scan reads u32 with 128-bit loads
     a.ou32 = (int)(bytes / sizeof(float)); bytes += (size_t)(round_up(a.n, 4) + U_PAD) * sizeof(float);
     bytes = (bytes + 15) / 16 * 16;
     // staging ring: RING columns of the fp32 matrix (screening scan) or RING rows of the row-major matrix plus the
     // scratch of the dot-product reduction, whichever is larger
     a.oarena = (int)bytes;
-    const size_t colb = (size_t)a.ldm * sizeof(float), rowb = (size_t)a.ldn * sizeof(T);
+    const size_t slab = (size_t)a.m * 16, rowb = (size_t)a.ldn * sizeof(T);
     const size_t rows_need = RING * rowb + 8 * 33 * sizeof(T);
     a.oscratch = (int)(bytes + RING * rowb);
-    bytes += (a.ldm <= 256 && RING * colb > rows_need) ? RING * colb : rows_need;
+    bytes += (a.m <= 256 && QRING * slab > rows_need) ? QRING * slab : rows_need;
     bytes = (bytes + 15) / 16 * 16;
     a.per_warp_bytes = (unsigned)bytes;
     a.sMt = (unsigned)((size_t)a.n * a.ldm * sizeof(T));
@@ -98,7 +99,7 @@ inline size_t ldp_layout(LdpArgs<T>& a) {
     a.sVec = (unsigned)((size_t)a.ldm * sizeof(T));
     a.sRinv = (unsigned)((size_t)a.n * (a.n + 1) / 2 * sizeof(T));
     a.sv = (unsigned)((size_t)a.n * sizeof(T));
-    a.sMt32 = (unsigned)((size_t)a.n * a.ldm * sizeof(float));
+    a.sMt32 = (unsigned)((size_t)((a.n + 3) / 4) * a.m * 16);
     return bytes;
 }
 
@@ -664,55 +665,55 @@ struct Warp {
     // the smallest s32 and it is below the threshold by more than delta, it IS the fp64 argmin. Anything ambiguous
     // (near-ties, rows within delta of the threshold that could win) returns -2 and the caller runs the fp64 scan, so
     // the selected row is always the one the fp64 scan selects.
-    template <int SG>
+    template <int NR>
     __device__ __forceinline__ int scan_screen() {
-        constexpr int GR = 128; // rows per group: one float4 per lane
-        const uint64_t pol = (a.tune & 4) ? policy_evict_first() : policy_evict_last();
-        const int r0 = 4 * lane;
-        float acc[SG][4];
-        bool own[SG];
+        // Quad layout (setup kernel): element (row r, column c) of the float copy sits at ((c/4) m + r) * 4 + c%4, so
+        // one 128-bit word is ONE row x FOUR columns and lane l owns rows l, l+32, ... (NR = ceil(m/32) of them).
+        // Per quad of columns: one broadcast 128-bit read of u, and per owned row one 128-bit read + four FMAs into
+        // that row's accumulator. Quads stream through the lane-private cp.async ring, QRING in flight.
+        constexpr uint64_t pol = policy_evict_last(); // resident problems' copies fit L2 and are re-read every scan
+        const bool own_last = lane + 32 * (NR - 1) < a.m; // rows of the groups before the last always exist
+        float acc[NR];
 #pragma unroll
-        for (int g = 0; g < SG; g++) {
-            own[g] = r0 + g * GR < a.ldm;
-#pragma unroll
-            for (int e = 0; e < 4; e++) acc[g][e] = 0.f;
-        }
-        // columns stream through the lane-private cp.async ring: RING columns in flight, rolled loop
+        for (int r = 0; r < NR; r++) acc[r] = 0.f;
+        const unsigned slab = (unsigned)a.m * 16u; // bytes of one quad of columns
         const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + 16 * lane;
-        const unsigned colb = (unsigned)a.ldm * (unsigned)sizeof(float);
-        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + RING * colb;
-        const int nn = a.n;
+        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + QRING * slab;
+        const int nq = (a.n + 3) >> 2;
 #pragma unroll 1
-        for (int sl = 0; sl < RING; sl++) {
-            const bool ok = sl < nn;
-            const char* sc_ = ok ? src + (size_t)sl * colb : src;
+        for (int sl = 0; sl < QRING; sl++) {
+            if (sl < nq) {
 #pragma unroll
-            for (int g = 0; g < SG; g++) if (ok && own[g]) cp_async16(ring0 + sl * colb + 512 * g, sc_ + 512 * g, 16, pol);
+                for (int r = 0; r < NR; r++)
+                    if (r < NR - 1 || own_last) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r, 16, pol);
+                src += slab;
+            }
             cp_async_commit();
         }
-        const float* up = u32();
+        const unsigned ub = smem_u32(u32());
         unsigned slot = ring0;
-        const char* nxt = src + (size_t)RING * colb;
 #pragma unroll 1
-        for (int c = 0; c < nn; c++) {
-            cp_async_wait<RING - 1>();
-            const float uc = up[c];
+        for (int q = 0; q < nq; q++) {
+            cp_async_wait<QRING - 1>();
+            float uq[4];
+            lds_vec<float>(ub + 16 * q, uq);
 #pragma unroll
-            for (int g = 0; g < SG; g++) {
-                if (own[g]) {
+            for (int r = 0; r < NR; r++) {
+                if (r < NR - 1 || own_last) {
                     float t[4];
-                    lds_vec<float>(slot + 512 * g, t);
+                    lds_vec<float>(slot + 512 * r, t);
 #pragma unroll
-                    for (int e = 0; e < 4; e++) acc[g][e] += t[e] * uc;
+                    for (int e = 0; e < 4; e++) acc[r] += t[e] * uq[e];
                 }
             }
-            const bool ok = c + RING < nn;
-            const char* sc_ = ok ? nxt : src;
+            if (q + QRING < nq) {
 #pragma unroll
-            for (int g = 0; g < SG; g++) if (ok && own[g]) cp_async16(slot + 512 * g, sc_ + 512 * g, 16, pol);
+                for (int r = 0; r < NR; r++)
+                    if (r < NR - 1 || own_last) cp_async16(slot + 512 * r, src + 512 * r, 16, pol);
+                src += slab;
+            }
             cp_async_commit();
-            nxt += colb;
-            slot += colb;
+            slot += slab;
             if (slot == ring_end) slot = ring0;
         }
         cp_async_wait<0>();
@@ -721,41 +722,35 @@ struct Warp {
         const double unorm = (double)sqrtf((float)fval) * 1.0001 + 1e-22;
         const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * unorm;
         const double ep = -(double)a.st.primal_tol;
-        const uint64_t polk = policy_evict_last();
         const unsigned char* se = sense();
         double best = 1e300, second = 1e300;
         int key = INT_MAX;
         bool best_sure = false;
+        double bu[NR], bl[NR], bs[NR];
+        const double* dup = reinterpret_cast<const double*>(du()) + lane;
+        const double* dlp = reinterpret_cast<const double*>(dl()) + lane;
+        const double* scp = reinterpret_cast<const double*>(sc()) + lane;
 #pragma unroll
-        for (int g = 0; g < SG; g++) {
-            const int rr = r0 + g * GR;
-            if (rr < a.m) {
-                double bu[4], bl[4], bs[4];
+        for (int r = 0; r < NR; r++) {
+            bu[r] = bl[r] = bs[r] = 0;
+            if (r < NR - 1 || own_last) { bu[r] = __ldg(dup + 32 * r); bl[r] = __ldg(dlp + 32 * r); bs[r] = __ldg(scp + 32 * r); }
+        }
 #pragma unroll
-                for (int h = 0; h < 2; h++) { // two 128-bit loads per vector of four doubles
-                    double t2[2];
-                    ldg_vec_hint<double>(reinterpret_cast<const double*>(du()) + rr + 2 * h, t2, polk); bu[2 * h] = t2[0]; bu[2 * h + 1] = t2[1];
-                    ldg_vec_hint<double>(reinterpret_cast<const double*>(dl()) + rr + 2 * h, t2, polk); bl[2 * h] = t2[0]; bl[2 * h + 1] = t2[1];
-                    ldg_vec_hint<double>(reinterpret_cast<const double*>(sc()) + rr + 2 * h, t2, polk); bs[2 * h] = t2[0]; bs[2 * h + 1] = t2[1];
-                }
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int row = rr + e;
-                    // at most one side of a row can be violated beyond the tolerance (check_bounds guarantees
-                    // bupper >= blower - tol), so the row's candidate is its more violated side
-                    const double mu = (double)acc[g][e];
-                    const double cu = bu[e] - mu, cl = mu - bl[e];
-                    const bool lower = cl < cu;
-                    const double cand = lower ? cl : cu;
-                    const double bound = ep * bs[e];
-                    const bool possible = row < a.m && !(se[row] & (B_ACTIVE + B_IMMUTABLE)) && cand - delta < bound;
-                    const bool nb = possible && cand < best;
-                    second = nb ? best : ((possible && cand < second) ? cand : second);
-                    best_sure = nb ? (cand + delta < bound) : best_sure;
-                    key = nb ? 2 * row + (int)lower : key;
-                    best = nb ? cand : best;
-                }
-            }
+        for (int r = 0; r < NR; r++) {
+            const int row = lane + 32 * r;
+            // at most one side of a row can be violated beyond the tolerance (check_bounds guarantees
+            // bupper >= blower - tol), so the row's candidate is its more violated side
+            const double mu = (double)acc[r];
+            const double cu = bu[r] - mu, cl = mu - bl[r];
+            const bool lower = cl < cu;
+            const double cand = lower ? cl : cu;
+            const double bound = ep * bs[r];
+            const bool possible = (r < NR - 1 || own_last) && !(se[row] & (B_ACTIVE + B_IMMUTABLE)) && cand - delta < bound;
+            const bool nb = possible && cand < best;
+            second = nb ? best : ((possible && cand < second) ? cand : second);
+            best_sure = nb ? (cand + delta < bound) : best_sure;
+            key = nb ? 2 * row + (int)lower : key;
+            best = nb ? cand : best;
         }
         // warp: argmin of (best, key); runner-up = smallest value that is not the winner
         double wbest = best;
@@ -775,8 +770,18 @@ struct Warp {
     __device__ __forceinline__ int scan_infeasible() {
         count(0);
         if constexpr (sizeof(T) == 8) {
-            if (a.Mt32 != nullptr && a.ldm <= 256) { // screening in fp32 (two row groups of 128)
-                const int r = scan_screen<2>();
+            if (a.Mt32 != nullptr) { // screening in fp32 (host enables it for m <= 256)
+                int r;
+                switch ((a.m + 31) >> 5) {
+                    case 1: r = scan_screen<1>(); break;
+                    case 2: r = scan_screen<2>(); break;
+                    case 3: r = scan_screen<3>(); break;
+                    case 4: r = scan_screen<4>(); break;
+                    case 5: r = scan_screen<5>(); break;
+                    case 6: r = scan_screen<6>(); break;
+                    case 7: r = scan_screen<7>(); break;
+                    default: r = scan_screen<8>(); break;
+                }
                 if (r != -2) return r;
             }
         }

@@ -19,7 +19,7 @@ struct SetupArgs {
     const T *H, *f, *A, *bupper, *blower; // packed inputs; f may be nullptr
     const int* sense_in;                  // [P][m] or nullptr
     T *Mt, *Mr, *dupper, *dlower, *scaling, *Rinv, *v;
-    float* Mt32;                          // [P][n][ldm] fp32 copy of Mt (screening scan) or nullptr
+    float* Mt32;                          // [P][ceil(n/4)][m][4] fp32 copy of M, quad layout (screening scan) or nullptr
     unsigned char* sense;                 // [P][ldm]
     int* setup_flag;                      // [P]
     T *x, *lam, *fval;                    // final outputs (written here only for problems finished by the setup)
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         const T* bl = a.blower + (size_t)p * m;
         const int* sin = a.sense_in ? a.sense_in + (size_t)p * m : nullptr;
         T* Mt = a.Mt + (size_t)p * n * ldm;
-        float* Mt32 = a.Mt32 ? a.Mt32 + (size_t)p * n * ldm : nullptr;
+        float* Mt32 = a.Mt32 ? a.Mt32 + (size_t)p * ((n + 3) / 4) * m * 4 : nullptr; // quad layout, see scan_screen
         T* Mr = a.Mr + (size_t)p * m * ldn;
         T* du = a.dupper + (size_t)p * ldm;
         T* dl = a.dlower + (size_t)p * ldm;
@@ -291,12 +291,12 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
 #pragma unroll
                     for (int b = 0; b < SETUP_RB; b++)
                         if (ms + r0 + b < ldm) dst[b] = (b < nr) ? acc[b][g] : (T)0;
-                    if (Mt32) {
-                        float* d32 = Mt32 + (size_t)c * ldm + ms + r0;
+                }
+                if (Mt32 && c < ((n + 3) & ~3)) { // columns n..4 ceil(n/4)-1 are zero padding
+                    float* d32 = Mt32 + ((size_t)(c >> 2) * m + ms + r0) * 4 + (c & 3);
 #pragma unroll
-                        for (int b = 0; b < SETUP_RB; b++)
-                            if (ms + r0 + b < ldm) d32[b] = (b < nr) ? (float)acc[b][g] : 0.f;
-                    }
+                    for (int b = 0; b < SETUP_RB; b++)
+                        if (b < nr) d32[4 * b] = (c < n) ? (float)acc[b][g] : 0.f;
                 }
             }
             __syncwarp();
@@ -319,10 +319,11 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
             __syncwarp();
             T dotd = 0;
             if (!unc) { for (int j = i + lane; j < n; j += 32) dotd += Ri[j] * vv[j]; dotd = warp_sum(dotd); }
-            for (int c = lane; c < ldn; c += 32) {
+            for (int c = lane; c < max(ldn, (n + 3) & ~3); c += 32) {
                 const T val = (c >= i && c < n) ? Ri[c] : (T)0;
-                Mr[(size_t)i * ldn + c] = val;
-                if (c < n) { Mt[(size_t)c * ldm + i] = val; if (Mt32) Mt32[(size_t)c * ldm + i] = (float)val; }
+                if (c < ldn) Mr[(size_t)i * ldn + c] = val;
+                if (c < n) Mt[(size_t)c * ldm + i] = val;
+                if (Mt32 && c < ((n + 3) & ~3)) Mt32[((size_t)(c >> 2) * m + i) * 4 + (c & 3)] = (float)val;
             }
             if (lane == 0) {
                 T u_ = bu[i], l_ = bl[i];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         }
         // pad rows m..ldm-1 of the column-major copy and of the per-row vectors
         for (int c = lane; c < n; c += 32)
-            for (int r = m; r < ldm; r++) { Mt[(size_t)c * ldm + r] = 0; if (Mt32) Mt32[(size_t)c * ldm + r] = 0.f; }
+            for (int r = m; r < ldm; r++) Mt[(size_t)c * ldm + r] = 0;
         for (int r = m + lane; r < ldm; r += 32) { du[r] = 0; dl[r] = 0; sc[r] = 1; }
         __syncwarp();
         for (int idx = lane; idx < ntri; idx += 32) Rg[idx] = R[idx];
