@@ -109,6 +109,15 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int src_bytes, uint64_t pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(pol) : "memory");
 }
+// plain 16-byte copy (no cache-hint operand: saves the uniform-register set-up in front of every group)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// the same, predicated INSIDE the instruction: a row's copies stay in one basic block (a branch around each copy costs
+// a reconvergence pair and makes ptxas re-emit its three filler instructions in front of every LDGSTS)
+__device__ __forceinline__ void cp_async16_if(bool pred, unsigned dst, const void* src) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q cp.async.cg.shared.global [%0], [%1], 16;\n}" ::"r"(dst), "l"(src), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <typename T> __device__ __forceinline__ void lds_vec(unsigned addr, T (&out)[VecOf<T>::N]);

@@ -23,12 +23,25 @@
 #pragma once
 #include "common.cuh"
 #include <limits.h>
+#include <algorithm>
 
 namespace dq {
 
-constexpr int U_PAD = 16; // zero entries behind u so that the scan pipeline can run past column n-1
-constexpr int RING = 8;   // depth of the cp.async staging ring of the active-row passes (rows in flight)
+constexpr int U_PAD = 16; // zero entries behind u so that the fp64 scan pipeline can run past column n-1
+constexpr int RB = 8;     // active rows per cp.async chunk of the row passes (two chunks in flight)
 constexpr int QRING = 3;  // depth of the screening scan's ring (quads of columns in flight)
+constexpr int SCR_PITCH = 34; // doubles per parked row of partial dot products (16-byte aligned rows)
+
+// Warp-uniform values are made PROVABLY uniform for the compiler by reading them from lane 0: loops and branches on
+// them then compile to plain uniform control flow (no BSSY/BSYNC reconvergence bookkeeping, no BRA.DIV in front of
+// every shuffle). Measured on the SASS of the sweeps: 20 -> 10 instructions per pivot step.
+// Lane-strided loop with a UNIFORM trip count (the bound must be uniform): a loop whose trip count differs per lane
+// makes ptxas treat everything downstream as possibly diverged.
+#define LANE_LOOP(i, lo, hi) for (int i##_base = (lo); i##_base < (hi); i##_base += 32) if (const int i = i##_base + lane; i < (hi))
+__device__ __forceinline__ int uni(int v) { return __reduce_max_sync(FULL, v); }       // REDUX: lands in a uniform register
+__device__ __forceinline__ bool uni(bool v) { return __any_sync(FULL, v); }               // VOTEU: uniform predicate
+__device__ __forceinline__ double uni(double v) { return __shfl_sync(FULL, v, 0); }
+__device__ __forceinline__ float uni(float v) { return __shfl_sync(FULL, v, 0); }
 
 template <typename T>
 struct LdpArgs {
@@ -36,7 +49,8 @@ struct LdpArgs {
     // shared-memory layout of one warp, in elements of T from the warp's base (host-computed, see ldp_layout)
     int oD, olamA, olamB, oxl, ozl, odact, ou, oWS /* in ints */, osense /* in bytes */, ocnt /* in ints */;
     int ou32; /* float copy of u for the screening scan, in floats from the warp's base */
-    int oarena, oscratch; /* byte offsets: cp.async staging ring / reduction scratch (see RING) */
+    int oarena; /* byte offset of the cp.async staging arena: scan ring, or two chunks of RB active rows */
+    unsigned rowbuf; /* bytes of one chunk buffer of the row passes */
     unsigned per_warp_bytes;
     // per-problem byte strides of the global arrays
     unsigned sMt, sMr, sVec, sRinv, sv, sMt32;
@@ -79,19 +93,19 @@ inline size_t ldp_layout(LdpArgs<T>& a) {
     a.odact = o; o += cap;
     a.ou = o; o += round_up(a.n, V) + U_PAD;
     size_t bytes = (size_t)o * sizeof(T);
-    a.oWS = (int)(bytes / sizeof(int)); bytes += (size_t)cap * sizeof(int);
+    bytes = (bytes + 15) / 16 * 16; // WS is read four indices at a time; padded so that a whole chunk is addressable
+    a.oWS = (int)(bytes / sizeof(int)); bytes += (size_t)round_up(cap, RB) * sizeof(int);
     a.ocnt = (int)(bytes / sizeof(int)); bytes += 4 * sizeof(int);
     a.osense = (int)bytes; bytes += (size_t)round_up(a.m, 4);
     bytes = (bytes + 15) / 16 * 16; // the screening scan reads u32 with 128-bit loads
     a.ou32 = (int)(bytes / sizeof(float)); bytes += (size_t)(round_up(a.n, 4) + U_PAD) * sizeof(float);
     bytes = (bytes + 15) / 16 * 16;
-    // staging ring: RING columns of the fp32 matrix (screening scan) or RING rows of the row-major matrix plus the
-    // scratch of the dot-product reduction, whichever is larger
+    // staging arena: QRING quads of the fp32 matrix (screening scan), or two chunk buffers of RB rows of the row-major
+    // matrix (the buffer of a consumed chunk doubles as the scratch of the dot-product reduction)
     a.oarena = (int)bytes;
     const size_t slab = (size_t)a.m * 16, rowb = (size_t)a.ldn * sizeof(T);
-    const size_t rows_need = RING * rowb + 8 * 33 * sizeof(T);
-    a.oscratch = (int)(bytes + RING * rowb);
-    bytes += (a.m <= 256 && QRING * slab > rows_need) ? QRING * slab : rows_need;
+    a.rowbuf = (unsigned)std::max<size_t>(RB * rowb, (size_t)RB * SCR_PITCH * sizeof(T));
+    bytes += (a.m <= 256) ? std::max<size_t>(QRING * slab, 2 * (size_t)a.rowbuf) : 2 * (size_t)a.rowbuf;
     bytes = (bytes + 15) / 16 * 16;
     a.per_warp_bytes = (unsigned)bytes;
     a.sMt = (unsigned)((size_t)a.n * a.ldm * sizeof(T));
@@ -158,11 +172,10 @@ struct Warp {
     __device__ __forceinline__ void reset() { sing = EMPTY_IND; k = 0; reuse = 0; } // daqp.c:142-146
 
     // ---- triangular sweeps. The vector lives in NV registers per lane (element i = lane + 32 q in x[q]); one pivot
-    // per step: shuffle-broadcast the pivot value, one predicated FMA per register. No shared-memory round trip and
-    // no __syncwarp inside the recurrence; the loop bodies are branch-free and ~17 instructions (NV = 2), which
-    // matters twice: fewer issue slots, and a hot footprint that stays inside the instruction cache.
-    // Loads of L are unconditional (a lane outside the triangle reads a neighbouring, valid shared-memory word and
-    // discards it through the select), so the compiler emits no divergence bookkeeping.
+    // per step: shuffle-broadcast the pivot value, one predicated load + FMA per register segment. No shared-memory
+    // round trip and no __syncwarp inside the recurrence. Written as plain predicated C++ on PROVABLY uniform bounds
+    // (see uni()): ptxas then emits, per pivot, 2 SHFL + per segment {ISETP, @p LDS.64, @p DFMA} and unrolls by four
+    // (10 instructions per pivot for two segments, 7 for one).
     __device__ __forceinline__ void vload(T (&x)[NV], const T* src, int len) {
 #pragma unroll
         for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; x[q] = (i < len) ? src[i] : (T)0; }
@@ -171,53 +184,83 @@ struct Warp {
 #pragma unroll
         for (int q = 0; q < NV; q++) { const int i = lane + 32 * q; if (i >= lo && i < len) dst[i] = x[q]; }
     }
+    // pivots [jbeg, jend) of register segment QP applied to row segments QP .. Q1-1
+    template <int QP, int Q1>
+    __device__ __forceinline__ void fwd_pivots(T (&x)[NV], const T* const (&row)[NV], const int (&lim)[NV], int jbeg, int jend) {
+#pragma unroll 4
+        for (int j = jbeg; j < jend; j++) {
+            const T xj = __shfl_sync(FULL, x[QP], j);
+#pragma unroll
+            for (int q = QP; q < Q1; q++)
+                if (j < lim[q]) x[q] -= row[q][j] * xj;
+        }
+    }
     // x <- L^-1 x restricted to rows >= rlo (rows < rlo already hold the solution); ascending pivots, the order of
-    // the reference's forward substitutions (factorization.c:86-92, auxiliary.c:334-337). One loop per register
-    // segment of the pivot (so the shuffle source is a fixed register); body = 2 shuffles + per register one shared
-    // load, one compare and one predicated FMA.
+    // the reference's forward substitutions (factorization.c:86-92, auxiliary.c:334-337). rlo and len are uniform.
     __device__ __forceinline__ void forward_sweep(T (&x)[NV], int rlo, int len) {
-        const T* col[NV]; // &L[i][j] for this lane's rows; advanced by one column per step
-        int lim[NV];      // row index, or a value no pivot exceeds for rows that must not be touched
+        const T* row[NV]; // &L[i][0] for this lane's rows
+        int lim[NV];      // row index, or -1 for rows that must not be touched
 #pragma unroll
         for (int q = 0; q < NV; q++) {
             const int i = lane + 32 * q;
             lim[q] = (i >= rlo && i < len) ? i : -1;
-            col[q] = L() + loff(min(i, a.cap - 1)); // clamp: lanes without a row still read inside the factor
+            row[q] = L() + loff(i);
         }
-#pragma unroll
-        for (int qp = 0; qp < NV; qp++) {
-            const int jend = min(len - 1, 32 * qp + 32);
-#pragma unroll 1
-            for (int j = 32 * qp; j < jend; j++) {
-                const T xj = __shfl_sync(FULL, x[qp], j & 31);
-#pragma unroll
-                for (int q = qp; q < NV; q++) { // rows above the pivot's segment are already final
-                    fms_if_lt(x[q], *col[q], xj, j, lim[q]);
-                    col[q]++;
-                }
-            }
+        fwd_from<0>(x, row, lim, len);
+    }
+    template <int QP>
+    __device__ __forceinline__ void fwd_from(T (&x)[NV], const T* const (&row)[NV], const int (&lim)[NV], int len) {
+        const int jbeg = 32 * QP, jend = min(len - 1, 32 * QP + 32);
+        if (jbeg >= jend) return;
+        if constexpr (QP + 1 == NV) fwd_pivots<QP, NV>(x, row, lim, jbeg, jend);
+        else {
+            if (len <= 32 * QP + 32) fwd_pivots<QP, QP + 1>(x, row, lim, jbeg, jend); // no rows beyond this segment
+            else { fwd_pivots<QP, NV>(x, row, lim, jbeg, jend); fwd_from<QP + 1>(x, row, lim, len); }
         }
     }
     // x <- L^-T x ; descending pivots (auxiliary.c:343-352, 363-370). Row j of the packed factor is contiguous.
     __device__ __forceinline__ void backward_sweep(T (&x)[NV], int len) {
-        const T* Lj = L() + loff(len - 1) + lane;
 #pragma unroll
         for (int qp = NV - 1; qp >= 0; qp--) {
-            const int jlo = max(1, 32 * qp);
-#pragma unroll 1
-            for (int j = min(len - 1, 32 * qp + 31); j >= jlo; j--) {
-                const T xj = __shfl_sync(FULL, x[qp], j & 31);
+            const int jlo = max(1, 32 * qp), jhi = min(len - 1, 32 * qp + 31);
+            // (running row pointer: with the offset recomputed from j, ptxas folded the counter update into a
+            // lane-predicated move, declared the loop divergent and guarded every shuffle of the kernel behind it)
+            const T* Lj = L() + loff(jhi) + lane;
+#pragma unroll 4
+            for (int j = jhi; j >= jlo; j--) {
+                const T xj = __shfl_sync(FULL, x[qp], j);
 #pragma unroll
-                for (int q = 0; q <= qp; q++) fms_if_lt(x[q], Lj[32 * q], xj, lane + 32 * q, j);
+                for (int q = 0; q <= qp; q++)
+                    if (q < qp || lane + 32 * q < j) x[q] -= Lj[32 * q] * xj; // rows of lower segments are all above the pivot
                 Lj -= j - 1; // loff(j-1) = loff(j) - (j-1)
             }
         }
     }
 
+    // ---- active-row passes (LDL' add, primal update): rows WS[0..kk) of the row-major matrix stream through two
+    // chunk buffers of RB rows (cp.async, one commit group per chunk, the next chunk in flight while this one is
+    // consumed). Lane l copies, and later reads back, only its own 16-byte slices of a row, so the buffers need no
+    // barrier: cp.async.wait_group is a per-thread wait. Everything that steers the loops is uniform, the chunk body
+    // is fully unrolled with static slots: per row ~3 instructions to issue and ~5 to consume.
+    // M = this lane's slice of row 0; rows >= kk are not fetched (their slots keep stale data that is never used).
+    __device__ __forceinline__ void issue_rows(int base, int kk, unsigned buf, const char* M, const bool (&okg)[NG]) const {
+        const unsigned rstride = a.ldn * (unsigned)sizeof(T);
+        const int4* wsv = reinterpret_cast<const int4*>(WS() + base);
+        int id[RB];
+#pragma unroll
+        for (int v4 = 0; v4 < RB / 4; v4++) { const int4 t = wsv[v4]; id[4 * v4] = t.x; id[4 * v4 + 1] = t.y; id[4 * v4 + 2] = t.z; id[4 * v4 + 3] = t.w; }
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const char* src = M + (size_t)(unsigned)id[r] * rstride; // ids behind kk are stale but never dereferenced
+#pragma unroll
+            for (int g = 0; g < NG; g++) cp_async16_if(okg[g] && base + r < kk, buf + r * rstride + 512 * g, src + 512 * g);
+        }
+        cp_async_commit();
+    }
+
     // ---- a2: LDL' row append (factorization.c:21-111) + bookkeeping of daqp_add_constraint (auxiliary.c:27-41)
     __device__ __forceinline__ void raw_add(int add, T lamval) {
         count(1);
-        const uint64_t pol = policy_evict_last(); // active rows are re-read every iteration: keep them in L2
         const int sb = sense()[add];
         __syncwarp();
         if (lane == 0) sense()[add] = (unsigned char)(sb | B_ACTIVE);
@@ -226,73 +269,57 @@ struct Warp {
         const char* M = Mr() + (size_t)(V * lane) * sizeof(T);   // this lane's column slice of row 0
         const unsigned rstride = a.ldn * (unsigned)sizeof(T);
         T mi[NG][V];
+        bool okg[NG];
         T part = 0;
 #pragma unroll
         for (int g = 0; g < NG; g++) {
+            okg[g] = V * (lane + 32 * g) < a.ldn;
 #pragma unroll
             for (int e = 0; e < V; e++) mi[g][e] = 0;
-            if (V * (lane + 32 * g) < a.ldn)
-                ldg_vec_hint<T>(reinterpret_cast<const T*>(M + (size_t)add * rstride) + 32 * V * g, mi[g], pol);
+            if (okg[g]) ldg_vec<T>(reinterpret_cast<const T*>(M + (size_t)add * rstride) + 32 * V * g, mi[g]);
 #pragma unroll
             for (int e = 0; e < V; e++) part += mi[g][e] * mi[g][e];
         }
-        T d = warp_sum(part);
-        const int kk = k;
+        const int kk = uni(k);
         T* Lk = L() + loff(kk);
+        const unsigned buf0 = smem_u32(S) + a.oarena;
+        if (kk > 0) issue_rows(0, kk, buf0 + 16 * lane, M, okg);
+        T d = warp_sum(part);
         if (kk > 0) {
-            // l_j = M_{WS[j]} . m_add. The active rows stream through the lane-private cp.async ring (RING rows in
-            // flight, rolled loop); per-lane partial products of 8 rows are parked in scratch and summed with a
-            // transposed read (lane = (row, quarter)) instead of 8 full shuffle reductions.
-            const int* ws = WS();
-            const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + RING * rstride;
-            T* scr = reinterpret_cast<T*>(reinterpret_cast<char*>(S) + a.oscratch);
-            bool okg[NG];
+            // l_j = M_{WS[j]} . m_add: per-lane partial products of a chunk's rows are parked in the consumed buffer and
+            // summed with a transposed read (lane = (row, quarter)) instead of RB full shuffle reductions.
+            for (int c0 = 0; c0 < kk; c0 += RB) {
+                const unsigned cur = buf0 + ((c0 / RB) & 1) * a.rowbuf, nxt = buf0 + (((c0 / RB) & 1) ^ 1) * a.rowbuf;
+                if (c0 + RB < kk) { issue_rows(c0 + RB, kk, nxt + 16 * lane, M, okg); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                T pj[RB];
 #pragma unroll
-            for (int g = 0; g < NG; g++) okg[g] = V * (lane + 32 * g) < a.ldn;
-#pragma unroll 1
-            for (int sl = 0; sl < RING; sl++) {
-                const bool ok = sl < kk;
-                const char* src = M + (size_t)(ok ? ws[sl] : 0) * rstride;
+                for (int r = 0; r < RB; r++) {
+                    pj[r] = 0;
 #pragma unroll
-                for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(ring0 + sl * rstride + 512 * g, src + 512 * g, 16, pol);
-                cp_async_commit();
-            }
-            unsigned slot = ring0;
-#pragma unroll 1
-            for (int j = 0; j < kk; j++) {
-                cp_async_wait<RING - 1>();
-                T pj = 0;
+                    for (int g = 0; g < NG; g++) {
+                        if (okg[g]) { // a lane without columns in this group has no slice in the slot
+                            T t[V];
+                            lds_vec<T>(cur + 16 * lane + r * rstride + 512 * g, t);
 #pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    if (okg[g]) { // a lane without columns in this group has no chunk in the slot
-                        T t[V];
-                        lds_vec<T>(slot + 512 * g, t);
-#pragma unroll
-                        for (int e = 0; e < V; e++) pj += t[e] * mi[g][e];
+                            for (int e = 0; e < V; e++) pj[r] += t[e] * mi[g][e];
+                        }
                     }
                 }
-                scr[(j & 7) * 33 + lane] = pj;
-                const bool ok = j + RING < kk;
-                const char* src = M + (size_t)(ok ? ws[j + RING] : 0) * rstride;
+                __syncwarp(); // every lane has read its slices: the consumed buffer becomes the reduction scratch
+                T* scr = reinterpret_cast<T*>(reinterpret_cast<char*>(S) + a.oarena + ((c0 / RB) & 1) * a.rowbuf);
 #pragma unroll
-                for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(slot + 512 * g, src + 512 * g, 16, pol);
-                cp_async_commit();
-                slot += rstride;
-                if (slot == ring_end) slot = ring0;
-                if ((j & 7) == 7 || j == kk - 1) { // sum the parked partials of rows j0..j
-                    __syncwarp();
-                    const int r8 = lane >> 2, q4 = lane & 3;
-                    const T* pr = scr + r8 * 33 + 8 * q4;
-                    T sum = ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
-                    sum += __shfl_xor_sync(FULL, sum, 1);
-                    sum += __shfl_xor_sync(FULL, sum, 2);
-                    const int jr = (j & ~7) + r8;
-                    if (q4 == 0 && jr <= j) Lk[jr] = sum;
-                    __syncwarp();
-                }
+                for (int r = 0; r < RB; r++) scr[r * SCR_PITCH + lane] = pj[r];
+                __syncwarp();
+                const int r8 = lane >> 2, q4 = lane & 3;
+                const T* pr = scr + r8 * SCR_PITCH + 8 * q4;
+                T sum = ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+                sum += __shfl_xor_sync(FULL, sum, 1);
+                sum += __shfl_xor_sync(FULL, sum, 2);
+                const int jr = c0 + r8;
+                if (q4 == 0 && jr < kk) Lk[jr] = sum;
+                __syncwarp(); // scratch reads are done before the buffer is refilled, results visible to the sweep
             }
-            cp_async_wait<0>();
-            __syncwarp();
             // l <- L^-1 l in registers, then l <- D^-1 l ; d -= l' D l
             T lv[NV];
             vload(lv, Lk, kk);
@@ -310,7 +337,7 @@ struct Warp {
                 }
             }
             d -= warp_sum(acc);
-            if (d < a.st.sing_tol || kk >= a.n) { // ns_active == 0 on this path (soft constraints not in kernel yet)
+            if (uni(d < a.st.sing_tol || kk >= a.n)) { // ns_active == 0 on this path (soft constraints not in kernel yet)
                 sing = kk;
                 d = 0;
             }
@@ -322,63 +349,82 @@ struct Warp {
 
     // ---- a3: LDL' row/column deletion + Gill-Golub-Murray-Saunders C1 update (factorization.c:112-151)
     //      + bookkeeping of daqp_remove_constraint (auxiliary.c:3-22). Returns 1 if the factor became singular.
+    // Lane = trailing row: the removed column (the reference's w = &zldl[rm_ind]) lives in registers, every lane walks
+    // along its own row, and the update writes each element straight to its compacted position (one row up, one
+    // column left), so only the columns left of the removed one need a copy pass. Same recurrences, same order.
     __device__ __forceinline__ int raw_remove(int r) {
         count(2);
-        const int kk = k;
+        const int kk = uni(k);
         T* Lp = L();
         T* Dp = D();
-        T* z = zl();
         int* ws = WS();
         if (lane == 0) sense()[ws[r]] &= ~B_ACTIVE;
         if (r != kk - 1) {
-            const int nu = kk - r - 1;
-            for (int t = lane; t < nu; t += 32) z[r + t] = Lp[loff(r + 1 + t) + r]; // removed column
-            __syncwarp();
-            // compaction: new row i-1 <- old row i without column r (source and destination never overlap)
-            T* dst = Lp + loff(r);
-            for (int i = r + 1; i < kk; i++) {
-                const T* src = dst + (i - 1); // loff(i) = loff(i-1) + (i-1)
-                for (int j = lane; j < i; j += 32)
-                    if (j != r) dst[j - (j > r)] = src[j];
-                __syncwarp();
-                dst = const_cast<T*>(src);
+            const int nu = kk - r - 1; // trailing rows; trailing row s is old row r+1+s and becomes row r+s
+            T w[NV];
+            const T* src[NV];
+            T* dst[NV];
+            int srow[NV];
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const int sidx = lane + 32 * q, io = min(r + 1 + sidx, a.cap - 1);
+                srow[q] = sidx < nu ? sidx : -1;
+                src[q] = Lp + loff(io) + r + 1;    // old element (s, t) = src[t]
+                dst[q] = Lp + loff(io - 1) + r;    // its compacted position = dst[t]
+                w[q] = sidx < nu ? src[q][-1] : (T)0; // removed column
             }
-            T alpha = Dp[r];
-            for (int t = 0; t < nu; t++) {
-                const int c = r + t; // new index of this pivot (old index c+1)
-                const T pv = z[c];
-                const T Dold = Dp[c + 1];
-                const T dbar = Dold + alpha * pv * pv;
-                const T rdb = fdiv((T)1, dbar); // one reciprocal for the two quotients of the reference
-                const T beta = pv * alpha * rdb;
-                alpha = Dold * alpha * rdb;
-                if (lane == 0) Dp[c] = dbar; // D[c] was consumed one step earlier, before that step's __syncwarp
-                for (int s = t + 1 + lane; s < nu; s += 32) {
-                    T* Lrc = Lp + loff(r + s) + c;
-                    const T lv = *Lrc;
-                    const T qs = z[r + s] - pv * lv;
-                    z[r + s] = qs;
-                    *Lrc = lv + beta * qs;
+            __syncwarp();
+            // columns left of the removed one: row i moves up by one (lane j handles column j of every row, so each
+            // destination was read by the same lane one step earlier)
+            if (r > 0) {
+                const T* from = Lp + loff(r + 1);
+                for (int i = r + 1; i < kk; i++) {
+                    LANE_LOOP(j, 0, r) const_cast<T*>(from)[j - (i - 1)] = from[j];
+                    from += i;
                 }
-                __syncwarp();
+            }
+            __syncwarp();
+            T alpha = Dp[r];
+#pragma unroll
+            for (int qp = 0; qp < NV; qp++) { // pivot = trailing row t, held in register segment qp
+                const int tend = min(nu, 32 * qp + 32);
+                for (int t = 32 * qp; t < tend; t++) {
+                    const T pvt = __shfl_sync(FULL, w[qp], t);
+                    const T Dold = Dp[r + 1 + t];
+                    const T dbar = Dold + alpha * pvt * pvt;
+                    const T rdb = fdiv((T)1, dbar); // one reciprocal for the two quotients of the reference
+                    const T beta = pvt * alpha * rdb;
+                    alpha = Dold * alpha * rdb;
+                    if (lane == 0) Dp[r + t] = dbar; // its old value was consumed one step earlier (as alpha for t = 0)
+#pragma unroll
+                    for (int q = qp; q < NV; q++) {
+                        if (t < srow[q]) {
+                            const T lv = src[q][t];
+                            const T qs = w[q] - pvt * lv;
+                            w[q] = qs;
+                            dst[q][t] = lv + beta * qs;
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
         k = kk - 1;
         T* lm = lam();
         T* da = dact();
-        for (int base = r; base < k; base += 32) { // shift WS / lam / active bounds down by one
+        for (int base = r; base < kk - 1; base += 32) { // shift WS / lam / active bounds down by one
             const int i = base + lane;
             int wv = 0; T lv = 0, dv = 0;
-            if (i < k) { wv = ws[i + 1]; lv = lm[i + 1]; dv = da[i + 1]; }
+            if (i < kk - 1) { wv = ws[i + 1]; lv = lm[i + 1]; dv = da[i + 1]; }
             __syncwarp();
-            if (i < k) { ws[i] = wv; lm[i] = lv; da[i] = dv; }
+            if (i < kk - 1) { ws[i] = wv; lm[i] = lv; da[i] = dv; }
         }
         __syncwarp();
         if (r < reuse) reuse = r;
-        if (k > 0 && Dp[k - 1] < a.st.sing_tol) {
-            sing = k - 1;
+        if (kk > 1 && uni(Dp[kk - 2] < a.st.sing_tol)) {
+            sing = kk - 2;
             __syncwarp();
-            if (lane == 0) Dp[k - 1] = 0;
+            if (lane == 0) Dp[kk - 2] = 0;
             __syncwarp();
             return 1;
         }
@@ -391,39 +437,42 @@ struct Warp {
     // pivoting rule asks for, so raw_add / raw_remove are instantiated once. A pending "re-add the removed row once
     // the nested removal returns" is one entry of an explicit stack (global scratch: rare path).
     __device__ __forceinline__ void modify(int op, int arg, T lamval) {
+        // (structured control flow on purpose: one back edge per loop, no `continue` -- anything else makes ptxas
+        // give up on convergence analysis and guard every later shuffle with a divergence check)
         int depth = 0;
         for (;;) {
             bool pivot_check = true;
             if (op == OP_ADD) raw_add(arg, lamval);
-            else if (raw_remove(arg)) pivot_check = false; // removal made the factor singular: no pivoting
-            if (pivot_check && k > 1) {
-                const int r = k - 2;
-                const T Dr = D()[r], Dl = D()[k - 1];
-                if (Dr < a.st.pivot_tol && Dr < Dl) {
+            else if (uni(raw_remove(arg))) pivot_check = false; // removal made the factor singular: no pivoting
+            bool next = false;
+            const int kq = uni(k);
+            if (pivot_check && kq > 1) {
+                const int r = kq - 2;
+                const T Dr = D()[r], Dl = D()[kq - 1];
+                if (uni(Dr < a.st.pivot_tol && Dr < Dl)) {
                     if (lane == 0) { pst_id[depth] = WS()[r]; pst_lam[depth] = lam()[r]; }
                     __syncwarp();
                     depth++;
                     op = OP_REMOVE; arg = r;
-                    continue;
+                    next = true;
                 }
             }
             // the innermost pivot_last / remove_constraint returned: unwind pending re-adds
-            bool again = false;
-            while (depth > 0) {
+            while (!next && depth > 0) {
                 depth--;
-                if (sing != EMPTY_IND) continue; // auxiliary.c:392: abort this frame, keep unwinding
-                op = OP_ADD; arg = pst_id[depth]; lamval = pst_lam[depth];
-                again = true;
-                break;
+                if (uni(sing == EMPTY_IND)) { // else auxiliary.c:392: abort this frame, keep unwinding
+                    op = OP_ADD; arg = uni(pst_id[depth]); lamval = uni(pst_lam[depth]);
+                    next = true;
+                }
             }
-            if (!again) return;
+            if (!next) return;
         }
     }
 
     // ---- a5: constrained stationary point L D L' lam* = -d_k (auxiliary.c:314-354), forward solve resumes at reuse
     __device__ __forceinline__ void compute_csp() {
         count(3);
-        const int kk = k, r = reuse;
+        const int kk = uni(k), r = uni(reuse);
         T* xp = xl();
         const T* da = dact();
         T xv[NV];
@@ -432,7 +481,8 @@ struct Warp {
             for (int i = r; i < kk; i++) {
                 const T* Li = L() + loff(i);
                 T acc = 0;
-                for (int j = lane; j < i; j += 32) acc += Li[j] * xp[j];
+#pragma unroll
+                for (int q = 0; q < NV; q++) { const int j = lane + 32 * q; if (j < i) acc += Li[j] * xp[j]; }
                 acc = warp_sum(acc);
                 if (lane == 0) xp[i] = -da[i] - acc;
                 __syncwarp();
@@ -453,12 +503,10 @@ struct Warp {
 #pragma unroll
         for (int q = 0; q < NV; q++) {
             const int i = lane + 32 * q;
-            T zi = 0;
-            if (i < kk) {
-                if (i >= r) { zi = fdiv(xv[q], Dp[i]); z[i] = zi; }
-                else zi = z[i];
-            }
-            xv[q] = zi;
+            const bool fresh = i >= r && i < kk;
+            const T zi = fdiv(xv[q], fresh ? Dp[i] : (T)1); // unconditional call: no divergence around the division
+            if (fresh) z[i] = zi;
+            xv[q] = (i < kk) ? (fresh ? zi : z[i]) : (T)0;
         }
         backward_sweep(xv, kk);
         vstore(xv, lams(), 0, kk);
@@ -485,6 +533,8 @@ struct Warp {
     }
 
     // ---- a6: dual ratio test + step (auxiliary.c:277-306). Returns the blocking position or -1.
+    // Straight-line over the register segments: the division is executed by every lane (masked lanes divide by one),
+    // so there is no divergent region and no loop with a per-lane trip count.
     __device__ __forceinline__ int find_blocking() {
         T best = (T)1e30;
         int key = INT_MAX;
@@ -493,20 +543,29 @@ struct Warp {
         const T* ls = lams();
         const int* ws = WS();
         const unsigned char* se = sense();
-        for (int i = lane; i < k; i += 32) {
-            const int sb = se[ws[i]];
-            if (sb & B_IMMUTABLE) continue;
-            const T s = ls[i];
-            if (sb & B_LOWER) { if (s < dual_tol) continue; }
-            else if (s > -dual_tol) continue;
-            const T l = lm[i];
-            const T ac = fdiv(-l, (sing == EMPTY_IND) ? s - l : s);
-            if (ac < best) { best = ac; key = i; }
+        const int kk = uni(k);
+        const bool nonsing = uni(sing == EMPTY_IND);
+        T lv[NV], sv[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const int i = lane + 32 * q;
+            const bool valid = i < kk;
+            const int sb = valid ? se[ws[i]] : B_IMMUTABLE;
+            const T s = valid ? ls[i] : (T)0, l = valid ? lm[i] : (T)0;
+            lv[q] = l; sv[q] = s;
+            const bool cand = !(sb & B_IMMUTABLE) && ((sb & B_LOWER) ? !(s < dual_tol) : !(s > -dual_tol));
+            const T ac = fdiv(-l, cand ? (nonsing ? s - l : s) : (T)1);
+            if (cand && ac < best) { best = ac; key = i; }
         }
         warp_argmin(best, key);
+        key = uni(key);
         if (key == INT_MAX) return -1;
-        if (sing == EMPTY_IND) { for (int i = lane; i < k; i += 32) lm[i] += best * (ls[i] - lm[i]); }
-        else { for (int i = lane; i < k; i += 32) lm[i] += best * ls[i]; }
+        best = uni(best);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const int i = lane + 32 * q;
+            if (i < kk) lm[i] = nonsing ? lv[q] + best * (sv[q] - lv[q]) : lv[q] + best * sv[q];
+        }
         __syncwarp();
         sing = EMPTY_IND;
         return key;
@@ -514,14 +573,8 @@ struct Warp {
 
     // ---- a7: u = -Mk' lam*, fval = |u|^2 (auxiliary.c:46-88)
     __device__ __forceinline__ void compute_primal() {
-        if (a.tune == 1 && lane == 0) { // optional: pull the streamed matrix into L2 ahead of the scan
-            const char* mt = Mt();
-            for (unsigned off = 0; off < a.sMt; off += 16384) bulk_prefetch_l2(mt + off, min(16384u, a.sMt - off));
-        }
-        const uint64_t pol = policy_evict_last();
         const char* M = Mr() + (size_t)(V * lane) * sizeof(T);
         const unsigned rstride = a.ldn * (unsigned)sizeof(T);
-        const int* ws = WS();
         const T* ls = lams();
         T acc[NG][V];
         bool okg[NG];
@@ -531,41 +584,30 @@ struct Warp {
 #pragma unroll
             for (int e = 0; e < V; e++) acc[g][e] = 0;
         }
-        // active rows stream through the lane-private cp.async ring: RING rows in flight, rolled loop, FMAs in index
-        // order (the order of the reference's accumulation, auxiliary.c:54-68)
-        const int kk = k;
-        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + RING * rstride;
-#pragma unroll 1
-        for (int sl = 0; sl < RING; sl++) {
-            const bool ok = sl < kk;
-            const char* src = M + (size_t)(ok ? ws[sl] : 0) * rstride;
+        // FMAs in index order (the order of the reference's accumulation, auxiliary.c:54-68)
+        const int kk = uni(k);
+        const unsigned buf0 = smem_u32(S) + a.oarena + 16 * lane;
+        if (kk > 0) issue_rows(0, kk, buf0, M, okg);
+        for (int c0 = 0; c0 < kk; c0 += RB) {
+            const unsigned cur = buf0 + ((c0 / RB) & 1) * a.rowbuf, nxt = buf0 + (((c0 / RB) & 1) ^ 1) * a.rowbuf;
+            if (c0 + RB < kk) { issue_rows(c0 + RB, kk, nxt, M, okg); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
 #pragma unroll
-            for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(ring0 + sl * rstride + 512 * g, src + 512 * g, 16, pol);
-            cp_async_commit();
-        }
-        unsigned slot = ring0;
-#pragma unroll 1
-        for (int i = 0; i < kk; i++) {
-            cp_async_wait<RING - 1>();
-            const T li = ls[i];
+            for (int r = 0; r < RB; r++) {
+                if (c0 + r < kk) {
+                    const T li = ls[c0 + r];
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                if (okg[g]) {
-                    T t[V];
-                    lds_vec<T>(slot + 512 * g, t);
+                    for (int g = 0; g < NG; g++) {
+                        if (okg[g]) {
+                            T t[V];
+                            lds_vec<T>(cur + r * rstride + 512 * g, t);
 #pragma unroll
-                    for (int e = 0; e < V; e++) acc[g][e] -= t[e] * li;
+                            for (int e = 0; e < V; e++) acc[g][e] -= t[e] * li;
+                        }
+                    }
                 }
             }
-            const bool ok = i + RING < kk;
-            const char* src = M + (size_t)(ok ? ws[i + RING] : 0) * rstride;
-#pragma unroll
-            for (int g = 0; g < NG; g++) if (ok && okg[g]) cp_async16(slot + 512 * g, src + 512 * g, 16, pol);
-            cp_async_commit();
-            slot += rstride;
-            if (slot == ring_end) slot = ring0;
         }
-        cp_async_wait<0>();
         T* up = u();
         T part = 0;
 #pragma unroll
@@ -576,7 +618,7 @@ struct Warp {
                 for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
             }
         }
-        fval = warp_sum(part); // soft_slack == 0 on this path
+        fval = uni(warp_sum(part)); // soft_slack == 0 on this path
         __syncwarp();
     }
 
@@ -671,50 +713,68 @@ struct Warp {
         // one 128-bit word is ONE row x FOUR columns and lane l owns rows l, l+32, ... (NR = ceil(m/32) of them).
         // Per quad of columns: one broadcast 128-bit read of u, and per owned row one 128-bit read + four FMAs into
         // that row's accumulator. Quads stream through the lane-private cp.async ring, QRING in flight.
-        constexpr uint64_t pol = policy_evict_last(); // resident problems' copies fit L2 and are re-read every scan
         const bool own_last = lane + 32 * (NR - 1) < a.m; // rows of the groups before the last always exist
         float acc[NR];
 #pragma unroll
         for (int r = 0; r < NR; r++) acc[r] = 0.f;
+        // the rows' bounds are needed only after the products: fetch them first so that their latency hides behind the scan
+        double bu[NR], bl[NR], bs[NR];
+        {
+            const double* dup = reinterpret_cast<const double*>(du()) + lane;
+            const double* dlp = reinterpret_cast<const double*>(dl()) + lane;
+            const double* scp = reinterpret_cast<const double*>(sc()) + lane;
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                bu[r] = bl[r] = bs[r] = 0;
+                if (r < NR - 1 || own_last) { bu[r] = __ldg(dup + 32 * r); bl[r] = __ldg(dlp + 32 * r); bs[r] = __ldg(scp + 32 * r); }
+            }
+        }
         const unsigned slab = (unsigned)a.m * 16u; // bytes of one quad of columns
         const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + 16 * lane;
-        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane, ring_end = ring0 + QRING * slab;
+        const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane;
         const int nq = (a.n + 3) >> 2;
-#pragma unroll 1
+        // ring slots are static (the quad loop is unrolled QRING times); every step commits one group, possibly empty
+#pragma unroll
         for (int sl = 0; sl < QRING; sl++) {
             if (sl < nq) {
 #pragma unroll
-                for (int r = 0; r < NR; r++)
-                    if (r < NR - 1 || own_last) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r, 16, pol);
+                for (int r = 0; r < NR; r++) {
+                    if (r < NR - 1) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r);
+                    else cp_async16_if(own_last, ring0 + sl * slab + 512 * r, src + 512 * r);
+                }
                 src += slab;
             }
             cp_async_commit();
         }
-        const unsigned ub = smem_u32(u32());
-        unsigned slot = ring0;
-#pragma unroll 1
-        for (int q = 0; q < nq; q++) {
-            cp_async_wait<QRING - 1>();
-            float uq[4];
-            lds_vec<float>(ub + 16 * q, uq);
+        unsigned ub = smem_u32(u32());
+        for (int q0 = 0; q0 < nq; q0 += QRING) {
 #pragma unroll
-            for (int r = 0; r < NR; r++) {
-                if (r < NR - 1 || own_last) {
-                    float t[4];
-                    lds_vec<float>(slot + 512 * r, t);
+            for (int sl = 0; sl < QRING; sl++) {
+                if (q0 + sl < nq) {
+                    cp_async_wait<QRING - 1>();
+                    float uq[4];
+                    lds_vec<float>(ub + 16 * sl, uq);
 #pragma unroll
-                    for (int e = 0; e < 4; e++) acc[r] += t[e] * uq[e];
+                    for (int r = 0; r < NR; r++) {
+                        if (r < NR - 1 || own_last) {
+                            float t[4];
+                            lds_vec<float>(ring0 + sl * slab + 512 * r, t);
+#pragma unroll
+                            for (int e = 0; e < 4; e++) acc[r] += t[e] * uq[e];
+                        }
+                    }
+                    if (q0 + sl + QRING < nq) {
+#pragma unroll
+                        for (int r = 0; r < NR; r++) {
+                            if (r < NR - 1) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r);
+                            else cp_async16_if(own_last, ring0 + sl * slab + 512 * r, src + 512 * r);
+                        }
+                        src += slab;
+                    }
+                    cp_async_commit();
                 }
             }
-            if (q + QRING < nq) {
-#pragma unroll
-                for (int r = 0; r < NR; r++)
-                    if (r < NR - 1 || own_last) cp_async16(slot + 512 * r, src + 512 * r, 16, pol);
-                src += slab;
-            }
-            cp_async_commit();
-            slot += slab;
-            if (slot == ring_end) slot = ring0;
+            ub += 16 * QRING;
         }
         cp_async_wait<0>();
         // candidates in double from the float products; track the best and the runner-up among "possible" candidates
@@ -726,15 +786,6 @@ struct Warp {
         double best = 1e300, second = 1e300;
         int key = INT_MAX;
         bool best_sure = false;
-        double bu[NR], bl[NR], bs[NR];
-        const double* dup = reinterpret_cast<const double*>(du()) + lane;
-        const double* dlp = reinterpret_cast<const double*>(dl()) + lane;
-        const double* scp = reinterpret_cast<const double*>(sc()) + lane;
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-            bu[r] = bl[r] = bs[r] = 0;
-            if (r < NR - 1 || own_last) { bu[r] = __ldg(dup + 32 * r); bl[r] = __ldg(dlp + 32 * r); bs[r] = __ldg(scp + 32 * r); }
-        }
 #pragma unroll
         for (int r = 0; r < NR; r++) {
             const int row = lane + 32 * r;
@@ -756,12 +807,14 @@ struct Warp {
         double wbest = best;
         int wkey = key;
         warp_argmin(wbest, wkey);
+        wkey = uni(wkey);
         if (wkey == INT_MAX) return -1; // no row can be violated beyond the tolerance: certain
+        wbest = uni(wbest);
         double other = (key == wkey) ? second : best;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) other = fmin(other, __shfl_xor_sync(FULL, other, o));
         const bool sure = __any_sync(FULL, key == wkey && best_sure);
-        if (sure && other - wbest > 2.0 * delta) return wkey;
+        if (sure && uni(other - wbest > 2.0 * delta)) return wkey;
         return -2; // ambiguous: decide in fp64
     }
 
@@ -794,6 +847,7 @@ struct Warp {
         else if (a.ldm <= 3 * GR) scan_rows<3, 5>(0, best, key);
         else for (int base = 0; base < a.m; base += 4 * GR) scan_rows<4, 4>(base, best, key);
         warp_argmin(best, key);
+        key = uni(key);
         return key == INT_MAX ? -1 : key;
     }
 
@@ -801,41 +855,43 @@ struct Warp {
     __device__ __forceinline__ int activate_constraints() {
         unsigned char* se = sense();
         for (int i = 0; i < a.m; i++) {
-            const int sb = se[i];
+            const int sb = uni((int)se[i]);
             if (sb & B_ACTIVE) modify(OP_ADD, i, (sb & B_LOWER) ? (T)-1 : (T)1);
-            if (sing != EMPTY_IND) {
-                const int last = WS()[k - 1];
-                if (se[last] & B_IMMUTABLE) {
+            if (uni(sing != EMPTY_IND)) {
+                const int last = uni(WS()[k - 1]);
+                if (uni((int)se[last]) & B_IMMUTABLE) {
                     singular_direction();
                     T resid = 0, scale = 0;
-                    for (int j = lane; j < k; j += 32) {
+                    const int kq = uni(k);
+                    LANE_LOOP(j, 0, kq) {
                         const T term = lams()[j] * dact()[j];
                         resid += term;
                         scale += term < 0 ? -term : term;
                     }
-                    resid = warp_sum(resid);
-                    scale = (T)1 + warp_sum(scale);
+                    resid = uni(warp_sum(resid));
+                    scale = (T)1 + uni(warp_sum(scale));
                     if (lane == 0) se[last] &= ~B_ACTIVE;
                     k--;
                     sing = EMPTY_IND;
                     if (reuse > k) reuse = k;
                     __syncwarp();
-                    if (resid <= a.st.primal_tol * scale && resid >= -a.st.primal_tol * scale) continue;
-                    return EXIT_OVERDETERMINED_INITIAL;
-                }
+                    if (!uni(resid <= a.st.primal_tol * scale && resid >= -a.st.primal_tol * scale))
+                        return EXIT_OVERDETERMINED_INITIAL;
+                } else {
                 int flag = 1;
-                for (int j = i + lane; j < a.m; j += 32) {
+                LANE_LOOP(j, i, a.m) {
                     const int s2 = se[j];
                     if (s2 & B_ACTIVE) {
                         if (s2 & B_IMMUTABLE) flag = EXIT_OVERDETERMINED_INITIAL;
                         else se[j] = s2 & ~B_ACTIVE;
                     }
                 }
-                flag = __reduce_min_sync(FULL, flag);
+                flag = uni(__reduce_min_sync(FULL, flag));
                 k--;
                 sing = EMPTY_IND;
                 __syncwarp();
                 return flag;
+                }
             }
         }
         return 1;
@@ -844,7 +900,7 @@ struct Warp {
     // ---- a12: one step of iterative refinement on the active rows (auxiliary.c:498-593)
     __device__ __forceinline__ void refine_active() {
         reuse = 0;
-        const int kk = k;
+        const int kk = uni(k);
         const char* M = Mr() + (size_t)(V * lane) * sizeof(T);
         const unsigned rstride = a.ldn * (unsigned)sizeof(T);
         T* xp = xl();
@@ -879,7 +935,7 @@ struct Warp {
             vstore(rv, xp, 0, kk);
             __syncwarp();
         }
-        for (int i = lane; i < kk; i += 32) lams()[i] += xp[i];
+        LANE_LOOP(i, 0, kk) lams()[i] += xp[i];
         T acc[NG][V];
 #pragma unroll
         for (int g = 0; g < NG; g++) {
@@ -907,10 +963,10 @@ struct Warp {
             const int c = V * (lane + 32 * g);
             if (c < a.ldn) {
 #pragma unroll
-                for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; part += acc[g][e] * acc[g][e]; }
+                for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
             }
         }
-        fval = warp_sum(part); // + soft_slack, which is zero on this path
+        fval = uni(warp_sum(part)); // + soft_slack, which is zero on this path
         __syncwarp();
     }
 
@@ -927,14 +983,15 @@ struct Warp {
     // initial activation failed, which the reference reports as a setup failure).
     __device__ __forceinline__ int step() {
         const T fval_bound = 2 * a.st.fval_bound;
-        if (do_activate) { // end of the previous iteration's refactor / cycle repair, or the warm start
+        if (uni(do_activate)) { // end of the previous iteration's refactor / cycle repair, or the warm start
             do_activate = false;
             if (iter > 0) reset();
-            const int aflag = activate_constraints();
+            const int aflag = uni(activate_constraints());
             if (iter == 0 && aflag < 0) return aflag;
         }
-        if (++iter >= a.st.iter_limit) return EXIT_ITERLIMIT; // for(iter=1; iter < iter_limit; ++iter)
-        const bool was_singular = sing != EMPTY_IND;
+        iter = uni(iter + 1);
+        if (iter >= a.st.iter_limit) return EXIT_ITERLIMIT; // for(iter=1; iter < iter_limit; ++iter)
+        const bool was_singular = uni(sing != EMPTY_IND);
         if (!was_singular) compute_csp(); else singular_direction();
         int op = OP_REMOVE, arg = find_blocking();
         T lamval = 0;
@@ -943,8 +1000,10 @@ struct Warp {
             if (was_singular) return EXIT_INFEASIBLE; // daqp.c:88-93
             compute_primal();
             if (fval > fval_bound) return EXIT_INFEASIBLE;
-            for (;;) {
-                const int key = scan_infeasible();
+            bool again = true;
+            while (again) { // at most two passes: the scan is repeated once after a refinement (daqp.c:52-56)
+                again = false;
+                const int key = uni(scan_infeasible());
                 if (key >= 0) {
                     arg = key >> 1;
                     const int lower = key & 1;
@@ -953,36 +1012,37 @@ struct Warp {
                     __syncwarp();
                     op = OP_ADD;
                     lamval = lower ? (T)-1 : (T)1;
-                    break;
-                }
-                // primal feasible: KKT point unless the factor is ill-conditioned (daqp.c:28-63)
-                T min_D = (T)1e30;
-                for (int i = lane; i < k; i += 32) min_D = fmin(min_D, D()[i]);
+                } else {
+                    // primal feasible: KKT point unless the factor is ill-conditioned (daqp.c:28-63)
+                    T min_D = (T)1e30;
+                    const int kq = uni(k);
+                    LANE_LOOP(i, 0, kq) min_D = fmin(min_D, D()[i]);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) min_D = fmin(min_D, __shfl_xor_sync(FULL, min_D, o));
-                if (k > 2 && tried_repair != 1 && min_D < a.st.refactor_tol) {
-                    tried_repair = 1;
-                    for (int i = lane; i < k; i += 32) {
-                        const int id = WS()[i];
-                        if (lam()[i] >= 0) sense()[id] &= ~B_LOWER; else sense()[id] |= B_LOWER;
+                    for (int o = 16; o > 0; o >>= 1) min_D = fmin(min_D, __shfl_xor_sync(FULL, min_D, o));
+                    min_D = uni(min_D);
+                    if (kq > 2 && uni(tried_repair != 1) && min_D < a.st.refactor_tol) {
+                        tried_repair = 1;
+                        LANE_LOOP(i, 0, kq) {
+                            const int id = WS()[i];
+                            if (lam()[i] >= 0) sense()[id] &= ~B_LOWER; else sense()[id] |= B_LOWER;
+                        }
+                        __syncwarp();
+                        do_activate = true; // refactor: handled at the top of the next step
+                        return RUNNING;
                     }
-                    __syncwarp();
-                    do_activate = true; // refactor: handled at the top of the next step
-                    return RUNNING;
+                    if (!refined && kq > 0 && min_D < a.st.pivot_tol) {
+                        refine_active();
+                        refined = true;
+                        again = true;
+                    } else return EXIT_OPTIMAL; // soft_slack == 0 on this path, so never SOFT_OPTIMAL
                 }
-                if (!refined && k > 0 && min_D < a.st.pivot_tol) {
-                    refine_active();
-                    refined = true;
-                    continue; // daqp.c:52-56: scan again after the refinement
-                }
-                return EXIT_OPTIMAL; // soft_slack == 0 on this path, so never SOFT_OPTIMAL
             }
         }
         modify(op, arg, lamval); // the ONE place where the working set changes inside the loop
         if (op == OP_ADD && !refined) { // cycle guard, daqp.c:67-85 (skipped on the refine path, daqp.c:54-55)
-            if (fval - best_fval < a.st.progress_tol) {
-                if (cycle_counter++ > a.st.cycle_tol) {
-                    if (tried_repair == 1) return EXIT_CYCLE;
+            if (uni(fval - best_fval < a.st.progress_tol)) {
+                if (uni(cycle_counter++ > a.st.cycle_tol)) {
+                    if (uni(tried_repair == 1)) return EXIT_CYCLE;
                     tried_repair = 1;
                     do_activate = true;
                     cycle_counter = 0;
@@ -1007,7 +1067,7 @@ struct Warp {
 template <typename T, int NV>
 __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant__ LdpArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = uni((int)(threadIdx.x >> 5)); // uniform: so are all shared-memory bases
     const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
 
     Warp<T, NV> w(a);
@@ -1016,49 +1076,42 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
     w.pst_id = a.pst_id + (size_t)gw * a.cap;
     w.pst_lam = a.pst_lam + (size_t)gw * a.cap;
 
-    bool have = false, exhausted = false;
+    // Structured on purpose (see modify()): a problem loop around an iteration loop, no loop-carried control flags.
     for (;;) {
         // ---- take the next problem off the queue (problems finished by the setup kernel are only passed through)
-        while (!have && !exhausted) {
-            int p = 0;
-            if (lane == 0) p = atomicAdd(a.work_counter, 1);
-            p = __shfl_sync(FULL, p, 0);
-            if (p >= a.P) { exhausted = true; break; }
-            w.p = p;
-            const int sflag = a.setup_flag[p];
-            if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) {
-                if (a.nact_out && lane == 0) a.nact_out[p] = 0;
-                if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = 0;
-                if (a.sense_out)
-                    for (int i = lane; i < a.m; i += 32) a.sense_out[(size_t)p * a.ldm + i] = a.sense[(size_t)p * a.ldm + i];
-                continue;
-            }
+        int pq = 0;
+        if (lane == 0) pq = atomicAdd(a.work_counter, 1);
+        pq = uni(pq); // lanes other than 0 hold 0 and queue indices are non-negative
+        if (pq >= a.P) break;
+        w.p = pq;
+        const int sflag = uni(a.setup_flag[pq]); // loaded values are divergent in ptxas' eyes until proven otherwise
+        if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) {
+            if (a.nact_out && lane == 0) a.nact_out[pq] = 0;
+            if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)pq + lane] = 0;
+            if (a.sense_out)
+                LANE_LOOP(i, 0, a.m) a.sense_out[(size_t)pq * a.ldm + i] = a.sense[(size_t)pq * a.ldm + i];
+            __syncwarp(); // reconverge before the back edge: a lane-divergent tail would leave the loop header diverged
+        } else {
+        {
             w.lsw = 0;
             w.fval = 0;
-            const unsigned char* sin = a.sense + (size_t)p * a.ldm;
+            const unsigned char* sin = a.sense + (size_t)pq * a.ldm;
             unsigned char* se = w.sense();
-            for (int i = lane; i < a.m; i += 32) se[i] = sin[i];
+            LANE_LOOP(i, 0, a.m) se[i] = sin[i];
             T* up = w.u();
-            for (int i = lane; i < round_up(a.n, VecOf<T>::N) + U_PAD; i += 32) up[i] = 0;
+            LANE_LOOP(i, 0, round_up(a.n, VecOf<T>::N) + U_PAD) up[i] = 0;
             if (lane < 4) w.cnt()[lane] = 0;
             float* u32p = w.u32();
-            for (int i = lane; i < round_up(a.n, 4) + U_PAD; i += 32) u32p[i] = 0.f;
+            LANE_LOOP(i, 0, round_up(a.n, 4) + U_PAD) u32p[i] = 0.f;
             __syncwarp();
             w.reset();
             w.begin(sflag == SETUP_SOLVE_ACTIVATE);
-            have = true;
         }
-        // ---- the alignment point; also the termination test (every warp calls it the same number of times)
-        if (a.tune & 8) { // experiment: one block barrier per iteration (phase alignment)
-            if (!__syncthreads_or(have)) break;
-            if (!have) continue;
-        } else if (!have) break;
-
-        const int exitflag = w.step();
-        if (exitflag == Warp<T, NV>::RUNNING) continue;
-        have = false;
-        const int p = w.p;
-        if (w.iter == 0) {
+        int exitflag;
+        do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV>::RUNNING);
+        {
+        const int p = w.p, kfin = uni(w.k);
+        if (uni(w.iter == 0)) {
             // the initial activation failed (utils.c:209-210 -> api.c:69-72): flag only, x untouched
             if (lane == 0) { a.exitflag[p] = exitflag; a.iter[p] = 0; }
         } else {
@@ -1067,27 +1120,27 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             T* xo = a.x + (size_t)p * a.n;
             T* up = w.u();
             T vnorm = 0;
-            if (vv) { for (int i = lane; i < a.n; i += 32) { const T t = vv[i]; vnorm += t * t; } vnorm = warp_sum(vnorm); }
+            if (vv) { LANE_LOOP(i, 0, a.n) { const T t = vv[i]; vnorm += t * t; } vnorm = warp_sum(vnorm); }
             if (exitflag > 0) {
                 const T* Ri = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.Rinv) + (size_t)p * a.sRinv);
-                if (vv) for (int i = lane; i < a.n; i += 32) up[i] -= vv[i];
+                if (vv) LANE_LOOP(i, 0, a.n) up[i] -= vv[i];
                 __syncwarp();
                 for (int i = 0; i < a.n; i++) { // x_i = sum_{j>=i} Rinv[i][j] (u-v)_j ; rows are independent
                     const T* row = Ri + roff(i, a.n);
                     T acc = 0;
-                    for (int j = i + lane; j < a.n; j += 32) acc += row[j] * up[j];
+                    LANE_LOOP(j, i, a.n) acc += row[j] * up[j];
                     acc = warp_sum(acc);
                     if (i < a.ms) acc /= w.sc()[i];
                     if (lane == 0) xo[i] = acc;
                 }
             } else {
-                for (int i = lane; i < a.n; i += 32) xo[i] = up[i];
+                LANE_LOOP(i, 0, a.n) xo[i] = up[i];
             }
             if (a.lam) {
                 T* lo = a.lam + (size_t)p * a.m;
-                for (int i = lane; i < a.m; i += 32) lo[i] = 0;
+                LANE_LOOP(i, 0, a.m) lo[i] = 0;
                 __syncwarp();
-                for (int i = lane; i < w.k; i += 32) {
+                LANE_LOOP(i, 0, kfin) {
                     const int id = w.WS()[i];
                     lo[id] = (exitflag > 0) ? w.lams()[i] * w.sc()[id] : w.lams()[i];
                 }
@@ -1099,10 +1152,12 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             }
         }
         if (a.nact_out && lane == 0) a.nact_out[p] = w.k;
-        if (a.ws_out) for (int i = lane; i < w.k; i += 32) a.ws_out[(size_t)p * a.cap + i] = w.WS()[i];
-        if (a.sense_out) for (int i = lane; i < a.m; i += 32) a.sense_out[(size_t)p * a.ldm + i] = w.sense()[i];
+        if (a.ws_out) LANE_LOOP(i, 0, kfin) a.ws_out[(size_t)p * a.cap + i] = w.WS()[i];
+        if (a.sense_out) LANE_LOOP(i, 0, a.m) a.sense_out[(size_t)p * a.ldm + i] = w.sense()[i];
         if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = w.cnt()[lane];
         __syncwarp();
+        }
+        }
     }
 }
 
