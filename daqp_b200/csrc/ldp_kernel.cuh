@@ -37,7 +37,7 @@ constexpr int SCR_PITCH = 34; // doubles per parked row of partial dot products 
 // every shuffle). Measured on the SASS of the sweeps: 20 -> 10 instructions per pivot step.
 // Lane-strided loop with a UNIFORM trip count (the bound must be uniform): a loop whose trip count differs per lane
 // makes ptxas treat everything downstream as possibly diverged.
-#define LANE_LOOP(i, lo, hi) for (int i##_base = (lo); i##_base < (hi); i##_base += 32) if (const int i = i##_base + lane; i < (hi))
+#define LANE_LOOP(i, lo, hi) _Pragma("unroll 1") for (int i##_base = (lo); i##_base < (hi); i##_base += 32) if (const int i = i##_base + lane; i < (hi))
 __device__ __forceinline__ int uni(int v) { return __reduce_max_sync(FULL, v); }       // REDUX: lands in a uniform register
 __device__ __forceinline__ bool uni(bool v) { return __any_sync(FULL, v); }               // VOTEU: uniform predicate
 __device__ __forceinline__ double uni(double v) { return __shfl_sync(FULL, v, 0); }
@@ -128,6 +128,25 @@ template <> __device__ __forceinline__ void ldg_vec_pred<float>(const void* p, f
                  : "+f"(out[0]), "+f"(out[1]), "+f"(out[2]), "+f"(out[3]) : "l"(p), "l"(pol), "r"(pred));
 }
 
+// One chunk of RB active rows, global -> shared (cp.async, one commit group). ONE copy of this code serves both row
+// passes (not inlined: the instruction cache is the scarce resource, see the header). ids = &WS[base]; rows at or
+// beyond nrows are not fetched (their ids are stale but never dereferenced); okmask bit g = this lane owns a 16-byte
+// slice in column group g.
+template <typename T, int NG>
+__device__ __noinline__ void issue_rows_fn(const int* ids, int nrows, unsigned buf, const char* M, unsigned rstride, unsigned okmask) {
+    const int4* wsv = reinterpret_cast<const int4*>(ids);
+    int id[RB];
+#pragma unroll
+    for (int v4 = 0; v4 < RB / 4; v4++) { const int4 t = wsv[v4]; id[4 * v4] = t.x; id[4 * v4 + 1] = t.y; id[4 * v4 + 2] = t.z; id[4 * v4 + 3] = t.w; }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        const char* src = M + (size_t)(unsigned)id[r] * rstride;
+#pragma unroll
+        for (int g = 0; g < NG; g++) cp_async16_if(((okmask >> g) & 1u) && r < nrows, buf + r * rstride + 512 * g, src + 512 * g);
+    }
+    cp_async_commit();
+}
+
 template <typename T, int NV>
 struct Warp {
     static constexpr int V = VecOf<T>::N;
@@ -187,7 +206,7 @@ struct Warp {
     // pivots [jbeg, jend) of register segment QP applied to row segments QP .. Q1-1
     template <int QP, int Q1>
     __device__ __forceinline__ void fwd_pivots(T (&x)[NV], const T* const (&row)[NV], const int (&lim)[NV], int jbeg, int jend) {
-#pragma unroll 4
+#pragma unroll 2
         for (int j = jbeg; j < jend; j++) {
             const T xj = __shfl_sync(FULL, x[QP], j);
 #pragma unroll
@@ -226,7 +245,7 @@ struct Warp {
             // (running row pointer: with the offset recomputed from j, ptxas folded the counter update into a
             // lane-predicated move, declared the loop divergent and guarded every shuffle of the kernel behind it)
             const T* Lj = L() + loff(jhi) + lane;
-#pragma unroll 4
+#pragma unroll 2
             for (int j = jhi; j >= jlo; j--) {
                 const T xj = __shfl_sync(FULL, x[qp], j);
 #pragma unroll
@@ -244,18 +263,10 @@ struct Warp {
     // is fully unrolled with static slots: per row ~3 instructions to issue and ~5 to consume.
     // M = this lane's slice of row 0; rows >= kk are not fetched (their slots keep stale data that is never used).
     __device__ __forceinline__ void issue_rows(int base, int kk, unsigned buf, const char* M, const bool (&okg)[NG]) const {
-        const unsigned rstride = a.ldn * (unsigned)sizeof(T);
-        const int4* wsv = reinterpret_cast<const int4*>(WS() + base);
-        int id[RB];
+        unsigned okmask = 0;
 #pragma unroll
-        for (int v4 = 0; v4 < RB / 4; v4++) { const int4 t = wsv[v4]; id[4 * v4] = t.x; id[4 * v4 + 1] = t.y; id[4 * v4 + 2] = t.z; id[4 * v4 + 3] = t.w; }
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const char* src = M + (size_t)(unsigned)id[r] * rstride; // ids behind kk are stale but never dereferenced
-#pragma unroll
-            for (int g = 0; g < NG; g++) cp_async16_if(okg[g] && base + r < kk, buf + r * rstride + 512 * g, src + 512 * g);
-        }
-        cp_async_commit();
+        for (int g = 0; g < NG; g++) okmask |= (unsigned)okg[g] << g;
+        issue_rows_fn<T, NG>(WS() + base, kk - base, buf, M, a.ldn * (unsigned)sizeof(T), okmask);
     }
 
     // ---- a2: LDL' row append (factorization.c:21-111) + bookkeeping of daqp_add_constraint (auxiliary.c:27-41)
@@ -283,15 +294,15 @@ struct Warp {
         const int kk = uni(k);
         T* Lk = L() + loff(kk);
         const unsigned buf0 = smem_u32(S) + a.oarena;
-        if (kk > 0) issue_rows(0, kk, buf0 + 16 * lane, M, okg);
         T d = warp_sum(part);
         if (kk > 0) {
             // l_j = M_{WS[j]} . m_add: per-lane partial products of a chunk's rows are parked in the consumed buffer and
             // summed with a transposed read (lane = (row, quarter)) instead of RB full shuffle reductions.
+            issue_rows(0, kk, buf0 + 16 * lane, M, okg);
             for (int c0 = 0; c0 < kk; c0 += RB) {
                 const unsigned cur = buf0 + ((c0 / RB) & 1) * a.rowbuf, nxt = buf0 + (((c0 / RB) & 1) ^ 1) * a.rowbuf;
-                if (c0 + RB < kk) { issue_rows(c0 + RB, kk, nxt + 16 * lane, M, okg); cp_async_wait<1>(); }
-                else cp_async_wait<0>();
+                if (c0 + RB < kk) issue_rows(c0 + RB, kk, nxt + 16 * lane, M, okg); else cp_async_commit();
+                cp_async_wait<1>();
                 T pj[RB];
 #pragma unroll
                 for (int r = 0; r < RB; r++) {
@@ -587,14 +598,14 @@ struct Warp {
         // FMAs in index order (the order of the reference's accumulation, auxiliary.c:54-68)
         const int kk = uni(k);
         const unsigned buf0 = smem_u32(S) + a.oarena + 16 * lane;
-        if (kk > 0) issue_rows(0, kk, buf0, M, okg);
-        for (int c0 = 0; c0 < kk; c0 += RB) {
+        // rotated loop: trip c issues chunk c+1 (or commits an empty group) and consumes chunk c, so the issue code exists once
+        for (int c0 = -RB; c0 < kk; c0 += RB) {
             const unsigned cur = buf0 + ((c0 / RB) & 1) * a.rowbuf, nxt = buf0 + (((c0 / RB) & 1) ^ 1) * a.rowbuf;
-            if (c0 + RB < kk) { issue_rows(c0 + RB, kk, nxt, M, okg); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
+            if (c0 + RB < kk) issue_rows(c0 + RB, kk, nxt, M, okg); else cp_async_commit();
+            cp_async_wait<1>();
 #pragma unroll
             for (int r = 0; r < RB; r++) {
-                if (c0 + r < kk) {
+                if (c0 >= 0 && c0 + r < kk) {
                     const T li = ls[c0 + r];
 #pragma unroll
                     for (int g = 0; g < NG; g++) {
