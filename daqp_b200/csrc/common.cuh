@@ -146,6 +146,10 @@ template <typename T> __device__ __noinline__ T warp_sum(T v) {
 }
 __device__ __noinline__ double fdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+// correctly rounded reciprocal: bit-identical to 1/x (IEEE division is correctly rounded too) at a third of the
+// instructions of the general division, and short enough to inline
+__device__ __forceinline__ double frcp(double x) { return __drcp_rn(x); }
+__device__ __forceinline__ float frcp(float x) { return __frcp_rn(x); }
 
 // Sum B per-lane values across the warp with a transposed butterfly: B/2 + B/4 + ... + 1 exchanges replace B full
 // 5-step reductions. Returns the warp total of value number multi_index<B>(lane); the 32/B lanes that share the

@@ -403,7 +403,7 @@ struct Warp {
                     const T pvt = __shfl_sync(FULL, w[qp], t);
                     const T Dold = Dp[r + 1 + t];
                     const T dbar = Dold + alpha * pvt * pvt;
-                    const T rdb = fdiv((T)1, dbar); // one reciprocal for the two quotients of the reference
+                    const T rdb = frcp(dbar); // one reciprocal (= 1 / dbar, correctly rounded) for the two quotients of the reference
                     const T beta = pvt * alpha * rdb;
                     alpha = Dold * alpha * rdb;
                     if (lane == 0) Dp[r + t] = dbar; // its old value was consumed one step earlier (as alpha for t = 0)

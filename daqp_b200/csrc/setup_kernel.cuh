@@ -28,12 +28,28 @@ struct SetupArgs {
     DevSettings<T> st;
 };
 
-constexpr int SETUP_RB = 4; // rows of A processed together (one 32-byte sector of Mt per lane and column)
+template <typename T> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+constexpr int SETUP_RB = 8; // rows of A processed together (two 32-byte sectors of Mt per lane and column)
 
 template <typename T>
 __host__ __device__ inline size_t setup_smem_per_warp(int n) {
     size_t e = (size_t)n * (n + 1) / 2 + (size_t)n * (2 + SETUP_RB);
     return (e * sizeof(T) + 15) / 16 * 16;
+}
+
+// Cooperative asynchronous copy of a contiguous block of `bytes` (a multiple of 8) from global to shared memory:
+// 16-byte cp.async when source and size allow it, 8-byte otherwise (odd n, or caller arrays that are only 8-byte
+// aligned). One commit group; the caller waits with cp_async_wait + __syncwarp.
+__device__ __forceinline__ void async_block_copy(unsigned dst, const char* src, unsigned bytes, int lane) {
+    if (((reinterpret_cast<size_t>(src) | bytes) & 15) == 0) {
+        for (unsigned off = 16u * lane; off < bytes; off += 512u) cp_async16(dst + off, src + off);
+    } else {
+        for (unsigned off = 8u * lane; off < bytes; off += 256u)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + off), "l"(src + off) : "memory");
+    }
+    cp_async_commit();
 }
 
 template <typename T, int NGS>
@@ -42,10 +58,10 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = a.n, m = a.m, ms = a.ms, mA = a.m - a.ms, ldm = a.ldm, ldn = a.ldn;
     const int ntri = n * (n + 1) / 2;
-    T* R = reinterpret_cast<T*>(smem_raw + setup_smem_per_warp<T>(n) * wib);
+    T* arow = reinterpret_cast<T*>(smem_raw + setup_smem_per_warp<T>(n) * wib); // SETUP_RB staged rows of A (16-byte aligned)
+    T* R = arow + (size_t)n * SETUP_RB;
     T* vv = R + ntri;          // f, then v = R^-T f
     T* xu = vv + n;            // unconstrained optimum
-    T* arow = xu + n;          // SETUP_RB staged rows of A
     const DevSettings<T>& st = a.st;
 
     for (;;) {
@@ -69,6 +85,16 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         unsigned char* so = a.sense + (size_t)p * ldm;
         T* Rg = a.Rinv + (size_t)p * ntri;
         int flag = SETUP_SOLVE;
+        // pull this problem's A into L2 now: the factorisation below gives the prefetch ~20k instructions of cover, so the
+        // row blocks of the product loop are L2 hits instead of exposed HBM round trips
+        if (lane == 0 && mA > 0) {
+            const char* ab = reinterpret_cast<const char*>(A);
+            const size_t abytes = ((size_t)mA * n * sizeof(T)) & ~(size_t)15;
+            const size_t mis = (16 - (reinterpret_cast<size_t>(ab) & 15)) & 15; // bulk prefetch needs 16-byte alignment
+            for (size_t off = mis; off + 16 <= abytes; off += 32768)
+                bulk_prefetch_l2(ab + off, (unsigned)(((abytes - off) < 32768 ? (abytes - off) : 32768) & ~(size_t)15));
+        }
+        __syncwarp();
 
         // ---- sense copy + check_bounds (utils.c:84-98, 546-567)
         int any_fixed = 0, bad = 0, unsupported = 0;
@@ -144,7 +170,8 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                 di = rsqrt_exact<T>(di);
                 for (int j = i + 1 + lane; j < n; j += 32) {
                     T s = Ri[j];
-                    for (int kk = 0; kk < i; kk++) { const T* Rk = R + roff(kk, n); s -= Rk[i] * Rk[j]; }
+                    const T* Rk = R; // running row pointer: roff(kk+1) = roff(kk) + (n - kk - 1)
+                    for (int kk = 0; kk < i; kk++) { s -= Rk[i] * Rk[j]; Rk += n - kk - 1; }
                     Ri[j] = s * di;
                 }
                 if (lane == 0) Ri[i] = di;
@@ -209,12 +236,18 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
 
         // ---- general rows: M = A R^-1, normalise, d (utils.c:434-472, 586-613, 663-678 / 499-544)
         int zero_row_infeasible = 0;
+        // The row blocks of A stream through ONE staging buffer with cp.async: the copy of block k+1 is issued as soon as
+        // the product loop of block k has read the buffer, and lands while block k's norms / d / stores are computed.
+        const unsigned stage = smem_u32(arow);
+        if (mA > 0) async_block_copy(stage, reinterpret_cast<const char*>(A), (unsigned)(min(SETUP_RB, mA) * n * sizeof(T)), lane);
         for (int r0 = 0; r0 < mA; r0 += SETUP_RB) {
             const int nr = min(SETUP_RB, mA - r0);
-            for (int idx = lane; idx < SETUP_RB * n; idx += 32) {
-                const int b = idx / n;
-                arow[idx] = (b < nr) ? A[(size_t)(r0 + b) * n + (idx - b * n)] : (T)0;
-            }
+            // the block's bounds, one row per lane, fetched before the product so that their latency is covered
+            T bub = 0, blb = 0;
+            if (lane < nr) { bub = bu[ms + r0 + lane]; blb = bl[ms + r0 + lane]; }
+            cp_async_wait<0>();
+            if (nr < SETUP_RB) // last, partial block: the missing rows read as zeros
+                for (int idx = nr * n + lane; idx < SETUP_RB * n; idx += 32) arow[idx] = 0;
             __syncwarp();
             T acc[SETUP_RB][NGS];
 #pragma unroll
@@ -222,59 +255,95 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
 #pragma unroll
                 for (int g = 0; g < NGS; g++) acc[b][g] = 0;
             // M[r][c] = sum_{i<=c} A[r][i] Rinv[i][c], accumulated from i = c down to 0 as the reference does
-            for (int i = n - 1; i >= 0; i--) {
-                const T* Ri = R + roff(i, n);
-                T ai[SETUP_RB];
+            {
+                const T* Ri = R + roff(n - 1, n); // running row pointer: roff(i-1) = roff(i) - (n - i)
+                const T* ap = arow + (n - 1); // column i of the staged rows: ap[b * n]
+                int lim[NGS]; // column index, or -1 for lanes without a column in this segment
 #pragma unroll
-                for (int b = 0; b < SETUP_RB; b++) ai[b] = arow[b * n + i];
+                for (int g = 0; g < NGS; g++) { const int c = lane + 32 * g; lim[g] = c < n ? c : -1; }
+#pragma unroll 2
+                for (int i = n - 1; i >= 0; i--) {
+                    T ai[SETUP_RB];
 #pragma unroll
-                for (int g = 0; g < NGS; g++) {
-                    const int c = lane + 32 * g;
-                    if (c >= i && c < n) {
-                        const T rv = Ri[c];
+                    for (int b = 0; b < SETUP_RB; b++) ai[b] = ap[b * n]; // broadcast reads
 #pragma unroll
-                        for (int b = 0; b < SETUP_RB; b++) acc[b][g] += rv * ai[b];
+                    for (int g = 0; g < NGS; g++) {
+                        if (lim[g] >= i) {
+                            const T rv = Ri[lane + 32 * g];
+#pragma unroll
+                            for (int b = 0; b < SETUP_RB; b++) acc[b][g] += rv * ai[b];
+                        }
                     }
+                    Ri -= n - i;
+                    ap -= 1;
                 }
             }
-            T scal[SETUP_RB];
+            // Row norms, scaling and d for the RB rows of the block, arranged in three branch-free phases so that the
+            // 2 RB warp reductions overlap instead of forming one long dependent chain (same operations per value).
+            T nrmv[SETUP_RB], scal[SETUP_RB], dotv[SETUP_RB];
+#pragma unroll
+            for (int b = 0; b < SETUP_RB; b++) { // A_row . x_unc needs the staged rows: take it before the buffer is refilled
+                T t = 0;
+                if (unc) {
+#pragma unroll
+                    for (int g = 0; g < NGS; g++) { const int c = lane + 32 * g; if (c < n) t += arow[b * n + c] * xu[c]; }
+                }
+                dotv[b] = t;
+            }
+            __syncwarp(); // every lane is done with the staged rows
+            if (r0 + SETUP_RB < mA)
+                async_block_copy(stage, reinterpret_cast<const char*>(A + (size_t)(r0 + SETUP_RB) * n),
+                                 (unsigned)(min(SETUP_RB, mA - r0 - SETUP_RB) * n * sizeof(T)), lane);
 #pragma unroll
             for (int b = 0; b < SETUP_RB; b++) {
-                T nrm = 0, dotd = 0;
+                T t = 0;
 #pragma unroll
-                for (int g = 0; g < NGS; g++) nrm += acc[b][g] * acc[b][g];
-                nrm = warp_sum(nrm);
-                const int row = ms + r0 + b; // constraint index
-                int sb = (b < nr) ? so[row] : 0;
-                T s = 1;
-                if (b < nr) {
-                    if (nrm < st.zero_tol) { // utils.c:595-606
-                        if ((bu[row] < -st.zero_tol || bl[row] > st.zero_tol) && !(sb & B_IMMUTABLE))
-                            zero_row_infeasible = 1;
-                        sb = B_IMMUTABLE;
-                    } else {
-                        s = rsqrt_exact<T>(nrm);
+                for (int g = 0; g < NGS; g++) t += acc[b][g] * acc[b][g];
+                nrmv[b] = t;
+            }
 #pragma unroll
-                        for (int g = 0; g < NGS; g++) acc[b][g] *= s;
-                    }
-                }
-                scal[b] = s;
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int b = 0; b < SETUP_RB; b++) nrmv[b] += __shfl_xor_sync(FULL, nrmv[b], o);
+#pragma unroll
+            for (int b = 0; b < SETUP_RB; b++) {
+                const bool scale = b < nr && !(nrmv[b] < st.zero_tol); // utils.c:595-606: zero rows are not scaled
+                const T sv = rsqrt_exact<T>(scale ? nrmv[b] : (T)1);   // exactly 1 for unscaled rows
+                scal[b] = sv;
+                T t = dotv[b];
 #pragma unroll
                 for (int g = 0; g < NGS; g++) {
+                    acc[b][g] *= sv;
                     const int c = lane + 32 * g;
-                    if (c < n) dotd += unc ? arow[b * n + c] * xu[c] : acc[b][g] * vv[c];
+                    if (!unc && c < n) t += acc[b][g] * vv[c];
                 }
-                dotd = warp_sum(dotd);
-                if (b < nr && lane == 0) {
-                    T u_ = bu[row], l_ = bl[row];
-                    if (unc) {
-                        u_ -= dotd; l_ -= dotd;
-                        if (u_ < -st.primal_tol || l_ > st.primal_tol) infeasible_pt = 1;
-                        u_ *= s; l_ *= s;
-                    } else {
-                        u_ = u_ * s + dotd; l_ = l_ * s + dotd;
+                dotv[b] = t;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int b = 0; b < SETUP_RB; b++) dotv[b] += __shfl_xor_sync(FULL, dotv[b], o);
+            {
+                // lane b finishes row b (its bounds are already in bub / blb): four coalesced stores for the block
+                T s_my = 1, d_my = 0, n_my = 1;
+#pragma unroll
+                for (int b = 0; b < SETUP_RB; b++) if (lane == b) { s_my = scal[b]; d_my = dotv[b]; n_my = nrmv[b]; }
+                if (lane < nr) {
+                    const int row = ms + r0 + lane; // constraint index
+                    int sb = so[row];
+                    if (n_my < st.zero_tol) {
+                        if ((bub < -st.zero_tol || blb > st.zero_tol) && !(sb & B_IMMUTABLE)) zero_row_infeasible = 1;
+                        sb = B_IMMUTABLE;
                     }
-                    du[row] = u_; dl[row] = l_; sc[row] = s; so[row] = (unsigned char)sb;
+                    T u_ = bub, l_ = blb;
+                    if (unc) {
+                        u_ -= d_my; l_ -= d_my;
+                        if (u_ < -st.primal_tol || l_ > st.primal_tol) infeasible_pt = 1;
+                        u_ *= s_my; l_ *= s_my;
+                    } else {
+                        u_ = u_ * s_my + d_my; l_ = l_ * s_my + d_my;
+                    }
+                    du[row] = u_; dl[row] = l_; sc[row] = s_my; so[row] = (unsigned char)sb;
                 }
             }
             // row-major copy (coalesced), column-major copy (one 32-byte sector per lane and column)
@@ -344,8 +413,8 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         __syncwarp();
         for (int idx = lane; idx < ntri; idx += 32) Rg[idx] = R[idx];
 
-        infeasible_pt = __shfl_sync(FULL, infeasible_pt, 0);
-        zero_row_infeasible = __shfl_sync(FULL, zero_row_infeasible, 0);
+        infeasible_pt = __any_sync(FULL, infeasible_pt);
+        zero_row_infeasible = __any_sync(FULL, zero_row_infeasible);
         if (unc && !infeasible_pt) { // utils.c:679-683 + api.c:40-45,455-495: solve is skipped
             for (int i = lane; i < n; i += 32) a.x[(size_t)p * n + i] = xu[i];
             if (a.lam) for (int i = lane; i < m; i += 32) a.lam[(size_t)p * m + i] = 0;

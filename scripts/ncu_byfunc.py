@@ -2,7 +2,7 @@
 usage: ncu_byfunc.py <report.ncu-rep>"""
 import csv, re, subprocess, sys, collections
 rep = sys.argv[1]
-src = open('daqp_b200/csrc/ldp_kernel.cuh').read().splitlines()
+src = open(sys.argv[2] if len(sys.argv)>2 else 'daqp_b200/csrc/ldp_kernel.cuh').read().splitlines()
 # function starts: lines with '__device__' and '(' -> name
 starts = []
 for i, l in enumerate(src, 1):
@@ -27,7 +27,7 @@ for r in rows:
     d = dict(zip(hdr[4:], r[4:]))
     try: i = int(d['Instructions Executed']); s = int(d['# Samples'])
     except Exception: continue
-    key = func(int(r[0])) if cur == 'ldp_kernel.cuh' else cur
+    key = func(int(r[0])) if cur in ('ldp_kernel.cuh','setup_kernel.cuh') else cur
     inst[key] += i; samp[key] += s
 ti = sum(inst.values()); ts = sum(samp.values())
 for k, v in inst.most_common(30):
