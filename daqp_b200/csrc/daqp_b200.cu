@@ -342,9 +342,14 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
     if (N <= 0) return 0;
     if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
     const int mA = m - ms, cap = n + 1, ldm = round_up(std::max(m, 1), 4);
-    int chunk = 16384;
-    if (const char* c = getenv("DAQP_B200_HOST_CHUNK")) chunk = std::max(1, atoi(c));
+    // The pipeline is bound by the host link (8.3 GB per 100k C3 problems at ~55 GB/s): what is left to tune is the part
+    // that cannot overlap -- the first chunk's copy-in and the last chunk's solve -- so chunks are small (8192) and
+    // the first one smaller still. Measured on C3: 16384 -> 174 ms, 8192 -> 163 ms, ramped 8192 -> see DESIGN.md.
+    int chunk = 8192, first_chunk = 2048;
+    if (const char* c = getenv("DAQP_B200_HOST_CHUNK")) { chunk = std::max(1, atoi(c)); first_chunk = chunk; }
+    if (const char* c = getenv("DAQP_B200_HOST_FIRST_CHUNK")) first_chunk = std::max(1, atoi(c));
     chunk = std::min(chunk, N);
+    first_chunk = std::min(first_chunk, chunk);
     const size_t in_b = ((size_t)n * n + n + (size_t)mA * n + 2 * (size_t)m) * sizeof(T) + (size_t)m * sizeof(int);
     const size_t out_b = ((size_t)n + m + 1) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
     const size_t per_buf = (size_t)chunk * (in_b + out_b) + 16 * 256;
@@ -370,8 +375,17 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
         CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
     }
     int result = 0, c = 0;
-    for (int p0 = 0; p0 < N && result == 0; p0 += chunk, c++) {
-        const int P = std::min(chunk, N - p0), s = c & 1;
+    // chunk schedule: small first chunk (its copy-in is exposed), small last chunk (its solve and copy-out are exposed)
+    std::vector<int> sched;
+    for (int left = N; left > 0;) {
+        int P = std::min(sched.empty() ? first_chunk : chunk, left);
+        if (left > first_chunk && left - P < first_chunk) P = left - first_chunk; // leave exactly one small chunk
+        sched.push_back(P);
+        left -= P;
+    }
+    int p0 = 0;
+    for (size_t ci = 0; ci < sched.size() && result == 0; p0 += sched[ci], ci++, c++) {
+        const int P = sched[ci], s = c & 1;
         Buf& B = b[s];
         // input buffers are free once the solve that read them (two chunks ago) has finished
         if (c >= 2) CK(cudaStreamWaitEvent(h->copy_in, ev_done[s], 0));

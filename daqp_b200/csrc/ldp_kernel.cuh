@@ -339,13 +339,11 @@ struct Warp {
             T acc = 0;
 #pragma unroll
             for (int q = 0; q < NV; q++) {
+                if (q > 0 && 32 * q >= kk) break; // uniform: no rows in this register segment
                 const int i = lane + 32 * q;
-                if (i < kk) {
-                    const T t = lv[q];
-                    const T qd = fdiv(t, Dp[i]);
-                    Lk[i] = qd;
-                    acc += t * qd;
-                }
+                const T t = lv[q];
+                const T qd = fdiv(t, i < kk ? Dp[i] : (T)1); // unconditional call: no divergence around the division
+                if (i < kk) { Lk[i] = qd; acc += t * qd; }
             }
             d -= warp_sum(acc);
             if (uni(d < a.st.sing_tol || kk >= a.n)) { // ns_active == 0 on this path (soft constraints not in kernel yet)
@@ -513,6 +511,7 @@ struct Warp {
         const T* Dp = D();
 #pragma unroll
         for (int q = 0; q < NV; q++) {
+            if (q > 0 && 32 * q >= kk) { xv[q] = 0; continue; } // uniform: no rows in this register segment
             const int i = lane + 32 * q;
             const bool fresh = i >= r && i < kk;
             const T zi = fdiv(xv[q], fresh ? Dp[i] : (T)1); // unconditional call: no divergence around the division
@@ -559,6 +558,8 @@ struct Warp {
         T lv[NV], sv[NV];
 #pragma unroll
         for (int q = 0; q < NV; q++) {
+            lv[q] = 0; sv[q] = 0;
+            if (q > 0 && 32 * q >= kk) continue; // uniform: no rows in this register segment
             const int i = lane + 32 * q;
             const bool valid = i < kk;
             const int sb = valid ? se[ws[i]] : B_IMMUTABLE;
@@ -744,27 +745,18 @@ struct Warp {
         const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + 16 * lane;
         const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane;
         const int nq = (a.n + 3) >> 2;
-        // ring slots are static (the quad loop is unrolled QRING times); every step commits one group, possibly empty
-#pragma unroll
-        for (int sl = 0; sl < QRING; sl++) {
-            if (sl < nq) {
-#pragma unroll
-                for (int r = 0; r < NR; r++) {
-                    if (r < NR - 1) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r);
-                    else cp_async16_if(own_last, ring0 + sl * slab + 512 * r, src + 512 * r);
-                }
-                src += slab;
-            }
-            cp_async_commit();
-        }
-        unsigned ub = smem_u32(u32());
-        for (int q0 = 0; q0 < nq; q0 += QRING) {
+        // Ring slots are static (the quad loop is unrolled QRING times) and the loop is rotated: the trip that consumes
+        // quad q also issues quad q + QRING into the slot it has just read, so the first trip (q < 0) is the prologue and
+        // the issue code exists once. Every step commits one group, possibly empty.
+        const unsigned ub = smem_u32(u32());
+        for (int q0 = -QRING; q0 < nq; q0 += QRING) {
 #pragma unroll
             for (int sl = 0; sl < QRING; sl++) {
-                if (q0 + sl < nq) {
+                const int q = q0 + sl;
+                if (q >= 0 && q < nq) {
                     cp_async_wait<QRING - 1>();
                     float uq[4];
-                    lds_vec<float>(ub + 16 * sl, uq);
+                    lds_vec<float>(ub + 16 * q, uq);
 #pragma unroll
                     for (int r = 0; r < NR; r++) {
                         if (r < NR - 1 || own_last) {
@@ -774,18 +766,17 @@ struct Warp {
                             for (int e = 0; e < 4; e++) acc[r] += t[e] * uq[e];
                         }
                     }
-                    if (q0 + sl + QRING < nq) {
-#pragma unroll
-                        for (int r = 0; r < NR; r++) {
-                            if (r < NR - 1) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r);
-                            else cp_async16_if(own_last, ring0 + sl * slab + 512 * r, src + 512 * r);
-                        }
-                        src += slab;
-                    }
-                    cp_async_commit();
                 }
+                if (q + QRING < nq) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) {
+                        if (r < NR - 1) cp_async16(ring0 + sl * slab + 512 * r, src + 512 * r);
+                        else cp_async16_if(own_last, ring0 + sl * slab + 512 * r, src + 512 * r);
+                    }
+                    src += slab;
+                }
+                cp_async_commit();
             }
-            ub += 16 * QRING;
         }
         cp_async_wait<0>();
         // candidates in double from the float products; track the best and the runner-up among "possible" candidates
