@@ -46,7 +46,7 @@ class DAQPResult(C.Structure):  # reference include/api.h:15-27
 
 
 class DAQPB200Diag(C.Structure):
-    _fields_ = [("n_active", _ip), ("ws", _ip), ("counts", _ip), ("sense", C.POINTER(C.c_ubyte))]
+    _fields_ = [("n_active", _ip), ("ws", _ip), ("counts", _ip), ("sense", C.POINTER(C.c_ubyte)), ("soft_slack", _dp)]
 
 
 class DAQPB200Stats(C.Structure):
@@ -120,11 +120,12 @@ def solve(H, f, A, bupper, blower=None, sense=None, **settings):
     res = DAQPResult(_p(x), _p(lam) if m else None, 0, 0, 0, 0, 0, 0, 0)
     lib().daqp_quadprog(C.byref(res), C.byref(qp), C.byref(st))
     return x, res.fval, res.exitflag, {"solve_time": res.solve_time, "setup_time": res.setup_time,
-                                       "iterations": res.iter, "nodes": res.nodes, "lam": lam}
+                                       "iterations": res.iter, "nodes": res.nodes, "lam": lam,
+                                       "soft_slack": res.soft_slack}
 
 
 class BatchResult:
-    __slots__ = ("x", "lam", "fval", "exitflag", "iter", "n_active", "ws", "counts", "sense")
+    __slots__ = ("x", "lam", "fval", "exitflag", "iter", "n_active", "ws", "counts", "sense", "soft_slack")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -177,10 +178,12 @@ class Engine:
         d = None
         if diag:
             ldm = (max(m, 1) + 3) // 4 * 4
-            r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + 1), np.intc)
+            ns = 0 if sense is None else int(((sense & SOFT) != 0).sum(axis=1).max(initial=0))
+            r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + ns + 1), np.intc)
             r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
+            r.soft_slack = np.zeros(N)
             d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
-                             r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)))
+                             r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)), _p(r.soft_slack))
         st = default_settings(**settings)
         _check(lib().daqp_b200_solve_packed(self._h, N, n, m, ms, _p(H), _p(f), _p(A), _p(bupper), _p(blower),
                                             _p(sense, _ip), C.byref(st), _p(r.x), _p(r.lam), _p(r.fval),
@@ -215,7 +218,8 @@ class Engine:
         if diag is not None:
             d = DAQPB200Diag(C.cast(diag["n_active"].data_ptr(), _ip), C.cast(diag["ws"].data_ptr(), _ip),
                              C.cast(diag["counts"].data_ptr(), _ip),
-                             C.cast(diag["sense"].data_ptr(), C.POINTER(C.c_ubyte)))
+                             C.cast(diag["sense"].data_ptr(), C.POINTER(C.c_ubyte)),
+                             C.cast(diag["soft_slack"].data_ptr(), _dp) if "soft_slack" in diag else None)
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         if stream == 0:
@@ -229,11 +233,13 @@ class Engine:
         return out
 
     @staticmethod
-    def alloc_diag(N: int, n: int, m: int, device):
+    def alloc_diag(N: int, n: int, m: int, device, ns: int = 0):
+        """ns = the largest number of soft constraints per problem (rows of ``ws`` hold n + ns + 1 entries)."""
         import torch
         ldm = (max(m, 1) + 3) // 4 * 4
         return {"n_active": torch.zeros(N, dtype=torch.int32, device=device),
-                "ws": torch.zeros((N, n + 1), dtype=torch.int32, device=device),
+                "soft_slack": torch.zeros(N, dtype=torch.float64, device=device),
+                "ws": torch.zeros((N, n + ns + 1), dtype=torch.int32, device=device),
                 "counts": torch.zeros((N, 4), dtype=torch.int32, device=device),
                 "sense": torch.zeros((N, ldm), dtype=torch.uint8, device=device)}
 
@@ -271,4 +277,5 @@ def quadprog_batch(problems: list[dict], **settings):
     _check(lib().daqp_quadprog_batch(N, qps, res, C.byref(st)))
     return [(keep[i][6], res[i].fval, res[i].exitflag,
              {"iterations": res[i].iter, "lam": keep[i][7], "solve_time": res[i].solve_time,
-              "setup_time": res[i].setup_time, "nodes": res[i].nodes}) for i in range(N)]
+              "setup_time": res[i].setup_time, "nodes": res[i].nodes, "soft_slack": res[i].soft_slack})
+            for i in range(N)]

@@ -201,17 +201,43 @@ static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size
     return cudaGetLastError();
 }
 
+// Largest number of soft constraints (sense & 8) any problem of the batch carries: it sizes the factor storage
+// (the reference allocates n + ns + 1 rows, src/api.c:305-313).
+__global__ void max_soft_kernel(const int* sense, int N, int m, int* out) {
+    int best = 0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        int c = 0;
+        for (int i = 0; i < m; i++) c += (sense[(size_t)p * m + i] & B_SOFT) ? 1 : 0;
+        best = max(best, c);
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, best);
+}
+
 // Device-resident batch: the core of every entry point.
 template <typename T>
 static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, const T* dH, const T* df, const T* dA,
                              const T* dbu, const T* dbl, const int* dsense, const DAQPSettings* settings, T* dx,
-                             T* dlam, T* dfval, int* dflag, int* diter, const DAQPB200Diag* diag, cudaStream_t stream) {
+                             T* dlam, T* dfval, int* dflag, int* diter, const DAQPB200Diag* diag, cudaStream_t stream,
+                             int ns_max = -1) {
     if (N <= 0) return 0;
     if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
     constexpr int V = VecOf<T>::N;
-    const int ldm = round_up(std::max(m, 1), 4), ldn = round_up(n, V), cap = n + 1, mA = m - ms;
+    if (!dsense) ns_max = 0;
+    if (ns_max < 0) { // sense lives on the device: count there (one small kernel and a 4-byte read-back)
+        int* dcount = nullptr;
+        int rc0 = ensure(&h->arena, &h->arena_bytes, 1 << 20);
+        if (rc0) return rc0;
+        dcount = reinterpret_cast<int*>(h->arena);
+        CK(cudaMemsetAsync(dcount, 0, sizeof(int), stream));
+        max_soft_kernel<<<std::min(1024, (N + 127) / 128), 128, 0, stream>>>(dsense, N, m, dcount);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&ns_max, dcount, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    const int ldm = round_up(std::max(m, 1), 4), ldn = round_up(n, V), cap = n + ns_max + 1, mA = m - ms;
     const int nv = (cap + 31) / 32, ngs = (n + 31) / 32; // register segments of a length-cap vector / of a row
-    if (nv > 8 || ngs > 8) { g_last_error = "daqp_b200: n > 255 is not supported"; return -2; }
+    if (nv > 8 || ngs > 8) { g_last_error = "daqp_b200: n + (soft constraints) > 255 is not supported"; return -2; }
 
     LdpArgs<T> la;
     memset(&la, 0, sizeof(la));
@@ -267,6 +293,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         sa.x = dx + (size_t)p0 * n; sa.lam = dlam ? dlam + (size_t)p0 * m : nullptr; sa.fval = dfval + p0;
         sa.exitflag = dflag + p0; sa.iter = diter + p0;
         sa.work_counter = counters; sa.st = st;
+        sa.soft_slack = (diag && diag->soft_slack) ? diag->soft_slack + p0 : nullptr; sa.ns_max = ns_max;
         {
             const int grid = std::min(grid_max, (P + w_setup - 1) / w_setup);
             const size_t smem = smem_setup_w * w_setup;
@@ -292,6 +319,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.counts_out = (diag && diag->counts) ? diag->counts + 4 * (size_t)p0 : nullptr;
         la.sense_out = (diag && diag->sense) ? diag->sense + (size_t)p0 * ldm : nullptr;
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
+        la.soft_slack = sa.soft_slack; la.ns_max = ns_max;
         la.tune = tune;
         {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
@@ -341,7 +369,14 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
     CK(cudaSetDevice(h->device));
     if (N <= 0) return 0;
     if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
-    const int mA = m - ms, cap = n + 1, ldm = round_up(std::max(m, 1), 4);
+    int ns_max = 0; // most soft constraints per problem: sizes the factor (and the ws diagnostic rows)
+    if (sense)
+        for (int p = 0; p < N; p++) {
+            int c = 0;
+            for (int i = 0; i < m; i++) c += (sense[(size_t)p * m + i] & DAQP_SOFT) ? 1 : 0;
+            ns_max = std::max(ns_max, c);
+        }
+    const int mA = m - ms, cap = n + ns_max + 1, ldm = round_up(std::max(m, 1), 4);
     // The pipeline is bound by the host link (8.3 GB per 100k C3 problems at ~55 GB/s): what is left to tune is the part
     // that cannot overlap -- the first chunk's copy-in and the last chunk's solve -- so chunks are small (8192) and
     // the first one smaller still. Measured on C3: 16384 -> 174 ms, 8192 -> 163 ms, ramped 8192 -> see DESIGN.md.
@@ -351,12 +386,12 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
     chunk = std::min(chunk, N);
     first_chunk = std::min(first_chunk, chunk);
     const size_t in_b = ((size_t)n * n + n + (size_t)mA * n + 2 * (size_t)m) * sizeof(T) + (size_t)m * sizeof(int);
-    const size_t out_b = ((size_t)n + m + 1) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
-    const size_t per_buf = (size_t)chunk * (in_b + out_b) + 16 * 256;
+    const size_t out_b = ((size_t)n + m + 2) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
+    const size_t per_buf = (size_t)chunk * (in_b + out_b) + 17 * 256;
     int rc = ensure(&h->stage, &h->stage_bytes, 2 * per_buf);
     if (rc) return rc;
 
-    struct Buf { T *H, *f, *A, *bu, *bl; int* sense; T *x, *lam, *fval; int *flag, *iter, *nact, *ws, *counts; unsigned char* so; };
+    struct Buf { T *H, *f, *A, *bu, *bl; int* sense; T *x, *lam, *fval, *slack; int *flag, *iter, *nact, *ws, *counts; unsigned char* so; };
     Buf b[2];
     for (int i = 0; i < 2; i++) {
         Carver cv(h->stage + i * per_buf);
@@ -364,7 +399,7 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
         b[i].A = cv.take<T>((size_t)chunk * mA * n); b[i].bu = cv.take<T>((size_t)chunk * m);
         b[i].bl = cv.take<T>((size_t)chunk * m); b[i].sense = cv.take<int>((size_t)chunk * m);
         b[i].x = cv.take<T>((size_t)chunk * n); b[i].lam = cv.take<T>((size_t)chunk * m);
-        b[i].fval = cv.take<T>(chunk); b[i].flag = cv.take<int>(chunk); b[i].iter = cv.take<int>(chunk);
+        b[i].fval = cv.take<T>(chunk); b[i].slack = cv.take<T>(chunk); b[i].flag = cv.take<int>(chunk); b[i].iter = cv.take<int>(chunk);
         b[i].nact = cv.take<int>(chunk); b[i].ws = cv.take<int>((size_t)chunk * cap);
         b[i].counts = cv.take<int>((size_t)chunk * 4); b[i].so = cv.take<unsigned char>((size_t)chunk * ldm);
     }
@@ -402,10 +437,11 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
         if (c >= 2) CK(cudaStreamWaitEvent(h->compute, ev_out[s], 0)); // output buffers drained
         DAQPB200Diag dd{};
         if (diag) { dd.n_active = diag->n_active ? B.nact : nullptr; dd.ws = diag->ws ? B.ws : nullptr;
-                    dd.counts = diag->counts ? B.counts : nullptr; dd.sense = diag->sense ? B.so : nullptr; }
+                    dd.counts = diag->counts ? B.counts : nullptr; dd.sense = diag->sense ? B.so : nullptr;
+                    dd.soft_slack = diag->soft_slack ? B.slack : nullptr; }
         result = solve_device_impl<T>(h, P, n, m, ms, B.H, f ? B.f : nullptr, B.A, B.bu, B.bl, sense ? B.sense : nullptr,
                                       settings, B.x, lam ? B.lam : nullptr, B.fval, B.flag, B.iter, diag ? &dd : nullptr,
-                                      h->compute);
+                                      h->compute, ns_max);
         if (result) break;
         CK(cudaEventRecord(ev_done[s], h->compute));
         CK(cudaStreamWaitEvent(h->copy_out, ev_done[s], 0));
@@ -419,6 +455,7 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
             if (diag->ws) CK(cudaMemcpyAsync(diag->ws + (size_t)p0 * cap, B.ws, (size_t)P * cap * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
             if (diag->counts) CK(cudaMemcpyAsync(diag->counts + (size_t)p0 * 4, B.counts, (size_t)P * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
             if (diag->sense) CK(cudaMemcpyAsync(diag->sense + (size_t)p0 * ldm, B.so, (size_t)P * ldm, cudaMemcpyDeviceToHost, h->copy_out));
+            if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack + p0, B.slack, (size_t)P * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
         }
         CK(cudaEventRecord(ev_out[s], h->copy_out));
     }
@@ -453,6 +490,9 @@ extern "C" int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQ
         const size_t G = ids.size();
         std::vector<c_float> H(G * n * n), f(has_f ? G * n : 0), A(G * mA * n), bu(G * m), bl(G * m), x(G * n), lam(G * m), fv(G);
         std::vector<int> se(has_s ? G * m : 0), flag(G), it(G);
+        std::vector<c_float> slack(G, 0);
+        DAQPB200Diag dg{};
+        dg.soft_slack = slack.data();
         for (size_t g = 0; g < G; g++) {
             const DAQPProblem& q = qps[ids[g]];
             memcpy(&H[g * n * n], q.H, sizeof(c_float) * n * n);
@@ -466,7 +506,7 @@ extern "C" int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQ
         daqp_b200_get_stats(h, &before, 0);
         rc = daqp_b200_solve_packed(h, (int)G, n, m, ms, H.data(), has_f ? f.data() : nullptr, A.data(), bu.data(),
                                     bl.data(), has_s ? se.data() : nullptr, settings, x.data(), lam.data(), fv.data(),
-                                    flag.data(), it.data(), nullptr);
+                                    flag.data(), it.data(), &dg);
         if (rc) return rc;
         daqp_b200_get_stats(h, &after, 0);
         for (size_t g = 0; g < G; g++) {
@@ -481,6 +521,7 @@ extern "C" int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQ
             memcpy(r.x, &x[g * n], sizeof(c_float) * n);
             if (r.lam && m > 0) memcpy(r.lam, &lam[g * m], sizeof(c_float) * m);
             if (has_f) r.fval = fv[g];
+            r.soft_slack = slack[g];
         }
     }
     return 0;

@@ -67,6 +67,8 @@ struct LdpArgs {
     T* x;                     // [P][n]
     T* lam;                   // [P][m] or nullptr
     T* fval;                  // [P]
+    T* soft_slack;            // [P] or nullptr
+    int ns_max;               // most soft constraints (sense & 8) any problem of the batch carries; cap = n + ns_max + 1
     int* exitflag;            // [P]
     int* iter;                // [P]
     int* ws_out;              // [P][cap] or nullptr : final working set (factor order)
@@ -159,7 +161,7 @@ struct Warp {
     int lane, p;         // lane id, problem index
     int k, reuse, sing;  // warp-uniform solver state (n_active, reuse_ind, sing_ind)
     int lsw;             // which of the two lambda buffers currently is `lam` (the reference swaps pointers)
-    T fval;
+    T fval, soft_slack;
     int* pst_id; T* pst_lam;
     // daqp_ldp loop state (daqp.c:7-10), kept across step() calls
     int iter, tried_repair, cycle_counter;
@@ -295,6 +297,16 @@ struct Warp {
         T* Lk = L() + loff(kk);
         const unsigned buf0 = smem_u32(S) + a.oarena;
         T d = warp_sum(part);
+        int ns_active = 0; // soft constraints in the working set, the entering one included (factorization.c:48-52,60-62)
+        if (a.ns_max > 0) {
+            if (sb & B_SOFT) { d += a.st.rho_soft; ns_active = 1; }
+            const unsigned char* se = sense();
+            const int* wsp = WS();
+            for (int base = 0; base < kk; base += 32) {
+                const int i = base + lane;
+                ns_active += __popc(__ballot_sync(FULL, i < kk && (se[wsp[min(i, kk - 1)]] & B_SOFT)));
+            }
+        }
         if (kk > 0) {
             // l_j = M_{WS[j]} . m_add: per-lane partial products of a chunk's rows are parked in the consumed buffer and
             // summed with a transposed read (lane = (row, quarter)) instead of RB full shuffle reductions.
@@ -346,7 +358,7 @@ struct Warp {
                 if (i < kk) { Lk[i] = qd; acc += t * qd; }
             }
             d -= warp_sum(acc);
-            if (uni(d < a.st.sing_tol || kk >= a.n)) { // ns_active == 0 on this path (soft constraints not in kernel yet)
+            if (uni(d < a.st.sing_tol || kk >= a.n + ns_active)) {
                 sing = kk;
                 d = 0;
             }
@@ -630,7 +642,16 @@ struct Warp {
                 for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
             }
         }
-        fval = uni(warp_sum(part)); // soft_slack == 0 on this path
+        T slack = 0; // soft_slack = rho_soft * sum over soft active rows of lam*^2 (auxiliary.c:69-84)
+        if (a.ns_max > 0) {
+            const unsigned char* se = sense();
+            const int* wsp = WS();
+            T sp = 0;
+            LANE_LOOP(i, 0, kk) { if (se[wsp[i]] & B_SOFT) { const T li = ls[i]; sp += li * li; } }
+            slack = uni(warp_sum(sp)) * a.st.rho_soft;
+        }
+        soft_slack = slack;
+        fval = slack + uni(warp_sum(part));
         __syncwarp();
     }
 
@@ -921,7 +942,11 @@ struct Warp {
                 }
             }
             part = warp_sum(part);
-            if (lane == 0) xp[i] = part - dact()[i];
+            if (lane == 0) {
+                T res = part - dact()[i];
+                if (a.ns_max > 0 && (sense()[WS()[i]] & B_SOFT)) res -= a.st.rho_soft * lams()[i]; // auxiliary.c:534-535
+                xp[i] = res;
+            }
         }
         __syncwarp();
         {
@@ -968,7 +993,7 @@ struct Warp {
                 for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
             }
         }
-        fval = uni(warp_sum(part)); // + soft_slack, which is zero on this path
+        fval = soft_slack + uni(warp_sum(part)); // auxiliary.c:589-593: the slack term is not recomputed
         __syncwarp();
     }
 
@@ -1036,7 +1061,7 @@ struct Warp {
                         refine_active();
                         refined = true;
                         again = true;
-                    } else return EXIT_OPTIMAL; // soft_slack == 0 on this path, so never SOFT_OPTIMAL
+                    } else return uni(soft_slack > a.st.primal_tol) ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; // daqp.c:59-62
                 }
             }
         }
@@ -1097,6 +1122,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
         {
             w.lsw = 0;
             w.fval = 0;
+            w.soft_slack = 0;
             const unsigned char* sin = a.sense + (size_t)pq * a.ldm;
             unsigned char* se = w.sense();
             LANE_LOOP(i, 0, a.m) se[i] = sin[i];
@@ -1149,6 +1175,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             }
             if (lane == 0) {
                 if (vv) a.fval[p] = (T)0.5 * (w.fval - vnorm);
+                if (a.soft_slack) a.soft_slack[p] = w.soft_slack;
                 a.exitflag[p] = exitflag;
                 a.iter[p] = w.iter;
             }

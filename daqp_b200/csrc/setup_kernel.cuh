@@ -25,6 +25,8 @@ struct SetupArgs {
     T *x, *lam, *fval;                    // final outputs (written here only for problems finished by the setup)
     int *exitflag, *iter;
     int* work_counter;
+    T* soft_slack;                        // [P] or nullptr
+    int ns_max;                           // upper bound on soft constraints per problem (sizes the solve kernel's factor)
     DevSettings<T> st;
 };
 
@@ -97,23 +99,25 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         __syncwarp();
 
         // ---- sense copy + check_bounds (utils.c:84-98, 546-567)
-        int any_fixed = 0, bad = 0, unsupported = 0;
+        int any_fixed = 0, bad = 0, unsupported = 0, nsoft = 0;
         for (int i = lane; i < ldm; i += 32) {
             int s = 0;
             if (i < m) {
                 s = sin ? sin[i] : 0;
-                if (s & (B_SOFT | B_BINARY) || (s & ~63)) unsupported = 1;
+                if ((s & B_BINARY) || (s & ~63)) unsupported = 1;
+                if (s & B_SOFT) nsoft++;
                 if (!(s & B_IMMUTABLE)) {
                     const T diff = bu[i] - bl[i];
                     if (diff < -st.primal_tol) bad = 1;
-                    else if (diff < st.zero_tol) s |= B_ACTIVE + B_IMMUTABLE;
+                    else if (diff < st.zero_tol && !(s & B_SOFT)) s |= B_ACTIVE + B_IMMUTABLE; // utils.c:560-563
                 }
                 if (s & (B_ACTIVE + B_IMMUTABLE)) any_fixed = 1;
             }
             so[i] = (unsigned char)s;
         }
         any_fixed = __any_sync(FULL, any_fixed);
-        if (__any_sync(FULL, unsupported)) flag = EXIT_UNSUPPORTED;
+        nsoft = __reduce_add_sync(FULL, nsoft);
+        if (__any_sync(FULL, unsupported) || nsoft > a.ns_max) flag = EXIT_UNSUPPORTED; // ns_max sizes the factor storage
         else if (__any_sync(FULL, bad)) flag = EXIT_INFEASIBLE;
 
         // ---- Hessian factor (utils.c:223-391)
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                     const int row = ms + r0 + lane; // constraint index
                     int sb = so[row];
                     if (n_my < st.zero_tol) {
-                        if ((bub < -st.zero_tol || blb > st.zero_tol) && !(sb & B_IMMUTABLE)) zero_row_infeasible = 1;
+                        if ((bub < -st.zero_tol || blb > st.zero_tol) && !(sb & B_IMMUTABLE) && !(sb & B_SOFT)) zero_row_infeasible = 1;
                         sb = B_IMMUTABLE;
                     }
                     T u_ = bub, l_ = blb;
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
             if (a.lam) for (int i = lane; i < m; i += 32) a.lam[(size_t)p * m + i] = 0;
             if (lane == 0) {
                 if (f) a.fval[p] = (T)-0.5 * vnorm;
+                if (a.soft_slack) a.soft_slack[p] = 0;
                 a.exitflag[p] = EXIT_OPTIMAL;
                 a.iter[p] = 1;
                 a.setup_flag[p] = SETUP_UNCONSTRAINED;

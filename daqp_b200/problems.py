@@ -205,3 +205,16 @@ def torch_to_batch(t: dict, n: int, m: int, ms: int, lo: int = 0, hi: int | None
     c = lambda k: np.ascontiguousarray(t[k][lo:hi].cpu().numpy())
     return QPBatch(n, m, ms, c("H"), c("f"), c("A"), c("bupper"), c("blower"), np.zeros((hi - lo, m), np.int32),
                    c("xref"), c("active_ref"))
+
+
+def soften(b, frac: float, shift: float, seed: int):
+    """Mark a random fraction of the constraints SOFT (sense bit 8, reference include/constants.h:84) and move their
+    bound pairs by N(0, shift): the hard problem would be infeasible, the soft one ends SOFT_OPTIMAL (exit flag 2)
+    with up to n + ns constraints in the working set. Test/bench input only."""
+    rng = np.random.default_rng(seed)
+    pick = rng.random((b.N, b.m)) < frac
+    d = shift * rng.standard_normal((b.N, b.m))
+    b.sense[pick] |= 8
+    b.bupper[pick] += d[pick]
+    b.blower[pick] += d[pick]
+    return b

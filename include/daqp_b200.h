@@ -11,7 +11,7 @@
  *   daqp_b200_solve_packed() NEW: same for a homogeneous batch in strided host arrays (no per-problem pointers)
  *   daqp_b200_solve_device() NEW: same with device-resident arrays, asynchronous on a caller stream
  *
- * Exit flags are the reference's (include/constants.h:42-51). Problems outside the hot-path scope (binary or soft
+ * Exit flags are the reference's (include/constants.h:42-51). Problems outside the hot-path scope (binary
  * constraints, hierarchies, AVI, H == NULL, singular H that needs the proximal-point driver) return
  * DAQP_EXIT_UNSUPPORTED (-8); there is no CPU fallback inside this library.
  *
@@ -122,9 +122,11 @@ void daqp_b200_destroy(DAQPB200Handle* h);
  * Any member may be NULL. */
 typedef struct {
     int* n_active;  /* [N]          final size of the working set                         */
-    int* ws;        /* [N][n+1]     final working set in factor order                     */
+    int* ws;        /* [N][n+ns+1]  final working set in factor order; ns = the largest number of soft
+                                    constraints (sense & DAQP_SOFT) any problem of the batch carries, 0 without sense */
     int* counts;    /* [N][4]       feasibility scans, LDL adds, LDL removes, CSP solves  */
     unsigned char* sense; /* [N][ldm], ldm = m rounded up to 4: final sense bits          */
+    c_float* soft_slack;  /* [N]    DAQPResult.soft_slack (reference src/api.c:469)       */
 } DAQPB200Diag;
 
 /* Homogeneous batch, strided HOST arrays: H[N][n][n], f[N][n] (or NULL), A[N][m-ms][n], bupper/blower[N][m],

@@ -81,6 +81,7 @@ class Solution:
     sense: np.ndarray | None = None  # [N, m] final sense bits
     counts: np.ndarray | None = None  # [N,4] scan, add, remove, csp (oracle only)
     seconds: float = 0.0
+    soft_slack: np.ndarray | None = None
 
 
 def default_settings(dtype=np.float64, **over):
@@ -124,6 +125,7 @@ class RefLib:
         x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
         fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
         ws = [] if want_ws else None
+        slack = np.zeros(N, self.dtype)
         sense_out = np.zeros((N, m), np.int32) if want_ws else None
         if use_sense is None:
             use_sense = bool(np.any(b.sense))
@@ -153,7 +155,8 @@ class RefLib:
                 else:
                     ws.append([])
             fval[p], flag[p], it[p] = res.fval, res.exitflag, res.iter
-        return Solution(x, lam, fval, flag, it, ws, sense_out, None, time.perf_counter() - t0)
+            slack[p] = res.soft_slack
+        return Solution(x, lam, fval, flag, it, ws, sense_out, None, time.perf_counter() - t0, slack)
 
 
 class RefDriver:
@@ -200,6 +203,7 @@ class OracleLib:
         x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
         fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
         counts = np.zeros((N, 4), np.int32)
+        slack = np.zeros(N, self.dtype)
         sense_out = np.zeros((N, m), np.int32)
         ws = []
         wsbuf = np.zeros(n + m + 2, np.int32)
@@ -219,9 +223,10 @@ class OracleLib:
                             sense_out[p].ctypes.data_as(C.POINTER(C.c_int)), 0, 0, 0, 0)
             self.lib.orc_quadprog(C.byref(res), C.byref(qp), sp, C.byref(tr))
             fval[p], flag[p], it[p] = res.fval, res.exitflag, res.iter
+            slack[p] = res.soft_slack
             counts[p] = (tr.n_scan, tr.n_add, tr.n_remove, tr.n_csp)
             ws.append(wsbuf[:tr.n_active].tolist())
-        return Solution(x, lam, fval, flag, it, ws, sense_out, counts, time.perf_counter() - t0)
+        return Solution(x, lam, fval, flag, it, ws, sense_out, counts, time.perf_counter() - t0, slack)
 
     def solve_packed(self, b, settings=None, nthreads: int = 1, use_sense: bool | None = None) -> Solution:
         """Whole batch inside C (no Python in the timed loop); returns wall seconds measured in C."""

@@ -26,7 +26,8 @@ def load_golden(name):
     return b, d
 
 
-def assert_parity(ref_x, ref_lam, ref_fval, ref_flag, ref_iter, x, lam, fval, flag, it, what="", x_tol=None):
+def assert_parity(ref_x, ref_lam, ref_fval, ref_flag, ref_iter, x, lam, fval, flag, it, what="", x_tol=None,
+                  f_tol=None):
     np.testing.assert_array_equal(flag, ref_flag, err_msg=f"{what}: exit flags differ")
     np.testing.assert_array_equal(it, ref_iter, err_msg=f"{what}: iteration counts differ")
     ok = ref_flag > 0
@@ -35,6 +36,7 @@ def assert_parity(ref_x, ref_lam, ref_fval, ref_flag, ref_iter, x, lam, fval, fl
     xs = 1 + np.abs(ref_x[ok]).max(axis=1, keepdims=True)
     lt = L_TOL if x_tol is None else max(L_TOL, 1e3 * x_tol)
     ft = F_TOL if x_tol is None else max(F_TOL, x_tol)
+    ft = ft if f_tol is None else f_tol
     x_tol = X_TOL if x_tol is None else x_tol
     assert (np.abs(x[ok] - ref_x[ok]) <= x_tol * xs).all(), f"{what}: x off by {np.abs(x[ok] - ref_x[ok]).max():.3e}"
     ls = 1 + np.abs(ref_lam[ok]).max(axis=1, keepdims=True)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from common import assert_parity, golden_names, kkt_residuals, load_golden, ws_sets
-from daqp_b200.problems import generate_config, generate_g0, generate_g1
+from daqp_b200.problems import generate_config, generate_g0, generate_g1, soften
 
 pytestmark = pytest.mark.gpu
 
@@ -32,13 +32,14 @@ def run_gpu(engine, b, use_sense=None, **settings):
                               **settings)
 
 
-def check_vs_oracle(engine, oracle, b, what, use_sense=None, settings=None, x_tol=None):
+def check_vs_oracle(engine, oracle, b, what, use_sense=None, settings=None, x_tol=None, f_tol=None):
     from oracle import harness
     settings = settings or {}
     st = harness.default_settings(**settings) if settings else None
     o = oracle.solve(b, settings=st, use_sense=use_sense)
     r = run_gpu(engine, b, use_sense=use_sense, **settings)
-    assert_parity(o.x, o.lam, o.fval, o.exitflag, o.iter, r.x, r.lam, r.fval, r.exitflag, r.iter, what, x_tol=x_tol)
+    assert_parity(o.x, o.lam, o.fval, o.exitflag, o.iter, r.x, r.lam, r.fval, r.exitflag, r.iter, what, x_tol=x_tol,
+                  f_tol=f_tol)
     started = o.exitflag >= -4
     got = r.working_sets()
     for p in np.nonzero(started)[0]:
@@ -122,6 +123,28 @@ def test_warm_start_and_equalities(engine, oracle):
             if b.active_ref[p, i] > 0: b.blower[p, i] = b.bupper[p, i]
             else: b.bupper[p, i] = b.blower[p, i]
     check_vs_oracle(engine, oracle, b, "equalities via bl == bu", use_sense=False)
+
+
+def test_soft_constraints(engine, oracle):
+    """sense & 8 (reference factorization.c:48-52, auxiliary.c:69-84,534-535, daqp.c:59-62): the working set grows past
+    n (up to n + ns rows of the factor), exit flag 2, soft_slack reported."""
+    seen = set()
+    for cfg, frac, shift in [((200, 10, 20, 0, 8), 0.2, 0.5), ((100, 20, 60, 5, 16), 0.5, 2.0),
+                             ((60, 12, 40, 12, 10), 1.0, 1.0), ((24, 50, 150, 0, 40), 0.2, 0.5)]:
+        b = soften(generate_g1(*cfg, seed=77), frac, shift, 5)
+        # fval is dominated by soft_slack = rho_soft * sum lam*^2 here (1e5 against |u|^2 ~ 1): it inherits twice the
+        # relative tolerance of lam (1e-7), so it is held to 1e-6 instead of 1e-9
+        o, r = check_vs_oracle(engine, oracle, b, f"soft {cfg} {frac}", use_sense=True, f_tol=1e-6)
+        np.testing.assert_allclose(r.soft_slack, o.soft_slack, rtol=1e-6, atol=1e-12)
+        seen |= set(np.unique(r.exitflag).tolist())
+    assert {1, 2} <= seen
+    b = soften(generate_g1(3, 10, 20, 0, 8, seed=78), 0.5, 1.0, 6)  # drop-in symbol reports soft_slack too
+    import daqp_b200
+    o = oracle.solve(b, use_sense=True)
+    for p in range(b.N):
+        x, fval, flag, info = daqp_b200.solve(b.H[p], b.f[p], b.A[p], b.bupper[p], b.blower[p], b.sense[p])
+        assert flag == o.exitflag[p] and info["iterations"] == o.iter[p]
+        np.testing.assert_allclose(info["soft_slack"], o.soft_slack[p], rtol=1e-6, atol=1e-12)
 
 
 def test_settings_and_limits(engine, oracle):

@@ -87,3 +87,25 @@ def test_oracle_out_of_scope_flags(oracle_libs):
     b = generate_g1(4, 8, 20, 0, 6, seed=13)
     b.H[:, 0, :] = 0; b.H[:, :, 0] = 0  # singular H -> proximal driver in the reference
     assert (oracle_libs.OracleLib().solve(b).exitflag == -8).all()
+
+
+def test_oracle_soft_constraints_vs_live_reference(oracle_libs):
+    """Soft constraints (sense & 8: +rho_soft on the pivot, n + ns + 1 factor rows, soft_slack, exit flag 2;
+    factorization.c:48-52, auxiliary.c:69-84,534-535, daqp.c:59-62): bit for bit against the strict reference build."""
+    if not oracle_libs.have_ref("libdaqp_ref_strict.so"):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    from daqp_b200.problems import soften
+    ref = oracle_libs.RefLib("libdaqp_ref_strict.so")
+    orc = oracle_libs.OracleLib()
+    seen = set()
+    for cfg, frac, shift in [((60, 10, 20, 0, 8), 0.2, 0.5), ((40, 20, 60, 5, 16), 0.5, 2.0), ((30, 12, 40, 12, 10), 1.0, 1.0),
+                             ((8, 50, 150, 0, 40), 0.2, 0.5)]:
+        b = soften(generate_g1(*cfg, seed=77), frac, shift, 5)
+        r = ref.solve(b, want_ws=True, use_sense=True)
+        o = orc.solve(b, use_sense=True)
+        for a, c in ((r.x, o.x), (r.lam, o.lam), (r.fval, o.fval), (r.iter, o.iter), (r.exitflag, o.exitflag),
+                     (r.soft_slack, o.soft_slack)):
+            np.testing.assert_array_equal(a, c)
+        assert [list(w) for w in r.ws] == [list(w) for w in o.ws]
+        seen |= set(np.unique(o.exitflag).tolist())
+    assert {1, 2} <= seen
