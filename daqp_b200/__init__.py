@@ -244,6 +244,74 @@ class Engine:
                 "sense": torch.zeros((N, ldm), dtype=torch.uint8, device=device)}
 
 
+class BatchModel:
+    """Batched counterpart of the reference's ``daqp.Model`` (interfaces/daqp-python/daqp.pyx:224-572): ``setup`` once,
+    then ``update(f=..., bupper=..., blower=...)`` + ``solve()`` per step. The QP -> LDP transform (Cholesky, R^-1,
+    M = A R^-1, row scaling) stays on the device; ``solve(warm=True)`` continues every problem from the LDL' factor,
+    multipliers and working set its previous solve ended with (``daqp_b200_workspace_*``)."""
+
+    def __init__(self, engine: "Engine | None" = None):
+        self._eng = engine
+        self._w = C.c_void_p()
+        self.shape = None
+
+    def setup(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, **settings):
+        L = lib()
+        L.daqp_b200_workspace_setup.restype = C.c_int
+        L.daqp_b200_workspace_update.restype = C.c_int
+        L.daqp_b200_workspace_solve.restype = C.c_int
+        L.daqp_b200_workspace_free.restype = None
+        self.close()
+        H = _f64(H); f = _f64(f); A = _f64(A); bupper = _f64(bupper); blower = _f64(blower)
+        N, n = H.shape[0], H.shape[1]
+        m = bupper.shape[1]
+        mA = A.shape[1] if A is not None and A.size else 0
+        ms = m - mA if ms is None else ms
+        ns = 0
+        if sense is not None:
+            sense = np.ascontiguousarray(sense, dtype=np.intc)
+            ns = int(((sense & SOFT) != 0).sum(axis=1).max(initial=0))
+        st = default_settings(**settings)
+        h = self._eng._h if self._eng is not None else None
+        _check(L.daqp_b200_workspace_setup(h, N, n, m, ms, _p(H), _p(f), _p(A), _p(bupper), _p(blower),
+                                           _p(sense, _ip), C.byref(st), C.byref(self._w)))
+        self.shape = (N, n, m, ms, ns)
+        return self
+
+    def update(self, f=None, bupper=None, blower=None):
+        f = _f64(f); bupper = _f64(bupper); blower = _f64(blower)
+        _check(lib().daqp_b200_workspace_update(self._w, _p(f), _p(bupper), _p(blower)))
+        return self
+
+    def solve(self, warm: bool = True, diag: bool = False) -> BatchResult:
+        N, n, m, ms, ns = self.shape
+        r = BatchResult(x=np.empty((N, n)), lam=np.empty((N, m)), fval=np.zeros(N), exitflag=np.empty(N, np.intc),
+                        iter=np.empty(N, np.intc))
+        d = None
+        if diag:
+            ldm = (max(m, 1) + 3) // 4 * 4
+            r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + ns + 1), np.intc)
+            r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8); r.soft_slack = np.zeros(N)
+            d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
+                             r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)), _p(r.soft_slack))
+        _check(lib().daqp_b200_workspace_solve(self._w, int(warm), _p(r.x), _p(r.lam), _p(r.fval),
+                                               _p(r.exitflag, _ip), _p(r.iter, _ip), C.byref(d) if d else None))
+        if diag:
+            r.sense = r.sense[:, :m]
+        return r
+
+    def close(self):
+        if self._w:
+            lib().daqp_b200_workspace_free(self._w)
+            self._w = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _default_engine = None
 
 

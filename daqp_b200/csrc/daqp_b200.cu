@@ -7,6 +7,7 @@
 #include "../../include/daqp_b200.h"
 #include "ldp_kernel.cuh"
 #include "setup_kernel.cuh"
+#include "update_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -214,12 +215,25 @@ __global__ void max_soft_kernel(const int* sense, int N, int m, int* out) {
     if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, best);
 }
 
+// Device arrays of a persistent workspace (daqp_b200_workspace_*): the LDP of a batch kept across solves.
+template <typename T>
+struct Persist {
+    T *Mt = nullptr, *Mr = nullptr, *du = nullptr, *dl = nullptr, *sc = nullptr, *Ri = nullptr, *vv = nullptr;
+    float* Mt32 = nullptr;
+    unsigned char *sense8 = nullptr, *sense_static = nullptr;
+    int* sflag = nullptr;
+    char* state = nullptr;
+    unsigned state_stride = 0;
+    int phase = 0;      // 1 = QP -> LDP only (no shortcut), 2 = solve only
+    int state_load = 0; // phase 2: continue from the saved factor / working set
+};
+
 // Device-resident batch: the core of every entry point.
 template <typename T>
 static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, const T* dH, const T* df, const T* dA,
                              const T* dbu, const T* dbl, const int* dsense, const DAQPSettings* settings, T* dx,
                              T* dlam, T* dfval, int* dflag, int* diter, const DAQPB200Diag* diag, cudaStream_t stream,
-                             int ns_max = -1) {
+                             int ns_max = -1, Persist<T>* ps = nullptr) {
     if (N <= 0) return 0;
     if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
     constexpr int V = VecOf<T>::N;
@@ -251,9 +265,10 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
 
     const size_t per = scratch_per_problem<T>(n, m, ldm, ldn);
     int chunk = (int)std::min<long long>(N, std::max<long long>(1, (h->scratch_limit - (8 << 20)) / (long long)per));
+    if (ps) chunk = N; // a workspace owns its LDP arrays: one launch over the whole batch
     const int grid_max = h->num_sms;
     const size_t pst = (size_t)grid_max * 16 * cap * (sizeof(int) + sizeof(T)) + 4096;
-    int rc = ensure(&h->arena, &h->arena_bytes, (size_t)chunk * per + pst + (1 << 20));
+    int rc = ensure(&h->arena, &h->arena_bytes, (ps ? 0 : (size_t)chunk * per) + pst + (1 << 20));
     if (rc) return rc;
 
     const DevSettings<T> st = to_dev_settings<T>(settings);
@@ -264,16 +279,16 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);
         int* counters = cv.take<int>(64);
-        T* Mt = cv.take<T>((size_t)P * n * ldm);
-        T* Mr = cv.take<T>((size_t)P * m * ldn);
-        float* Mt32 = screening ? cv.take<float>((size_t)P * ((n + 3) / 4) * m * 4) : nullptr;
-        T* du = cv.take<T>((size_t)P * ldm);
-        T* dl = cv.take<T>((size_t)P * ldm);
-        T* sc = cv.take<T>((size_t)P * ldm);
-        T* Ri = cv.take<T>((size_t)P * n * (n + 1) / 2);
-        T* vv = cv.take<T>((size_t)P * n);
-        unsigned char* sense8 = cv.take<unsigned char>((size_t)P * ldm);
-        int* sflag = cv.take<int>(P);
+        T* Mt = ps ? ps->Mt : cv.take<T>((size_t)P * n * ldm);
+        T* Mr = ps ? ps->Mr : cv.take<T>((size_t)P * m * ldn);
+        float* Mt32 = !screening ? nullptr : ps ? ps->Mt32 : cv.take<float>((size_t)P * ((n + 3) / 4) * m * 4);
+        T* du = ps ? ps->du : cv.take<T>((size_t)P * ldm);
+        T* dl = ps ? ps->dl : cv.take<T>((size_t)P * ldm);
+        T* sc = ps ? ps->sc : cv.take<T>((size_t)P * ldm);
+        T* Ri = ps ? ps->Ri : cv.take<T>((size_t)P * n * (n + 1) / 2);
+        T* vv = ps ? ps->vv : cv.take<T>((size_t)P * n);
+        unsigned char* sense8 = ps ? ps->sense8 : cv.take<unsigned char>((size_t)P * ldm);
+        int* sflag = ps ? ps->sflag : cv.take<int>(P);
         int* pst_id = cv.take<int>((size_t)grid_max * 16 * cap);
         T* pst_lam = cv.take<T>((size_t)grid_max * 16 * cap);
 
@@ -294,7 +309,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         sa.exitflag = dflag + p0; sa.iter = diter + p0;
         sa.work_counter = counters; sa.st = st;
         sa.soft_slack = (diag && diag->soft_slack) ? diag->soft_slack + p0 : nullptr; sa.ns_max = ns_max;
-        {
+        sa.no_shortcut = ps ? 1 : 0; sa.sense_static = ps ? ps->sense_static : nullptr;
+        if (!ps || ps->phase == 1) {
             const int grid = std::min(grid_max, (P + w_setup - 1) / w_setup);
             const size_t smem = smem_setup_w * w_setup;
             cudaError_t e = cudaErrorInvalidValue;
@@ -321,7 +337,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
         la.soft_slack = sa.soft_slack; la.ns_max = ns_max;
         la.tune = tune;
-        {
+        if (ps) { la.state = ps->state; la.state_stride = ps->state_stride; la.state_load = ps->state_load; la.state_save = 1; }
+        if (!ps || ps->phase == 2) {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
             const size_t smem = smem_solve_w * w_solve;
             cudaError_t e = cudaErrorInvalidValue;
@@ -465,6 +482,169 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
     if (e1 != cudaSuccess) return fail("copy_in stream", e1, __LINE__);
     if (e2 != cudaSuccess) return fail("compute stream", e2, __LINE__);
     if (e3 != cudaSuccess) return fail("copy_out stream", e3, __LINE__);
+    return 0;
+}
+
+// ---- persistent batch workspace: setup once, update(f, b) + solve many (reference setup_daqp / daqp_update_ldp /
+// daqp_solve on a kept DAQPWorkspace: src/api.c:88-160, src/utils.c:58-221, docs/docs/c.md:44-77) ---------------
+struct DAQPB200Workspace {
+    DAQPB200Handle* h = nullptr;
+    int N = 0, n = 0, m = 0, ms = 0, ldm = 0, ns_max = 0, cap = 0;
+    bool has_f = false, has_sense = false;
+    DAQPSettings settings{};
+    Persist<c_float> ps;
+    std::vector<void*> owned; // every device allocation of the workspace
+    c_float *d_f = nullptr, *d_bu = nullptr, *d_bl = nullptr;                           // inputs of update
+    c_float *d_x = nullptr, *d_lam = nullptr, *d_fval = nullptr, *d_slack = nullptr;    // outputs of solve
+    int *d_flag = nullptr, *d_iter = nullptr, *d_nact = nullptr, *d_ws = nullptr, *d_counts = nullptr;
+    int* d_sense = nullptr; // user sense (device copy; only its non-NULL-ness matters after the setup)
+    unsigned char* d_so = nullptr;
+};
+
+template <typename U> static int ws_alloc(DAQPB200Workspace* w, U** p, size_t count) {
+    CK(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(U)));
+    w->owned.push_back(*p);
+    return 0;
+}
+
+extern "C" void daqp_b200_workspace_free(DAQPB200Workspace* w) {
+    if (!w) return;
+    cudaSetDevice(w->h->device);
+    cudaDeviceSynchronize();
+    for (void* p : w->owned) cudaFree(p);
+    delete w;
+}
+
+extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* H,
+                                         const c_float* f, const c_float* A, const c_float* bupper,
+                                         const c_float* blower, const int* sense, const DAQPSettings* settings,
+                                         DAQPB200Workspace** out) {
+    typedef c_float T;
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (N <= 0 || n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
+    DAQPB200Workspace* w = new DAQPB200Workspace();
+    w->h = h; w->N = N; w->n = n; w->m = m; w->ms = ms; w->ldm = round_up(std::max(m, 1), 4);
+    w->has_f = f != nullptr; w->has_sense = sense != nullptr;
+    if (settings) w->settings = *settings; else daqp_default_settings(&w->settings);
+    if (sense)
+        for (int p = 0; p < N; p++) {
+            int c = 0;
+            for (int i = 0; i < m; i++) c += (sense[(size_t)p * m + i] & DAQP_SOFT) ? 1 : 0;
+            w->ns_max = std::max(w->ns_max, c);
+        }
+    w->cap = n + w->ns_max + 1;
+    const int ldm = w->ldm, ldn = round_up(n, VecOf<T>::N), mA = m - ms;
+    LdpArgs<T> la;
+    memset(&la, 0, sizeof(la));
+    la.n = n; la.m = m; la.ms = ms; la.ldm = ldm; la.ldn = ldn; la.cap = w->cap;
+    ldp_layout<T>(la);
+    Persist<T>& ps = w->ps;
+    ps.state_stride = (unsigned)round_up(la.oarena, 16) + 16;
+    int rc = 0;
+    T *dH = nullptr, *dA = nullptr;
+#define WS_TRY(call) do { rc = (call); if (rc) { daqp_b200_workspace_free(w); return rc; } } while (0)
+    WS_TRY(ws_alloc(w, &ps.Mt, (size_t)N * n * ldm));
+    WS_TRY(ws_alloc(w, &ps.Mr, (size_t)N * m * ldn));
+    if (m <= 256) WS_TRY(ws_alloc(w, &ps.Mt32, (size_t)N * ((n + 3) / 4) * m * 4));
+    WS_TRY(ws_alloc(w, &ps.du, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.dl, (size_t)N * ldm));
+    WS_TRY(ws_alloc(w, &ps.sc, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.Ri, (size_t)N * n * (n + 1) / 2));
+    WS_TRY(ws_alloc(w, &ps.vv, (size_t)N * n)); WS_TRY(ws_alloc(w, &ps.sense8, (size_t)N * ldm));
+    WS_TRY(ws_alloc(w, &ps.sense_static, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.sflag, (size_t)N));
+    WS_TRY(ws_alloc(w, &ps.state, (size_t)N * ps.state_stride));
+    WS_TRY(ws_alloc(w, &w->d_f, (size_t)N * n)); WS_TRY(ws_alloc(w, &w->d_bu, (size_t)N * m)); WS_TRY(ws_alloc(w, &w->d_bl, (size_t)N * m));
+    WS_TRY(ws_alloc(w, &w->d_x, (size_t)N * n)); WS_TRY(ws_alloc(w, &w->d_lam, (size_t)N * m));
+    WS_TRY(ws_alloc(w, &w->d_fval, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_slack, (size_t)N));
+    WS_TRY(ws_alloc(w, &w->d_flag, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_iter, (size_t)N));
+    WS_TRY(ws_alloc(w, &w->d_nact, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_ws, (size_t)N * w->cap));
+    WS_TRY(ws_alloc(w, &w->d_counts, (size_t)N * 4)); WS_TRY(ws_alloc(w, &w->d_so, (size_t)N * ldm));
+    if (sense) WS_TRY(ws_alloc(w, &w->d_sense, (size_t)N * m));
+    WS_TRY(ws_alloc(w, &dH, (size_t)N * n * n)); WS_TRY(ws_alloc(w, &dA, (size_t)N * std::max(mA, 1) * n));
+    cudaStream_t st = h->compute;
+#define WS_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { daqp_b200_workspace_free(w); return fail(#call, e_, __LINE__); } } while (0)
+    WS_CK(cudaMemsetAsync(ps.state, 0, (size_t)N * ps.state_stride, st));
+    WS_CK(cudaMemsetAsync(w->d_fval, 0, (size_t)N * sizeof(T), st));
+    WS_CK(cudaMemsetAsync(w->d_flag, 0, (size_t)N * sizeof(int), st));
+    WS_CK(cudaMemsetAsync(w->d_iter, 0, (size_t)N * sizeof(int), st));
+    WS_CK(cudaMemcpyAsync(dH, H, (size_t)N * n * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (mA > 0) WS_CK(cudaMemcpyAsync(dA, A, (size_t)N * mA * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (f) WS_CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (m > 0) {
+        WS_CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+        WS_CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (sense) WS_CK(cudaMemcpyAsync(w->d_sense, sense, (size_t)N * m * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    ps.phase = 1;
+    WS_TRY(solve_device_impl<T>(h, N, n, m, ms, dH, f ? w->d_f : nullptr, dA, w->d_bu, w->d_bl, w->d_sense, &w->settings,
+                                w->d_x, w->d_lam, w->d_fval, w->d_flag, w->d_iter, nullptr, st, w->ns_max, &ps));
+    WS_CK(cudaStreamSynchronize(st));
+    // H and A are not needed again: the LDP is what the workspace keeps
+    cudaFree(dH); cudaFree(dA);
+    w->owned.erase(std::remove(w->owned.begin(), w->owned.end(), (void*)dH), w->owned.end());
+    w->owned.erase(std::remove(w->owned.begin(), w->owned.end(), (void*)dA), w->owned.end());
+#undef WS_TRY
+#undef WS_CK
+    *out = w;
+    return 0;
+}
+
+extern "C" int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f, const c_float* bupper,
+                                          const c_float* blower) {
+    typedef c_float T;
+    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
+    DAQPB200Handle* h = w->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->compute;
+    const int N = w->N, n = w->n, m = w->m;
+    if (f && !w->has_f) { g_last_error = "daqp_b200: the workspace was set up without a linear term"; return -2; }
+    if (f) CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (bupper) CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (blower) CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+    UpdateArgs<T> ua;
+    ua.P = N; ua.n = n; ua.m = m; ua.ms = w->ms; ua.ldm = w->ldm;
+    ua.f = f ? w->d_f : nullptr; ua.bupper = w->d_bu; ua.blower = w->d_bl;
+    ua.Rinv = w->ps.Ri; ua.Mt = w->ps.Mt; ua.scaling = w->ps.sc; ua.sense_static = w->ps.sense_static;
+    ua.v = w->ps.vv; ua.dupper = w->ps.du; ua.dlower = w->ps.dl; ua.sense = w->ps.sense8;
+    ua.setup_flag = w->ps.sflag; ua.exitflag = w->d_flag; ua.iter = w->d_iter;
+    ua.st = to_dev_settings<T>(&w->settings);
+    const int warps = 8;
+    const size_t smem = (size_t)warps * 2 * n * sizeof(T);
+    ldp_update_kernel<T><<<std::min(h->num_sms * 4, (N + warps - 1) / warps), 32 * warps, smem, st>>>(ua);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float* x, c_float* lam, c_float* fval,
+                                         int* exitflag, int* iter, const DAQPB200Diag* diag) {
+    typedef c_float T;
+    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
+    DAQPB200Handle* h = w->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->compute;
+    const int N = w->N, n = w->n, m = w->m;
+    DAQPB200Diag dd{};
+    dd.n_active = w->d_nact; dd.ws = w->d_ws; dd.counts = w->d_counts; dd.sense = w->d_so; dd.soft_slack = w->d_slack;
+    w->ps.phase = 2; w->ps.state_load = warm ? 1 : 0;
+    int rc = solve_device_impl<T>(h, N, n, m, w->ms, nullptr, w->has_f ? w->d_f : nullptr, nullptr, w->d_bu, w->d_bl,
+                                  w->has_sense ? w->d_sense : nullptr, &w->settings, w->d_x, w->d_lam, w->d_fval,
+                                  w->d_flag, w->d_iter, &dd, st, w->ns_max, &w->ps);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(x, w->d_x, (size_t)N * n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    if (lam && m > 0) CK(cudaMemcpyAsync(lam, w->d_lam, (size_t)N * m * sizeof(T), cudaMemcpyDeviceToHost, st));
+    if (fval) CK(cudaMemcpyAsync(fval, w->d_fval, (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(exitflag, w->d_flag, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iter) CK(cudaMemcpyAsync(iter, w->d_iter, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (diag) {
+        if (diag->n_active) CK(cudaMemcpyAsync(diag->n_active, w->d_nact, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (diag->ws) CK(cudaMemcpyAsync(diag->ws, w->d_ws, (size_t)N * w->cap * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (diag->counts) CK(cudaMemcpyAsync(diag->counts, w->d_counts, (size_t)N * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (diag->sense) CK(cudaMemcpyAsync(diag->sense, w->d_so, (size_t)N * w->ldm, cudaMemcpyDeviceToHost, st));
+        if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack, w->d_slack, (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 

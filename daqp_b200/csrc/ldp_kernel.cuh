@@ -68,6 +68,12 @@ struct LdpArgs {
     T* lam;                   // [P][m] or nullptr
     T* fval;                  // [P]
     T* soft_slack;            // [P] or nullptr
+    // persistent-workspace mode (daqp_b200_workspace_*): the warp's shared-memory block (factor, multipliers, working
+    // set, sense) is saved at exit and restored at the start of the next solve, like the reference's DAQPWorkspace keeps
+    // its LDL' factor and working set between daqp_solve calls (src/api.c:214-260)
+    char* state;              // [P][state_stride] or nullptr
+    unsigned state_stride;    // bytes per problem: oarena rounded up to 16, plus 16 for {k, lsw, valid}
+    int state_load, state_save;
     int ns_max;               // most soft constraints (sense & 8) any problem of the batch carries; cap = n + ns_max + 1
     int* exitflag;            // [P]
     int* iter;                // [P]
@@ -1133,7 +1139,44 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             LANE_LOOP(i, 0, round_up(a.n, 4) + U_PAD) u32p[i] = 0.f;
             __syncwarp();
             w.reset();
-            w.begin(sflag == SETUP_SOLVE_ACTIVATE);
+            bool activate = sflag == SETUP_SOLVE_ACTIVATE;
+            if (a.state && a.state_load) {
+                // warm: continue from the previous solve's factor and working set (the reference's daqp_solve on a kept
+                // workspace). The right-hand sides changed (daqp_update_d sets reuse_ind = 0, utils.c:506), so the active
+                // bounds are re-read; a constraint that the new bounds turned into an equality (check_bounds,
+                // utils.c:546-567) forces the reference's reset + re-activation (utils.c:199-211).
+                const char* blob = a.state + (size_t)pq * a.state_stride;
+                const int* meta = reinterpret_cast<const int*>(blob + a.state_stride - 16);
+                if (uni(meta[2]) == 1) {
+                    const int4* src4 = reinterpret_cast<const int4*>(blob);
+                    int4* dst4 = reinterpret_cast<int4*>(w.S);
+                    LANE_LOOP(i, 0, (int)((a.state_stride - 16) / 16)) dst4[i] = src4[i];
+                    __syncwarp();
+                    w.k = uni(meta[0]);
+                    w.lsw = uni(meta[1]);
+                    int fresh = 0; // marks the new bounds add to the kept sense bits
+                    LANE_LOOP(i, 0, a.m) {
+                        const int now = sin[i], kept = se[i];
+                        if ((now & ~kept) & (B_ACTIVE | B_IMMUTABLE)) { fresh = 1; se[i] = (unsigned char)(kept | now); }
+                    }
+                    __syncwarp();
+                    if (uni(fresh != 0)) { w.reset(); activate = true; }
+                    else {
+                        activate = false;
+                        T* da = w.dact();
+                        const int* wsp = w.WS();
+                        LANE_LOOP(i, 0, w.k) {
+                            const int id = wsp[i];
+                            da[i] = (se[id] & B_LOWER) ? w.dl()[id] : w.du()[id];
+                        }
+                        LANE_LOOP(i, 0, round_up(a.n, VecOf<T>::N) + U_PAD) up[i] = 0;
+                        LANE_LOOP(i, 0, round_up(a.n, 4) + U_PAD) u32p[i] = 0.f;
+                        if (lane < 4) w.cnt()[lane] = 0;
+                        __syncwarp();
+                    }
+                }
+            }
+            w.begin(activate);
         }
         int exitflag;
         do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV>::RUNNING);
@@ -1184,6 +1227,17 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
         if (a.ws_out) LANE_LOOP(i, 0, kfin) a.ws_out[(size_t)p * a.cap + i] = w.WS()[i];
         if (a.sense_out) LANE_LOOP(i, 0, a.m) a.sense_out[(size_t)p * a.ldm + i] = w.sense()[i];
         if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = w.cnt()[lane];
+        if (a.state && a.state_save) { // keep factor, multipliers, working set and sense for the next warm solve
+            char* blob = a.state + (size_t)p * a.state_stride;
+            int4* dst4 = reinterpret_cast<int4*>(blob);
+            const int4* src4 = reinterpret_cast<const int4*>(w.S);
+            __syncwarp();
+            LANE_LOOP(i, 0, (int)((a.state_stride - 16) / 16)) dst4[i] = src4[i];
+            if (lane == 0) {
+                int* meta = reinterpret_cast<int*>(blob + a.state_stride - 16);
+                meta[0] = w.k; meta[1] = w.lsw; meta[2] = (exitflag > 0 && w.sing == EMPTY_IND) ? 1 : 0; meta[3] = 0;
+            }
+        }
         __syncwarp();
         }
         }

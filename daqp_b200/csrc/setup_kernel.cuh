@@ -26,6 +26,10 @@ struct SetupArgs {
     int *exitflag, *iter;
     int* work_counter;
     T* soft_slack;                        // [P] or nullptr
+    // persistent-workspace mode (reference setup_daqp: no unconstrained shortcut, d = b * scaling + M v, utils.c:499-544)
+    int no_shortcut;
+    unsigned char* sense_static;          // [P][ldm] or nullptr: user sense bits with zero rows marked IMMUTABLE, WITHOUT
+                                          // the equality marks check_bounds derives from the current bounds
     int ns_max;                           // upper bound on soft constraints per problem (sizes the solve kernel's factor)
     DevSettings<T> st;
 };
@@ -114,11 +118,15 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                 if (s & (B_ACTIVE + B_IMMUTABLE)) any_fixed = 1;
             }
             so[i] = (unsigned char)s;
+            if (a.sense_static) a.sense_static[(size_t)p * ldm + i] = (unsigned char)((i < m && sin) ? sin[i] : 0);
         }
         any_fixed = __any_sync(FULL, any_fixed);
         nsoft = __reduce_add_sync(FULL, nsoft);
         if (__any_sync(FULL, unsupported) || nsoft > a.ns_max) flag = EXIT_UNSUPPORTED; // ns_max sizes the factor storage
-        else if (__any_sync(FULL, bad)) flag = EXIT_INFEASIBLE;
+        // workspace mode: conflicting bounds do not stop the transform (new bounds may arrive with the next update); the
+        // problem is flagged once its LDP is in place
+        const bool bad_bounds = __any_sync(FULL, bad);
+        if (flag >= 0 && bad_bounds && !a.no_shortcut) flag = EXIT_INFEASIBLE;
 
         // ---- Hessian factor (utils.c:223-391)
         bool is_diag = true;
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         if (a.v) for (int i = lane; i < n; i += 32) a.v[(size_t)p * n + i] = vv[i];
 
         // ---- unconstrained optimum x = -R^-1 v (utils.c:633-660), only when nothing is pre-activated/immutable
-        const bool unc = !any_fixed;
+        const bool unc = !any_fixed && !a.no_shortcut;
         int infeasible_pt = 0;
         if (unc) {
             for (int i = lane; i < n; i += 32) {
@@ -348,6 +356,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                         u_ = u_ * s_my + d_my; l_ = l_ * s_my + d_my;
                     }
                     du[row] = u_; dl[row] = l_; sc[row] = s_my; so[row] = (unsigned char)sb;
+                    if (a.sense_static && n_my < st.zero_tol) a.sense_static[(size_t)p * ldm + row] = (unsigned char)B_IMMUTABLE;
                 }
             }
             // row-major copy (coalesced), column-major copy (one 32-byte sector per lane and column)
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                 a.iter[p] = 1;
                 a.setup_flag[p] = SETUP_UNCONSTRAINED;
             }
-        } else if (zero_row_infeasible) {
+        } else if (zero_row_infeasible || bad_bounds) {
             if (lane == 0) { a.setup_flag[p] = EXIT_INFEASIBLE; a.exitflag[p] = EXIT_INFEASIBLE; a.iter[p] = 0; }
         } else {
             if (lane == 0) a.setup_flag[p] = (sin != nullptr || any_fixed) ? SETUP_SOLVE_ACTIVATE : SETUP_SOLVE;

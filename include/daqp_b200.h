@@ -149,6 +149,26 @@ int daqp_b200_solve_device(DAQPB200Handle* h, int N, int n, int m, int ms,
                            c_float* dx, c_float* dlam, c_float* dfval, int* dexitflag, int* diter,
                            const DAQPB200Diag* diag, void* stream);
 
+/* ---- persistent batch workspace (new): setup once, update(f, b) + solve many ------------------------------
+ * The batched counterpart of the reference's workspace flow -- setup_daqp() once, then daqp_update_ldp(DAQP_UPDATE_v +
+ * DAQP_UPDATE_d) and daqp_solve() per step (include/api.h:33-37, src/api.c:88-160,214-260, src/utils.c:58-221,
+ * docs/docs/c.md:44-77): the Cholesky factor, R^-1, M and the row scaling stay on the device; with warm != 0 every
+ * problem continues from the LDL' factor, multipliers and working set its previous solve ended with, exactly like
+ * daqp_solve() on a kept DAQPWorkspace. All arrays are HOST arrays shaped as in daqp_b200_solve_packed; H and A are
+ * read by the setup only. */
+typedef struct DAQPB200Workspace DAQPB200Workspace;
+int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m, int ms,
+                              const c_float* H, const c_float* f, const c_float* A,
+                              const c_float* bupper, const c_float* blower, const int* sense,
+                              const DAQPSettings* settings, DAQPB200Workspace** out);
+/* New linear term and / or bounds (NULL keeps the current one). Asynchronous; the next solve is ordered after it. */
+int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f, const c_float* bupper, const c_float* blower);
+/* Active-set loop + result extraction. warm = 0: start from the sense bits; warm != 0: continue from the previous solve.
+ * Blocks until the results are in the host arrays. diag may be NULL (ws rows hold n + ns + 1 entries). */
+int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float* x, c_float* lam, c_float* fval,
+                              int* exitflag, int* iter, const DAQPB200Diag* diag);
+void daqp_b200_workspace_free(DAQPB200Workspace* w);
+
 /* Device-time accounting of the engine since the last reset (CUDA events on the launching stream). */
 typedef struct {
     int setup_launches; /* qp_setup_kernel launches   */

@@ -159,6 +159,62 @@ class RefLib:
         return Solution(x, lam, fval, flag, it, ws, sense_out, None, time.perf_counter() - t0, slack)
 
 
+def ref_solve_sequence(reflib, b, steps, settings=None, use_sense=None):
+    """The reference's workspace flow on every problem of the batch: setup_daqp() + daqp_solve(), then per step
+    daqp_update_ldp(DAQP_UPDATE_v + DAQP_UPDATE_d) with new (f, bupper, blower) + daqp_solve() on the KEPT workspace
+    (src/api.c:88-160,214-260, src/utils.c:58-221). steps = list of (f[N,n], bupper[N,m], blower[N,m]).
+    Returns one Solution per solve (len(steps) + 1)."""
+    self = reflib
+    N, n, m = b.N, b.n, b.m
+    nsol = len(steps) + 1
+    outs = [dict(x=np.zeros((N, n)), lam=np.zeros((N, m)), fval=np.zeros(N), flag=np.zeros(N, np.int32),
+                 it=np.zeros(N, np.int32), ws=[], slack=np.zeros(N)) for _ in range(nsol)]
+    if use_sense is None:
+        use_sense = bool(np.any(b.sense))
+    sp = C.byref(settings) if settings is not None else None
+    self.lib.daqp_update_ldp.restype = C.c_int
+    for p in range(N):
+        f = b.f[p].copy(); bu = b.bupper[p].copy(); bl = b.blower[p].copy()
+        sense = b.sense[p].copy() if use_sense else None
+        mA = m - b.ms
+        qp = self.Problem(n, m, b.ms, _ptr(b.H[p], self.real), _ptr(f, self.real),
+                          _ptr(b.A[p], self.real) if mA > 0 else None, _ptr(bu, self.real), _ptr(bl, self.real),
+                          sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)
+        work = self.Workspace()
+        work.settings = C.cast(sp, C.c_void_p) if sp is not None else None
+        st = self.real(0)
+        rc = self.lib.setup_daqp_main(C.byref(qp), C.byref(work), C.byref(st), 0)
+        for k in range(nsol):
+            o = outs[k]
+            if k > 0 and rc >= 0:
+                f[:] = steps[k - 1][0][p]; bu[:] = steps[k - 1][1][p]; bl[:] = steps[k - 1][2][p]
+                rc = self.lib.daqp_update_ldp(4 + 8, C.byref(work), C.byref(qp))
+                if rc >= 0:
+                    rc = 1
+            res = self.Result(_ptr(o["x"][p], self.real), _ptr(o["lam"][p], self.real), 0, 0, 0, 0, 0, 0, 0)
+            if rc >= 0:
+                self.lib.daqp_solve(C.byref(res), C.byref(work))
+                o["ws"].append([work.WS[i] for i in range(work.n_active)])
+            else:
+                res.exitflag = rc
+                o["ws"].append([])
+            o["fval"][p], o["flag"][p], o["it"][p], o["slack"][p] = res.fval, res.exitflag, res.iter, res.soft_slack
+            if rc < 0 and k == 0:
+                break
+            if rc < 0:
+                rc = 1  # an update that failed (infeasible bounds) does not destroy the workspace
+        if work.n > 0 or True:
+            try:
+                if sp is not None:
+                    work.settings = None
+                if rc >= 0 or nsol > 1:
+                    self.lib.free_daqp_workspace(C.byref(work))
+                    self.lib.free_daqp_ldp(C.byref(work))
+            except Exception:
+                pass
+    return [Solution(o["x"], o["lam"], o["fval"], o["flag"], o["it"], o["ws"], None, None, 0.0, o["slack"]) for o in outs]
+
+
 class RefDriver:
     """pthread loop around the unmodified reference's daqp_quadprog (oracle/ref_driver.c -> oracle/_ref)."""
 

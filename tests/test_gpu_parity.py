@@ -147,6 +147,51 @@ def test_soft_constraints(engine, oracle):
         np.testing.assert_allclose(info["soft_slack"], o.soft_slack[p], rtol=1e-6, atol=1e-12)
 
 
+WS_GOLDEN = ["wsseq_n10_m30_ms3", "wsseq_n20_m60_ms5", "wsseq_n50_m150", "wsseq_soft_n12_m40", "wsseq_equalities_n16_m48"]
+
+
+@pytest.mark.parametrize("name", WS_GOLDEN)
+def test_workspace_sequence_matches_reference(cuda_lib, name):
+    """Persistent workspace: setup once, then update(f, b) + warm solve, against the UNMODIFIED reference driven through
+    setup_daqp / daqp_update_ldp(UPDATE_v + UPDATE_d) / daqp_solve on a kept workspace (tests/golden/
+    make_golden_workspace.py). Exit flags, iteration counts and working sets (factor order) must be equal for every
+    solve of a problem as long as its previous solves ended (soft-)optimal: the state a reference workspace is left in
+    after an INFEASIBLE exit (a zero pivot in D) is not something to reproduce."""
+    import os
+    import daqp_b200
+    from common import GOLDEN_DIR
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    use_sense = bool(d["use_sense"])
+    mdl = daqp_b200.BatchModel().setup(d["H"], d["f"], d["A"], d["bupper"], d["blower"],
+                                       d["sense"].astype(np.int32) if use_sense else None, ms=int(d["ms"]))
+    N = d["H"].shape[0]
+    live = np.ones(N, bool)
+    checked = 0
+    for k in range(int(d["K"]) + 1):
+        if k > 0:
+            mdl.update(f=d[f"f{k-1}"], bupper=d[f"bu{k-1}"], blower=d[f"bl{k-1}"])
+        r = mdl.solve(warm=True, diag=True)
+        flag, it = d[f"flag_{k}"], d[f"iter_{k}"]
+        np.testing.assert_array_equal(r.exitflag[live], flag[live], err_msg=f"{name} solve {k}: exit flags")
+        np.testing.assert_array_equal(r.iter[live], it[live], err_msg=f"{name} solve {k}: iteration counts")
+        ok = live & (flag > 0)
+        want_ws = d[f"ws_{k}"]
+        got = r.working_sets()
+        for p in np.nonzero(ok)[0]:
+            assert got[p] == want_ws[p, : d[f"nact_{k}"][p]].tolist(), f"{name} solve {k} problem {p}: working set"
+        f_tol = 1e-6 if "soft" in name else None
+        assert_parity(d[f"x_{k}"][ok], d[f"lam_{k}"][ok], d[f"fval_{k}"][ok], flag[ok], it[ok], r.x[ok], r.lam[ok],
+                      r.fval[ok], r.exitflag[ok], r.iter[ok], f"{name} solve {k}", f_tol=f_tol)
+        checked += int(ok.sum())
+        live &= flag > 0
+    assert checked >= N  # the sequences are not vacuous
+    cold = mdl.solve(warm=False)  # same data, cold start: same optimum
+    ok = live
+    if ok.any():
+        np.testing.assert_allclose(cold.x[ok], r.x[ok], rtol=0, atol=1e-8 * (1 + np.abs(r.x[ok]).max()))
+    mdl.close()
+
+
 def test_settings_and_limits(engine, oracle):
     b = generate_g1(100, 20, 60, 0, 16, seed=51)
     o, r = check_vs_oracle(engine, oracle, b, "iter_limit", settings={"iter_limit": 7})
