@@ -187,12 +187,18 @@ static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
     return e * sizeof(T) + (size_t)((n + 3) / 4) * m * 16 + ldm + sizeof(int) + 64; // + fp32 quad copy + sense + flag + slack
 }
 
+template <typename T, int NV, bool EXT>
+static cudaError_t launch_solve_x(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NV, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ldp_solve_kernel<T, NV, EXT><<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+// soft constraints or a persistent workspace select the extended instantiation
 template <typename T, int NV>
 static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ldp_solve_kernel<T, NV><<<grid, block, smem, s>>>(a);
-    return cudaGetLastError();
+    return (a.ns_max > 0 || a.state) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
+                                     : launch_solve_x<T, NV, false>(a, grid, block, smem, s);
 }
 template <typename T, int NGS>
 static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
@@ -315,11 +321,15 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
             const size_t smem = smem_setup_w * w_setup;
             cudaError_t e = cudaErrorInvalidValue;
             switch (ngs) {
+#ifndef DAQP_B200_FAST_BUILD /* experiment builds instantiate the C3 shape only */
                 case 1: e = launch_setup<T, 1>(sa, grid, 32 * w_setup, smem, stream); break;
+#endif
                 case 2: e = launch_setup<T, 2>(sa, grid, 32 * w_setup, smem, stream); break;
+#ifndef DAQP_B200_FAST_BUILD
                 case 3: e = launch_setup<T, 3>(sa, grid, 32 * w_setup, smem, stream); break;
                 case 4: e = launch_setup<T, 4>(sa, grid, 32 * w_setup, smem, stream); break;
                 default: e = launch_setup<T, 8>(sa, grid, 32 * w_setup, smem, stream); break;
+#endif
             }
             if (e != cudaSuccess) return fail("qp_setup_kernel launch", e, __LINE__);
             h->stats.setup_launches++;
@@ -343,14 +353,18 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
             const size_t smem = smem_solve_w * w_solve;
             cudaError_t e = cudaErrorInvalidValue;
             switch (nv) {
+#ifndef DAQP_B200_FAST_BUILD
                 case 1: e = launch_solve<T, 1>(la, grid, 32 * w_solve, smem, stream); break;
+#endif
                 case 2: e = launch_solve<T, 2>(la, grid, 32 * w_solve, smem, stream); break;
+#ifndef DAQP_B200_FAST_BUILD
                 case 3: e = launch_solve<T, 3>(la, grid, 32 * w_solve, smem, stream); break;
                 case 4: e = launch_solve<T, 4>(la, grid, 32 * w_solve, smem, stream); break;
                 case 5: e = launch_solve<T, 5>(la, grid, 32 * w_solve, smem, stream); break;
                 case 6: e = launch_solve<T, 6>(la, grid, 32 * w_solve, smem, stream); break;
                 case 7: e = launch_solve<T, 7>(la, grid, 32 * w_solve, smem, stream); break;
                 default: e = launch_solve<T, 8>(la, grid, 32 * w_solve, smem, stream); break;
+#endif
             }
             if (e != cudaSuccess) return fail("ldp_solve_kernel launch", e, __LINE__);
             h->stats.solve_launches++;

@@ -28,8 +28,10 @@
 namespace dq {
 
 constexpr int U_PAD = 16; // zero entries behind u so that the fp64 scan pipeline can run past column n-1
-constexpr int RB = 8;     // active rows per cp.async chunk of the row passes (two chunks in flight)
-constexpr int QRING = 3;  // depth of the screening scan's ring (quads of columns in flight)
+constexpr int RB = 6;     // active rows per cp.async chunk of the row passes (two chunks in flight); measured on C3:
+                          // 8 -> 112.0 ms (11 problems per SM), 6 -> 107.7 ms (12 per SM), 4 -> 115.8 ms
+constexpr int QRING = 2;  // depth of the screening scan's ring (quads of columns in flight); 3 buys nothing (the scan
+                          // is not latency-bound) and costs the twelfth resident problem, 4 -> 125 ms, 1 -> 119 ms
 constexpr int SCR_PITCH = 34; // doubles per parked row of partial dot products (16-byte aligned rows)
 
 // Warp-uniform values are made PROVABLY uniform for the compiler by reading them from lane 0: loops and branches on
@@ -142,10 +144,15 @@ template <> __device__ __forceinline__ void ldg_vec_pred<float>(const void* p, f
 // slice in column group g.
 template <typename T, int NG>
 __device__ __noinline__ void issue_rows_fn(const int* ids, int nrows, unsigned buf, const char* M, unsigned rstride, unsigned okmask) {
-    const int4* wsv = reinterpret_cast<const int4*>(ids);
     int id[RB];
+    if constexpr (RB % 4 == 0) { // chunk starts are multiples of RB: 16-byte aligned index quads
+        const int4* wsv = reinterpret_cast<const int4*>(ids);
 #pragma unroll
-    for (int v4 = 0; v4 < RB / 4; v4++) { const int4 t = wsv[v4]; id[4 * v4] = t.x; id[4 * v4 + 1] = t.y; id[4 * v4 + 2] = t.z; id[4 * v4 + 3] = t.w; }
+        for (int v4 = 0; v4 < RB / 4; v4++) { const int4 t = wsv[v4]; id[4 * v4] = t.x; id[4 * v4 + 1] = t.y; id[4 * v4 + 2] = t.z; id[4 * v4 + 3] = t.w; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < RB; r++) id[r] = ids[r];
+    }
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         const char* src = M + (size_t)(unsigned)id[r] * rstride;
@@ -155,7 +162,9 @@ __device__ __noinline__ void issue_rows_fn(const int* ids, int nrows, unsigned b
     cp_async_commit();
 }
 
-template <typename T, int NV>
+// EXT = the extended feature set (soft constraints, persistent-workspace state): a separate instantiation, so that the
+// plain path -- the one the headline benchmark runs -- does not carry that code through its instruction cache.
+template <typename T, int NV, bool EXT>
 struct Warp {
     static constexpr int V = VecOf<T>::N;
     static constexpr int NG = (NV + 1) / 2;                         // 128-bit column groups of a row: n <= 32 NV - 1
@@ -214,7 +223,7 @@ struct Warp {
     // pivots [jbeg, jend) of register segment QP applied to row segments QP .. Q1-1
     template <int QP, int Q1>
     __device__ __forceinline__ void fwd_pivots(T (&x)[NV], const T* const (&row)[NV], const int (&lim)[NV], int jbeg, int jend) {
-#pragma unroll 2
+#pragma unroll 1 // (unroll 4: 120 ms, 2: 112 ms, 1: 109.5 ms -- the instruction cache decides, see the header)
         for (int j = jbeg; j < jend; j++) {
             const T xj = __shfl_sync(FULL, x[QP], j);
 #pragma unroll
@@ -253,7 +262,7 @@ struct Warp {
             // (running row pointer: with the offset recomputed from j, ptxas folded the counter update into a
             // lane-predicated move, declared the loop divergent and guarded every shuffle of the kernel behind it)
             const T* Lj = L() + loff(jhi) + lane;
-#pragma unroll 2
+#pragma unroll 1
             for (int j = jhi; j >= jlo; j--) {
                 const T xj = __shfl_sync(FULL, x[qp], j);
 #pragma unroll
@@ -304,7 +313,7 @@ struct Warp {
         const unsigned buf0 = smem_u32(S) + a.oarena;
         T d = warp_sum(part);
         int ns_active = 0; // soft constraints in the working set, the entering one included (factorization.c:48-52,60-62)
-        if (a.ns_max > 0) {
+        if (EXT && a.ns_max > 0) {
             if (sb & B_SOFT) { d += a.st.rho_soft; ns_active = 1; }
             const unsigned char* se = sense();
             const int* wsp = WS();
@@ -341,12 +350,12 @@ struct Warp {
                 for (int r = 0; r < RB; r++) scr[r * SCR_PITCH + lane] = pj[r];
                 __syncwarp();
                 const int r8 = lane >> 2, q4 = lane & 3;
-                const T* pr = scr + r8 * SCR_PITCH + 8 * q4;
+                const T* pr = scr + min(r8, RB - 1) * SCR_PITCH + 8 * q4; // lanes beyond the chunk's rows re-read the last one
                 T sum = ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
                 sum += __shfl_xor_sync(FULL, sum, 1);
                 sum += __shfl_xor_sync(FULL, sum, 2);
                 const int jr = c0 + r8;
-                if (q4 == 0 && jr < kk) Lk[jr] = sum;
+                if (q4 == 0 && r8 < RB && jr < kk) Lk[jr] = sum;
                 __syncwarp(); // scratch reads are done before the buffer is refilled, results visible to the sweep
             }
             // l <- L^-1 l in registers, then l <- D^-1 l ; d -= l' D l
@@ -649,15 +658,15 @@ struct Warp {
             }
         }
         T slack = 0; // soft_slack = rho_soft * sum over soft active rows of lam*^2 (auxiliary.c:69-84)
-        if (a.ns_max > 0) {
+        if (EXT && a.ns_max > 0) {
             const unsigned char* se = sense();
             const int* wsp = WS();
             T sp = 0;
             LANE_LOOP(i, 0, kk) { if (se[wsp[i]] & B_SOFT) { const T li = ls[i]; sp += li * li; } }
             slack = uni(warp_sum(sp)) * a.st.rho_soft;
         }
-        soft_slack = slack;
-        fval = slack + uni(warp_sum(part));
+        if constexpr (EXT) { soft_slack = slack; fval = slack + uni(warp_sum(part)); }
+        else fval = uni(warp_sum(part));
         __syncwarp();
     }
 
@@ -950,7 +959,7 @@ struct Warp {
             part = warp_sum(part);
             if (lane == 0) {
                 T res = part - dact()[i];
-                if (a.ns_max > 0 && (sense()[WS()[i]] & B_SOFT)) res -= a.st.rho_soft * lams()[i]; // auxiliary.c:534-535
+                if (EXT && a.ns_max > 0 && (sense()[WS()[i]] & B_SOFT)) res -= a.st.rho_soft * lams()[i]; // auxiliary.c:534-535
                 xp[i] = res;
             }
         }
@@ -999,7 +1008,8 @@ struct Warp {
                 for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
             }
         }
-        fval = soft_slack + uni(warp_sum(part)); // auxiliary.c:589-593: the slack term is not recomputed
+        if constexpr (EXT) fval = soft_slack + uni(warp_sum(part)); // auxiliary.c:589-593: the slack term is not recomputed
+        else fval = uni(warp_sum(part));
         __syncwarp();
     }
 
@@ -1067,7 +1077,7 @@ struct Warp {
                         refine_active();
                         refined = true;
                         again = true;
-                    } else return uni(soft_slack > a.st.primal_tol) ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; // daqp.c:59-62
+                    } else return (EXT && uni(soft_slack > a.st.primal_tol)) ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; // daqp.c:59-62
                 }
             }
         }
@@ -1097,13 +1107,13 @@ struct Warp {
 // different routines and the SM's instruction cache thrashes (measured: 24 % of all stall samples were
 // "no instruction", icc hit rate 75 %); with it the instruction working set at any moment is one routine. The
 // barrier carries no data -- problems stay independent -- it only keeps the instruction streams together.
-template <typename T, int NV>
+template <typename T, int NV, bool EXT>
 __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant__ LdpArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = uni((int)(threadIdx.x >> 5)); // uniform: so are all shared-memory bases
     const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
 
-    Warp<T, NV> w(a);
+    Warp<T, NV, EXT> w(a);
     w.lane = lane;
     w.S = reinterpret_cast<T*>(smem_raw + (size_t)a.per_warp_bytes * wib);
     w.pst_id = a.pst_id + (size_t)gw * a.cap;
@@ -1128,7 +1138,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
         {
             w.lsw = 0;
             w.fval = 0;
-            w.soft_slack = 0;
+            if constexpr (EXT) w.soft_slack = 0;
             const unsigned char* sin = a.sense + (size_t)pq * a.ldm;
             unsigned char* se = w.sense();
             LANE_LOOP(i, 0, a.m) se[i] = sin[i];
@@ -1140,7 +1150,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             __syncwarp();
             w.reset();
             bool activate = sflag == SETUP_SOLVE_ACTIVATE;
-            if (a.state && a.state_load) {
+            if (EXT && a.state && a.state_load) {
                 // warm: continue from the previous solve's factor and working set (the reference's daqp_solve on a kept
                 // workspace). The right-hand sides changed (daqp_update_d sets reuse_ind = 0, utils.c:506), so the active
                 // bounds are re-read; a constraint that the new bounds turned into an equality (check_bounds,
@@ -1179,7 +1189,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             w.begin(activate);
         }
         int exitflag;
-        do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV>::RUNNING);
+        do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV, EXT>::RUNNING);
         {
         const int p = w.p, kfin = uni(w.k);
         if (uni(w.iter == 0)) {
@@ -1218,7 +1228,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             }
             if (lane == 0) {
                 if (vv) a.fval[p] = (T)0.5 * (w.fval - vnorm);
-                if (a.soft_slack) a.soft_slack[p] = w.soft_slack;
+                if (a.soft_slack) a.soft_slack[p] = EXT ? w.soft_slack : (T)0;
                 a.exitflag[p] = exitflag;
                 a.iter[p] = w.iter;
             }
@@ -1227,7 +1237,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
         if (a.ws_out) LANE_LOOP(i, 0, kfin) a.ws_out[(size_t)p * a.cap + i] = w.WS()[i];
         if (a.sense_out) LANE_LOOP(i, 0, a.m) a.sense_out[(size_t)p * a.ldm + i] = w.sense()[i];
         if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = w.cnt()[lane];
-        if (a.state && a.state_save) { // keep factor, multipliers, working set and sense for the next warm solve
+        if (EXT && a.state && a.state_save) { // keep factor, multipliers, working set and sense for the next warm solve
             char* blob = a.state + (size_t)p * a.state_stride;
             int4* dst4 = reinterpret_cast<int4*>(blob);
             const int4* src4 = reinterpret_cast<const int4*>(w.S);

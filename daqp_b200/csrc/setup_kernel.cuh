@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                 bulk_prefetch_l2(ab + off, (unsigned)(((abytes - off) < 32768 ? (abytes - off) : 32768) & ~(size_t)15));
         }
         __syncwarp();
+        // ... and the first row block into its staging buffer (nothing else touches it before the product loop)
+        const unsigned stage = smem_u32(arow);
+        if (mA > 0) async_block_copy(stage, reinterpret_cast<const char*>(A), (unsigned)(min(SETUP_RB, mA) * n * sizeof(T)), lane);
 
         // ---- sense copy + check_bounds (utils.c:84-98, 546-567)
         int any_fixed = 0, bad = 0, unsupported = 0, nsoft = 0;
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
 
         if (flag < 0) { // setup failure: exit flag only, x untouched (api.c:69-72)
             if (lane == 0) { a.setup_flag[p] = flag; a.exitflag[p] = flag; a.iter[p] = 0; }
+            cp_async_wait<0>(); // the staged row block must land before the next problem reuses the buffer
             __syncwarp();
             continue;
         }
@@ -250,8 +254,6 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
         int zero_row_infeasible = 0;
         // The row blocks of A stream through ONE staging buffer with cp.async: the copy of block k+1 is issued as soon as
         // the product loop of block k has read the buffer, and lands while block k's norms / d / stores are computed.
-        const unsigned stage = smem_u32(arow);
-        if (mA > 0) async_block_copy(stage, reinterpret_cast<const char*>(A), (unsigned)(min(SETUP_RB, mA) * n * sizeof(T)), lane);
         for (int r0 = 0; r0 < mA; r0 += SETUP_RB) {
             const int nr = min(SETUP_RB, mA - r0);
             // the block's bounds, one row per lane, fetched before the product so that their latency is covered
