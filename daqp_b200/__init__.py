@@ -283,10 +283,11 @@ class BatchModel:
         _check(lib().daqp_b200_workspace_update(self._w, _p(f), _p(bupper), _p(blower)))
         return self
 
-    def solve(self, warm: bool = True, diag: bool = False) -> BatchResult:
+    def solve(self, warm: bool = True, diag: bool = False, out: BatchResult | None = None) -> BatchResult:
+        """``out``: reuse result arrays (pinned host memory keeps the read-back asynchronous)."""
         N, n, m, ms, ns = self.shape
-        r = BatchResult(x=np.empty((N, n)), lam=np.empty((N, m)), fval=np.zeros(N), exitflag=np.empty(N, np.intc),
-                        iter=np.empty(N, np.intc))
+        r = out or BatchResult(x=np.empty((N, n)), lam=np.empty((N, m)), fval=np.zeros(N),
+                               exitflag=np.empty(N, np.intc), iter=np.empty(N, np.intc))
         d = None
         if diag:
             ldm = (max(m, 1) + 3) // 4 * 4
