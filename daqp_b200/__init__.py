@@ -192,6 +192,39 @@ class Engine:
             r.sense = r.sense[:, :m]
         return r
 
+    def solve_batch_f32(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, diag: bool = False,
+                        **settings) -> BatchResult:
+        """Same batch in fp32 arithmetic end to end (``daqp_b200_solve_packed_f32``): the batched form of the reference
+        built with -DDAQP_SINGLE_PRECISION. Inputs are converted to float32; results are float32 arrays."""
+        L = lib()
+        L.daqp_b200_solve_packed_f32.restype = C.c_int
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        H = f32(H); f = f32(f); A = f32(A); bupper = f32(bupper); blower = f32(blower)
+        N, n = H.shape[0], H.shape[1]
+        m = bupper.shape[1]
+        mA = A.shape[1] if A is not None and A.size else 0
+        ms = m - mA if ms is None else ms
+        if sense is not None:
+            sense = np.ascontiguousarray(sense, dtype=np.intc)
+        r = BatchResult(x=np.empty((N, n), np.float32), lam=np.empty((N, m), np.float32), fval=np.zeros(N, np.float32),
+                        exitflag=np.empty(N, np.intc), iter=np.empty(N, np.intc))
+        d = None
+        if diag:
+            ldm = (max(m, 1) + 3) // 4 * 4
+            r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + 1), np.intc)
+            r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
+            d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
+                             r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)), None)
+        st = default_settings(**settings)
+        _check(L.daqp_b200_solve_packed_f32(self._h, N, n, m, ms, _p(H, fp), _p(f, fp), _p(A, fp), _p(bupper, fp),
+                                            _p(blower, fp), _p(sense, _ip), C.byref(st), _p(r.x, fp), _p(r.lam, fp),
+                                            _p(r.fval, fp), _p(r.exitflag, _ip), _p(r.iter, _ip),
+                                            C.byref(d) if d else None))
+        if diag:
+            r.sense = r.sense[:, :m]
+        return r
+
     # -- device arrays (torch CUDA tensors) -------------------------------------------------------------------
     def solve_batch_device(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, out=None,
                            diag=None, stream=None, **settings):

@@ -197,8 +197,14 @@ static cudaError_t launch_solve_x(const LdpArgs<T>& a, int grid, int block, size
 // soft constraints or a persistent workspace select the extended instantiation
 template <typename T, int NV>
 static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
-    return (a.ns_max > 0 || a.state) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
-                                     : launch_solve_x<T, NV, false>(a, grid, block, smem, s);
+    if constexpr (sizeof(T) == 4) { // fp32: plain path only, n <= 158 (five register segments)
+        if (a.ns_max > 0 || a.state || NV > 5) return cudaErrorNotSupported;
+        if constexpr (NV <= 5) return launch_solve_x<T, NV, false>(a, grid, block, smem, s);
+        else return cudaErrorNotSupported;
+    } else {
+        return (a.ns_max > 0 || a.state) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
+                                         : launch_solve_x<T, NV, false>(a, grid, block, smem, s);
+    }
 }
 template <typename T, int NGS>
 static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
@@ -314,7 +320,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         sa.x = dx + (size_t)p0 * n; sa.lam = dlam ? dlam + (size_t)p0 * m : nullptr; sa.fval = dfval + p0;
         sa.exitflag = dflag + p0; sa.iter = diter + p0;
         sa.work_counter = counters; sa.st = st;
-        sa.soft_slack = (diag && diag->soft_slack) ? diag->soft_slack + p0 : nullptr; sa.ns_max = ns_max;
+        sa.soft_slack = nullptr; sa.ns_max = ns_max;
+        if constexpr (sizeof(T) == sizeof(c_float)) sa.soft_slack = (diag && diag->soft_slack) ? diag->soft_slack + p0 : nullptr;
         sa.no_shortcut = ps ? 1 : 0; sa.sense_static = ps ? ps->sense_static : nullptr;
         if (!ps || ps->phase == 1) {
             const int grid = std::min(grid_max, (P + w_setup - 1) / w_setup);
@@ -390,11 +397,10 @@ extern "C" int daqp_b200_solve_device(DAQPB200Handle* h, int N, int n, int m, in
 
 // Host arrays: chunks are copied in on one stream while the previous chunk is solved on another and the one before
 // that is copied out on a third (double-buffered device staging).
-extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* H,
-                                      const c_float* f, const c_float* A, const c_float* bupper, const c_float* blower,
-                                      const int* sense, const DAQPSettings* settings, c_float* x, c_float* lam,
-                                      c_float* fval, int* exitflag, int* iter, const DAQPB200Diag* diag) {
-    typedef c_float T;
+template <typename T>
+static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, const T* H, const T* f, const T* A,
+                             const T* bupper, const T* blower, const int* sense, const DAQPSettings* settings, T* x,
+                             T* lam, T* fval, int* exitflag, int* iter, const DAQPB200Diag* diag) {
     if (!h) { int rc = default_handle(&h); if (rc) return rc; }
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
@@ -469,7 +475,7 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
         DAQPB200Diag dd{};
         if (diag) { dd.n_active = diag->n_active ? B.nact : nullptr; dd.ws = diag->ws ? B.ws : nullptr;
                     dd.counts = diag->counts ? B.counts : nullptr; dd.sense = diag->sense ? B.so : nullptr;
-                    dd.soft_slack = diag->soft_slack ? B.slack : nullptr; }
+                    if constexpr (sizeof(T) == sizeof(c_float)) dd.soft_slack = diag->soft_slack ? B.slack : nullptr; }
         result = solve_device_impl<T>(h, P, n, m, ms, B.H, f ? B.f : nullptr, B.A, B.bu, B.bl, sense ? B.sense : nullptr,
                                       settings, B.x, lam ? B.lam : nullptr, B.fval, B.flag, B.iter, diag ? &dd : nullptr,
                                       h->compute, ns_max);
@@ -486,7 +492,8 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
             if (diag->ws) CK(cudaMemcpyAsync(diag->ws + (size_t)p0 * cap, B.ws, (size_t)P * cap * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
             if (diag->counts) CK(cudaMemcpyAsync(diag->counts + (size_t)p0 * 4, B.counts, (size_t)P * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
             if (diag->sense) CK(cudaMemcpyAsync(diag->sense + (size_t)p0 * ldm, B.so, (size_t)P * ldm, cudaMemcpyDeviceToHost, h->copy_out));
-            if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack + p0, B.slack, (size_t)P * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
+            if constexpr (sizeof(T) == sizeof(c_float))
+                if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack + p0, B.slack, (size_t)P * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
         }
         CK(cudaEventRecord(ev_out[s], h->copy_out));
     }
@@ -497,6 +504,36 @@ extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, in
     if (e2 != cudaSuccess) return fail("compute stream", e2, __LINE__);
     if (e3 != cudaSuccess) return fail("copy_out stream", e3, __LINE__);
     return 0;
+}
+
+extern "C" int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* H,
+                                      const c_float* f, const c_float* A, const c_float* bupper, const c_float* blower,
+                                      const int* sense, const DAQPSettings* settings, c_float* x, c_float* lam,
+                                      c_float* fval, int* exitflag, int* iter, const DAQPB200Diag* diag) {
+    return solve_packed_impl<c_float>(h, N, n, m, ms, H, f, A, bupper, blower, sense, settings, x, lam, fval, exitflag,
+                                      iter, diag);
+}
+
+// fp32 arithmetic end to end: the batched form of the reference built with -DDAQP_SINGLE_PRECISION (include/types.h:8-12)
+extern "C" int daqp_b200_solve_packed_f32(DAQPB200Handle* h, int N, int n, int m, int ms, const float* H, const float* f,
+                                          const float* A, const float* bupper, const float* blower, const int* sense,
+                                          const DAQPSettings* settings, float* x, float* lam, float* fval,
+                                          int* exitflag, int* iter, const DAQPB200Diag* diag) {
+    return solve_packed_impl<float>(h, N, n, m, ms, H, f, A, bupper, blower, sense, settings, x, lam, fval, exitflag,
+                                    iter, diag);
+}
+
+extern "C" int daqp_b200_solve_device_f32(DAQPB200Handle* h, int N, int n, int m, int ms, const float* dH,
+                                          const float* df, const float* dA, const float* dbupper, const float* dblower,
+                                          const int* dsense, const DAQPSettings* settings, float* dx, float* dlam,
+                                          float* dfval, int* dexitflag, int* diter, const DAQPB200Diag* diag,
+                                          void* stream) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->compute;
+    return solve_device_impl<float>(h, N, n, m, ms, dH, df, dA, dbupper, dblower, dsense, settings, dx, dlam, dfval,
+                                    dexitflag, diter, diag, s);
 }
 
 // ---- persistent batch workspace: setup once, update(f, b) + solve many (reference setup_daqp / daqp_update_ldp /

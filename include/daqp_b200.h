@@ -15,7 +15,8 @@
  * constraints, hierarchies, AVI, H == NULL, singular H that needs the proximal-point driver) return
  * DAQP_EXIT_UNSUPPORTED (-8); there is no CPU fallback inside this library.
  *
- * All arithmetic is fp64 (c_float = double), like the reference's default build.
+ * Arithmetic is fp64 (c_float = double), like the reference's default build; the *_f32 entry points run the same
+ * kernels in fp32.
  */
 #ifndef DAQP_B200_H
 #define DAQP_B200_H
@@ -148,6 +149,23 @@ int daqp_b200_solve_device(DAQPB200Handle* h, int N, int n, int m, int ms,
                            const DAQPSettings* settings,
                            c_float* dx, c_float* dlam, c_float* dfval, int* dexitflag, int* diter,
                            const DAQPB200Diag* diag, void* stream);
+
+/* fp32 arithmetic end to end (c_float = float): the batched form of the reference built with -DDAQP_SINGLE_PRECISION
+ * (include/types.h:8-12). Same array shapes in float; settings stay the double struct and are rounded to float like
+ * the reference's constants. Plain inequality / equality / warm-start path only (no soft constraints), n <= 158;
+ * diag->soft_slack must be NULL. */
+int daqp_b200_solve_packed_f32(DAQPB200Handle* h, int N, int n, int m, int ms,
+                               const float* H, const float* f, const float* A,
+                               const float* bupper, const float* blower, const int* sense,
+                               const DAQPSettings* settings,
+                               float* x, float* lam, float* fval, int* exitflag, int* iter,
+                               const DAQPB200Diag* diag);
+int daqp_b200_solve_device_f32(DAQPB200Handle* h, int N, int n, int m, int ms,
+                               const float* dH, const float* df, const float* dA,
+                               const float* dbupper, const float* dblower, const int* dsense,
+                               const DAQPSettings* settings,
+                               float* dx, float* dlam, float* dfval, int* dexitflag, int* diter,
+                               const DAQPB200Diag* diag, void* stream);
 
 /* ---- persistent batch workspace (new): setup once, update(f, b) + solve many ------------------------------
  * The batched counterpart of the reference's workspace flow -- setup_daqp() once, then daqp_update_ldp(DAQP_UPDATE_v +
