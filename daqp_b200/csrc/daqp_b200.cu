@@ -415,9 +415,9 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         }
     const int mA = m - ms, cap = n + ns_max + 1, ldm = round_up(std::max(m, 1), 4);
     // The pipeline is bound by the host link (8.3 GB per 100k C3 problems at ~55 GB/s): what is left to tune is the part
-    // that cannot overlap -- the first chunk's copy-in and the last chunk's solve -- so chunks are small (8192) and
-    // the first one smaller still. Measured on C3: 16384 -> 174 ms, 8192 -> 163 ms, ramped 8192 -> see DESIGN.md.
-    int chunk = 8192, first_chunk = 2048;
+    // that cannot overlap -- the first chunk's copy-in and the last chunk's solve -- so chunks are small and the first
+    // and last one smaller still. Measured on C3 (ms per 100k): 16384 -> 174, 8192 -> 163, 6144 with 1024 ends -> 160.
+    int chunk = 6144, first_chunk = 1024;
     if (const char* c = getenv("DAQP_B200_HOST_CHUNK")) { chunk = std::max(1, atoi(c)); first_chunk = chunk; }
     if (const char* c = getenv("DAQP_B200_HOST_FIRST_CHUNK")) first_chunk = std::max(1, atoi(c));
     chunk = std::min(chunk, N);
@@ -425,12 +425,14 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     const size_t in_b = ((size_t)n * n + n + (size_t)mA * n + 2 * (size_t)m) * sizeof(T) + (size_t)m * sizeof(int);
     const size_t out_b = ((size_t)n + m + 2) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
     const size_t per_buf = (size_t)chunk * (in_b + out_b) + 17 * 256;
-    int rc = ensure(&h->stage, &h->stage_bytes, 2 * per_buf);
+    // three staging buffers: the copy-in of chunk c+2 does not have to wait for the solve of chunk c
+    constexpr int NB = 3;
+    int rc = ensure(&h->stage, &h->stage_bytes, NB * per_buf);
     if (rc) return rc;
 
     struct Buf { T *H, *f, *A, *bu, *bl; int* sense; T *x, *lam, *fval, *slack; int *flag, *iter, *nact, *ws, *counts; unsigned char* so; };
-    Buf b[2];
-    for (int i = 0; i < 2; i++) {
+    Buf b[NB];
+    for (int i = 0; i < NB; i++) {
         Carver cv(h->stage + i * per_buf);
         b[i].H = cv.take<T>((size_t)chunk * n * n); b[i].f = cv.take<T>((size_t)chunk * n);
         b[i].A = cv.take<T>((size_t)chunk * mA * n); b[i].bu = cv.take<T>((size_t)chunk * m);
@@ -440,8 +442,8 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         b[i].nact = cv.take<int>(chunk); b[i].ws = cv.take<int>((size_t)chunk * cap);
         b[i].counts = cv.take<int>((size_t)chunk * 4); b[i].so = cv.take<unsigned char>((size_t)chunk * ldm);
     }
-    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
-    for (int i = 0; i < 2; i++) {
+    cudaEvent_t ev_in[NB], ev_done[NB], ev_out[NB];
+    for (int i = 0; i < NB; i++) {
         CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
@@ -457,10 +459,10 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     }
     int p0 = 0;
     for (size_t ci = 0; ci < sched.size() && result == 0; p0 += sched[ci], ci++, c++) {
-        const int P = sched[ci], s = c & 1;
+        const int P = sched[ci], s = c % NB;
         Buf& B = b[s];
         // input buffers are free once the solve that read them (two chunks ago) has finished
-        if (c >= 2) CK(cudaStreamWaitEvent(h->copy_in, ev_done[s], 0));
+        if (c >= NB) CK(cudaStreamWaitEvent(h->copy_in, ev_done[s], 0));
         CK(cudaMemcpyAsync(B.H, H + (size_t)p0 * n * n, (size_t)P * n * n * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
         if (f) CK(cudaMemcpyAsync(B.f, f + (size_t)p0 * n, (size_t)P * n * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
         if (mA > 0) CK(cudaMemcpyAsync(B.A, A + (size_t)p0 * mA * n, (size_t)P * mA * n * sizeof(T), cudaMemcpyHostToDevice, h->copy_in));
@@ -471,7 +473,7 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         }
         CK(cudaEventRecord(ev_in[s], h->copy_in));
         CK(cudaStreamWaitEvent(h->compute, ev_in[s], 0));
-        if (c >= 2) CK(cudaStreamWaitEvent(h->compute, ev_out[s], 0)); // output buffers drained
+        if (c >= NB) CK(cudaStreamWaitEvent(h->compute, ev_out[s], 0)); // output buffers drained
         DAQPB200Diag dd{};
         if (diag) { dd.n_active = diag->n_active ? B.nact : nullptr; dd.ws = diag->ws ? B.ws : nullptr;
                     dd.counts = diag->counts ? B.counts : nullptr; dd.sense = diag->sense ? B.so : nullptr;
@@ -498,7 +500,7 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         CK(cudaEventRecord(ev_out[s], h->copy_out));
     }
     cudaError_t e1 = cudaStreamSynchronize(h->copy_in), e2 = cudaStreamSynchronize(h->compute), e3 = cudaStreamSynchronize(h->copy_out);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
+    for (int i = 0; i < NB; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
     if (result) return result;
     if (e1 != cudaSuccess) return fail("copy_in stream", e1, __LINE__);
     if (e2 != cudaSuccess) return fail("compute stream", e2, __LINE__);

@@ -5,21 +5,29 @@
 // machine, and the LDP->QP back-transform + result extraction.
 //
 // Memory plan per problem
-//   shared (warp-private, lives for the whole solve): packed L, D, lam, lam*, xldl, zldl, active bounds, u, WS, sense
-//   global, streamed every feasibility scan : Mt  = constraint matrix, column-major [n][ldm]  (128-bit coalesced)
-//   global, gathered per add / primal update: Mr  = same matrix, row-major [m][ldn]           (128-bit coalesced rows)
+//   shared (warp-private, lives for the whole solve): packed L, D, lam, lam*, xldl, zldl, active bounds, u, WS, sense,
+//                                             and a small cp.async staging arena (scan ring / active-row chunks)
+//   global, streamed every feasibility scan : Mt32 = fp32 copy of the constraint matrix in quad layout (screening);
+//                                             Mt   = fp64 column-major [n][ldm] for the exact scan when the
+//                                                    screening cannot name the winner
+//   global, gathered per add / primal update: Mr   = same matrix, fp64 row-major [m][ldn] (128-bit coalesced rows)
 //   global, once                            : dupper, dlower, scaling, Rinv (packed), v
-// Both matrix copies are written by the setup kernel; rows 0..ms-1 are the normalised rows of R^-1 (simple bounds,
+// All matrix copies are written by the setup kernel; rows 0..ms-1 are the normalised rows of R^-1 (simple bounds,
 // zero-filled below the diagonal), rows ms..m-1 the normalised rows of A R^-1.
 //
-// Two constraints shaped this file (both measured, see profiles/ and DESIGN.md §6):
-//  * Instruction cache. Sixteen warps of one SM sit in sixteen different phases, so the HOT instruction footprint
-//    must stay well below the SM's ~32 KB instruction cache (hit rate fell 94% -> 81% -> 73% as it grew 29 -> 34 -> 41
-//    KB, and kernel time rose 146 -> 163 -> 200 ms). Every heavy routine therefore has ONE call site on the hot
-//    path, loops over register segments are dynamic, and there are no remainder loops.
-//  * Registers. 16 warps/SM leave 128 registers per thread. Persistent state is kept to a dozen registers: one
-//    shared-memory base pointer, the problem index and a few counters; every array position is a kernel-parameter
-//    offset (constant bank operand), every global pointer is rebuilt from the problem index where it is used.
+// Three constraints shaped this file (all measured, see profiles/ and DESIGN.md §6):
+//  * Convergence proofs. ptxas guards every warp collective with a divergence check and a slow path unless it can
+//    PROVE the warp is converged, and one unproven spot taints the rest of the enclosing loop. Hence: structured
+//    control flow (a problem loop around an iteration loop, no `continue`, one back edge per loop), an explicit
+//    __syncwarp() before a back edge that follows a lane-divergent `if`, uniform-trip LANE_LOOPs, and uni() around
+//    every branch condition that comes from memory or from a butterfly reduction.
+//  * Instruction cache. A dozen warps of one SM sit in a dozen different phases, so the HOT instruction footprint
+//    must stay near the SM's ~32 KB instruction cache (hit rate 94% / 82% / 75% at 29 / 39 / 45 KB). Heavy routines
+//    have ONE call site on the hot path, the row-chunk issue code is one shared __noinline__ function, pipelined loops
+//    are rotated so that their prologue is the first trip, sweeps are rolled, and the features the headline path does
+//    not need (soft constraints, workspace state) live in a separate instantiation (EXT).
+//  * Shared memory sets the occupancy (the packed factor alone is 10 KB at n = 50): the staging arena is sized so
+//    that twelve problems stay resident per SM.
 #pragma once
 #include "common.cuh"
 #include <limits.h>

@@ -33,6 +33,7 @@ for _ in range(2): d.copy_(a, non_blocking=True); torch.cuda.synchronize()
 t0 = time.perf_counter(); d.copy_(a, non_blocking=True); torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print("raw pinned H2D GB/s: %.1f" % (1.0737 / dt), flush=True)
 del a, d
-for chunk in (4096, 8192, 16384, 32768, 50000):
-    env = dict(os.environ, DAQP_B200_HOST_CHUNK=str(chunk))
+for chunk, first in ((8192, 2048), (4096, 2048), (8192, 1024), (6144, 1024), (12288, 2048)):
+    env = dict(os.environ, DAQP_B200_HOST_CHUNK=str(chunk), DAQP_B200_HOST_FIRST_CHUNK=str(first))
+    print("first", first, end=" ", flush=True)
     subprocess.run([sys.executable, "/tmp/e2e_one.py", str(P)], env=env)
