@@ -265,6 +265,39 @@ class Engine:
                                             C.byref(d) if d else None, C.c_void_p(stream)))
         return out
 
+    def solve_batch_device_f32(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, out=None, stream=None,
+                               **settings):
+        """fp32 CUDA tensors through ``daqp_b200_solve_device_f32`` (asynchronous on the current torch stream)."""
+        import torch
+        L = lib()
+        L.daqp_b200_solve_device_f32.restype = C.c_int
+        N, n = H.shape[0], H.shape[1]
+        m = bupper.shape[1]
+        mA = A.shape[1] if A is not None and A.numel() else 0
+        ms = m - mA if ms is None else ms
+        dev = H.device
+        for t in (H, f, A, bupper, blower):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        if out is None:
+            out = {"x": torch.empty((N, n), dtype=torch.float32, device=dev),
+                   "lam": torch.empty((N, m), dtype=torch.float32, device=dev),
+                   "fval": torch.zeros(N, dtype=torch.float32, device=dev),
+                   "exitflag": torch.empty(N, dtype=torch.int32, device=dev),
+                   "iter": torch.empty(N, dtype=torch.int32, device=dev)}
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        if stream == 0:
+            stream = 1
+        fp = C.POINTER(C.c_float)
+        ptr = lambda t, ty=fp: None if t is None else C.cast(t.data_ptr(), ty)
+        st = default_settings(**settings)
+        _check(L.daqp_b200_solve_device_f32(self._h, N, n, m, ms, ptr(H), ptr(f), ptr(A), ptr(bupper), ptr(blower),
+                                            ptr(sense, _ip), C.byref(st), ptr(out["x"]), ptr(out["lam"]),
+                                            ptr(out["fval"]), ptr(out["exitflag"], _ip), ptr(out["iter"], _ip),
+                                            None, C.c_void_p(stream)))
+        return out
+
     @staticmethod
     def alloc_diag(N: int, n: int, m: int, device, ns: int = 0):
         """ns = the largest number of soft constraints per problem (rows of ``ws`` hold n + ns + 1 entries)."""
