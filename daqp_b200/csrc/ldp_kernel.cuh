@@ -429,6 +429,7 @@ struct Warp {
             }
             __syncwarp();
             T alpha = Dp[r];
+            __syncwarp(); // every lane holds D[r] before lane 0 overwrites it in the first step below
 #pragma unroll
             for (int qp = 0; qp < NV; qp++) { // pivot = trailing row t, held in register segment qp
                 const int tend = min(nu, 32 * qp + 32);

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(512, 1) qp_setup_kernel(const SetupArgs<T> a) 
                 T part = 0;
                 for (int kk = lane; kk < i; kk += 32) { const T t = R[roff(kk, n) + i]; part += t * t; }
                 T di = Ri[i] - warp_sum(part);
+                __syncwarp(); // every lane has read the pivot before lane 0 replaces it below
                 if (di <= st.zero_tol) { singular = true; break; }
                 min_piv = fmin(min_piv, di);
                 max_piv = fmax(max_piv, di);
