@@ -367,6 +367,42 @@ class BatchModel:
             r.sense = r.sense[:, :m]
         return r
 
+    # -- closed loops that live on the GPU: torch CUDA tensors in, torch CUDA tensors out, nothing synchronises ----------
+    def update_device(self, f=None, bupper=None, blower=None, stream=None):
+        import torch
+        L = lib()
+        L.daqp_b200_workspace_update_device.restype = C.c_int
+        for t in (f, bupper, blower):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        ptr = lambda t: None if t is None else C.cast(t.data_ptr(), _dp)
+        _check(L.daqp_b200_workspace_update_device(self._w, ptr(f), ptr(bupper), ptr(blower), self._stream(stream)))
+        return self
+
+    def solve_device(self, warm: bool = True, out=None, stream=None):
+        import torch
+        L = lib()
+        L.daqp_b200_workspace_solve_device.restype = C.c_int
+        N, n, m, ms, ns = self.shape
+        if out is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            out = {"x": torch.empty((N, n), dtype=torch.float64, device=dev),
+                   "lam": torch.empty((N, m), dtype=torch.float64, device=dev),
+                   "fval": torch.zeros(N, dtype=torch.float64, device=dev),
+                   "exitflag": torch.empty(N, dtype=torch.int32, device=dev),
+                   "iter": torch.empty(N, dtype=torch.int32, device=dev)}
+        ptr = lambda t, ty=_dp: C.cast(t.data_ptr(), ty)
+        _check(L.daqp_b200_workspace_solve_device(self._w, int(warm), ptr(out["x"]), ptr(out["lam"]), ptr(out["fval"]),
+                                                  ptr(out["exitflag"], _ip), ptr(out["iter"], _ip), self._stream(stream)))
+        return out
+
+    @staticmethod
+    def _stream(stream):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        return C.c_void_p(1 if stream == 0 else stream)  # cudaStreamLegacy names torch's default stream explicitly
+
     def close(self):
         if self._w:
             lib().daqp_b200_workspace_free(self._w)

@@ -642,19 +642,17 @@ extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m,
     return 0;
 }
 
-extern "C" int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f, const c_float* bupper,
-                                          const c_float* blower) {
+// kind: host arrays are staged with cudaMemcpyHostToDevice, device arrays with DeviceToDevice (the workspace keeps its
+// own copy of the current f / bounds either way: a later update may replace only some of them)
+static int workspace_update_impl(DAQPB200Workspace* w, const c_float* f, const c_float* bupper, const c_float* blower,
+                                 cudaMemcpyKind kind, cudaStream_t st) {
     typedef c_float T;
-    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
     DAQPB200Handle* h = w->h;
-    std::lock_guard<std::mutex> lk(h->mu);
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = h->compute;
     const int N = w->N, n = w->n, m = w->m;
     if (f && !w->has_f) { g_last_error = "daqp_b200: the workspace was set up without a linear term"; return -2; }
-    if (f) CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (bupper) CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (blower) CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (f) CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), kind, st));
+    if (bupper) CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), kind, st));
+    if (blower) CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), kind, st));
     UpdateArgs<T> ua;
     ua.P = N; ua.n = n; ua.m = m; ua.ms = w->ms; ua.ldm = w->ldm;
     ua.f = f ? w->d_f : nullptr; ua.bupper = w->d_bu; ua.blower = w->d_bl;
@@ -667,6 +665,23 @@ extern "C" int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f
     ldp_update_kernel<T><<<std::min(h->num_sms * 4, (N + warps - 1) / warps), 32 * warps, smem, st>>>(ua);
     CK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f, const c_float* bupper,
+                                          const c_float* blower) {
+    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
+    std::lock_guard<std::mutex> lk(w->h->mu);
+    CK(cudaSetDevice(w->h->device));
+    return workspace_update_impl(w, f, bupper, blower, cudaMemcpyHostToDevice, w->h->compute);
+}
+
+extern "C" int daqp_b200_workspace_update_device(DAQPB200Workspace* w, const c_float* df, const c_float* dbupper,
+                                                 const c_float* dblower, void* stream) {
+    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
+    std::lock_guard<std::mutex> lk(w->h->mu);
+    CK(cudaSetDevice(w->h->device));
+    return workspace_update_impl(w, df, dbupper, dblower, cudaMemcpyDeviceToDevice,
+                                 stream ? (cudaStream_t)stream : w->h->compute);
 }
 
 extern "C" int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float* x, c_float* lam, c_float* fval,
@@ -698,6 +713,29 @@ extern "C" int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float
         if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack, w->d_slack, (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Device-resident variant for closed loops that live on the GPU: results go straight to the caller's device arrays,
+// nothing is copied to the host and nothing synchronises.
+extern "C" int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, c_float* dx, c_float* dlam,
+                                                c_float* dfval, int* dexitflag, int* diter, void* stream) {
+    typedef c_float T;
+    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
+    DAQPB200Handle* h = w->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->compute;
+    // the update kernel records setup failures (infeasible bounds) in the workspace's own flag / iter arrays: carry them over
+    CK(cudaMemcpyAsync(dexitflag, w->d_flag, (size_t)w->N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (diter) CK(cudaMemcpyAsync(diter, w->d_iter, (size_t)w->N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    w->ps.phase = 2; w->ps.state_load = warm ? 1 : 0;
+    int rc = solve_device_impl<T>(h, w->N, w->n, w->m, w->ms, nullptr, w->has_f ? w->d_f : nullptr, nullptr, w->d_bu, w->d_bl,
+                                  w->has_sense ? w->d_sense : nullptr, &w->settings, dx, dlam, dfval ? dfval : w->d_fval,
+                                  dexitflag, diter ? diter : w->d_iter, nullptr, st, w->ns_max, &w->ps);
+    if (rc) return rc;
+    // keep the workspace's flag array current: the next update consults it for setups the Hessian made permanent failures
+    CK(cudaMemcpyAsync(w->d_flag, dexitflag, (size_t)w->N * sizeof(int), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

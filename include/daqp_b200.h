@@ -185,6 +185,12 @@ int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f, const c_f
  * Blocks until the results are in the host arrays. diag may be NULL (ws rows hold n + ns + 1 entries). */
 int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float* x, c_float* lam, c_float* fval,
                               int* exitflag, int* iter, const DAQPB200Diag* diag);
+/* The same two calls for closed loops that live on the GPU: DEVICE arrays, asynchronous on `stream` (a cudaStream_t;
+ * NULL = the engine's own stream), no host copies, no synchronisation. Use ONE stream for a workspace. */
+int daqp_b200_workspace_update_device(DAQPB200Workspace* w, const c_float* df, const c_float* dbupper,
+                                      const c_float* dblower, void* stream);
+int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, c_float* dx, c_float* dlam, c_float* dfval,
+                                     int* dexitflag, int* diter, void* stream);
 void daqp_b200_workspace_free(DAQPB200Workspace* w);
 
 /* Device-time accounting of the engine since the last reset (CUDA events on the launching stream). */

@@ -254,6 +254,32 @@ def test_workspace_sequence_matches_reference(cuda_lib, name):
     mdl.close()
 
 
+def test_workspace_device_entry_points(cuda_lib):
+    """update_device / solve_device (torch CUDA tensors, asynchronous) give the same sequence as the host entry points."""
+    import os
+    import torch
+    import daqp_b200
+    from common import GOLDEN_DIR
+    d = np.load(os.path.join(GOLDEN_DIR, "wsseq_n20_m60_ms5.npz"))
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    host = daqp_b200.BatchModel().setup(d["H"], d["f"], d["A"], d["bupper"], d["blower"], None, ms=int(d["ms"]))
+    devm = daqp_b200.BatchModel().setup(d["H"], d["f"], d["A"], d["bupper"], d["blower"], None, ms=int(d["ms"]))
+    for k in range(int(d["K"]) + 1):
+        if k > 0:
+            host.update(f=d[f"f{k-1}"], bupper=d[f"bu{k-1}"], blower=d[f"bl{k-1}"])
+            devm.update_device(t(d[f"f{k-1}"]), t(d[f"bu{k-1}"]), t(d[f"bl{k-1}"]))
+        rh = host.solve(warm=True)
+        rd = devm.solve_device(warm=True)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(rd["exitflag"].cpu().numpy(), rh.exitflag)
+        np.testing.assert_array_equal(rd["iter"].cpu().numpy(), rh.iter)
+        ok = rh.exitflag > 0
+        np.testing.assert_array_equal(rd["x"].cpu().numpy()[ok], rh.x[ok])
+        np.testing.assert_array_equal(rd["lam"].cpu().numpy()[ok], rh.lam[ok])
+    host.close(); devm.close()
+
+
 def test_settings_and_limits(engine, oracle):
     b = generate_g1(100, 20, 60, 0, 16, seed=51)
     o, r = check_vs_oracle(engine, oracle, b, "iter_limit", settings={"iter_limit": 7})
