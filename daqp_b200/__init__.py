@@ -298,6 +298,47 @@ class Engine:
                                             None, C.c_void_p(stream)))
         return out
 
+    # -- minimal representation of polyhedra (batched LDP consumer) ----------------------------------------------
+    def minrep_batch(self, A, b, ms: int | None = None, info: bool = False, **settings):
+        """P polyhedra {x : [I(ms); A[q]] x <= b[q]} in host memory: A[P,m-ms,n], b[P,m] -> is_redundant[P,m]
+        (``daqp_b200_minrep_batch``; the batched form of the reference's ``daqp.minrep``, daqp.pyx:636-652). With
+        ``info`` also returns the exit flag and iteration count of every LDP."""
+        L = lib()
+        L.daqp_b200_minrep_batch.restype = C.c_int
+        A = _f64(A); b = _f64(b)
+        P, m = b.shape
+        mA, n = A.shape[1], A.shape[2]
+        ms = m - mA if ms is None else ms
+        red = np.empty((P, m), np.intc); flag = np.empty((P, m), np.intc); it = np.empty((P, m), np.intc)
+        st = default_settings(**settings)
+        _check(L.daqp_b200_minrep_batch(self._h, P, n, m, ms, _p(A), _p(b), C.byref(st), _p(red, _ip),
+                                        _p(flag, _ip), _p(it, _ip)))
+        return (red, flag, it) if info else red
+
+    def minrep_batch_device(self, A, b, ms: int | None = None, out=None, stream=None, **settings):
+        """CUDA tensors (float64, contiguous) through ``daqp_b200_minrep_device``; asynchronous on the current torch
+        stream. Returns {"is_redundant", "exitflag", "iter"} int32 tensors of shape [P, m]."""
+        import torch
+        L = lib()
+        L.daqp_b200_minrep_device.restype = C.c_int
+        P, m = b.shape
+        mA, n = A.shape[1], A.shape[2]
+        ms = m - mA if ms is None else ms
+        for t in (A, b):
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        if out is None:
+            out = {k: torch.empty((P, m), dtype=torch.int32, device=b.device) for k in ("is_redundant", "exitflag", "iter")}
+        if stream is None:
+            stream = torch.cuda.current_stream(b.device).cuda_stream
+        if stream == 0:
+            stream = 1
+        ptr = lambda t, ty=_dp: C.cast(t.data_ptr(), ty)
+        st = default_settings(**settings)
+        _check(L.daqp_b200_minrep_device(self._h, P, n, m, ms, ptr(A), ptr(b), C.byref(st),
+                                         ptr(out["is_redundant"], _ip), ptr(out["exitflag"], _ip),
+                                         ptr(out["iter"], _ip), C.c_void_p(stream)))
+        return out
+
     @staticmethod
     def alloc_diag(N: int, n: int, m: int, device, ns: int = 0):
         """ns = the largest number of soft constraints per problem (rows of ``ws`` hold n + ns + 1 entries)."""
@@ -424,6 +465,30 @@ def solve_batch(H, f, A, bupper, blower, sense=None, **kw) -> BatchResult:
     if _default_engine is None:
         _default_engine = Engine()
     return _default_engine.solve_batch(H, f, A, bupper, blower, sense, **kw)
+
+
+def minrep(A, b):
+    """Drop-in for the reference's ``daqp.minrep(A, b)`` (interfaces/daqp-python/daqp.pyx:636-652): which constraints
+    of {x : A x <= b} are redundant. ``b`` longer than A's row count means the leading entries are simple bounds.
+    Goes through the ``daqp_minrep`` symbol (reference include/api.h:54); the m LDPs run concurrently on the GPU."""
+    L = lib()
+    L.daqp_minrep.restype = None
+    A = _f64(A); b = _f64(b)
+    mA, n = A.shape
+    m = b.shape[0]
+    red = np.zeros(m, np.intc)
+    L.daqp_minrep(_p(red, _ip), _p(A), _p(b), C.c_int(n), C.c_int(m), C.c_int(m - mA))
+    if m and red[0] < 0:
+        raise RuntimeError(f"daqp_minrep failed: {L.daqp_b200_last_error().decode()}")
+    return red
+
+
+def minrep_batch(A, b, **kw):
+    """Module-level convenience: ``Engine().minrep_batch`` on a process-wide engine."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine.minrep_batch(A, b, **kw)
 
 
 def quadprog_batch(problems: list[dict], **settings):

@@ -8,6 +8,7 @@
 #include "ldp_kernel.cuh"
 #include "setup_kernel.cuh"
 #include "update_kernel.cuh"
+#include "minrep_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -198,11 +199,11 @@ static cudaError_t launch_solve_x(const LdpArgs<T>& a, int grid, int block, size
 template <typename T, int NV>
 static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
     if constexpr (sizeof(T) == 4) { // fp32: plain path only, n <= 158 (five register segments)
-        if (a.ns_max > 0 || a.state || NV > 5) return cudaErrorNotSupported;
+        if (a.ns_max > 0 || a.state || a.grp > 1 || NV > 5) return cudaErrorNotSupported;
         if constexpr (NV <= 5) return launch_solve_x<T, NV, false>(a, grid, block, smem, s);
         else return cudaErrorNotSupported;
     } else {
-        return (a.ns_max > 0 || a.state) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
+        return (a.ns_max > 0 || a.state || a.grp > 1) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
                                          : launch_solve_x<T, NV, false>(a, grid, block, smem, s);
     }
 }
@@ -536,6 +537,211 @@ extern "C" int daqp_b200_solve_device_f32(DAQPB200Handle* h, int N, int n, int m
     cudaStream_t s = stream ? (cudaStream_t)stream : h->compute;
     return solve_device_impl<float>(h, N, n, m, ms, dH, df, dA, dbupper, dblower, dsense, settings, dx, dlam, dfval,
                                     dexitflag, diter, diag, s);
+}
+
+// ---- batched minimal representation (reference daqp_minrep: src/api.c:531-556, src/utils.c:808-835) ---------------
+// Device arrays in, device array out: P polyhedra x m constraints = P m LDPs, solved concurrently by the solve kernel in
+// shared-matrix mode (minrep_kernel.cuh). Chunked over polyhedra when the scratch limit asks for it.
+static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA, const c_float* db,
+                              const DAQPSettings* settings, int* dred, int* dflag_out, int* diter_out,
+                              cudaStream_t stream, const unsigned char* ddropped = nullptr) {
+    if (P <= 0 || m <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid polyhedron dimensions"; return -2; }
+    typedef c_float T;
+    constexpr int V = VecOf<T>::N;
+    const int ldm = round_up(m, 4), ldn = round_up(n, V), cap = n + 1, mA = m - ms, nv = (cap + 31) / 32;
+    if (nv > 8) { g_last_error = "daqp_b200: n > 255 is not supported"; return -2; }
+    LdpArgs<T> la;
+    memset(&la, 0, sizeof(la));
+    la.n = n; la.m = m; la.ms = ms; la.ldm = ldm; la.ldn = ldn; la.cap = cap;
+    const size_t smem_w = ldp_layout<T>(la);
+    int w_solve = (int)std::min<size_t>(16, h->smem_optin / smem_w);
+    if (w_solve < 1) { g_last_error = "daqp_b200: polyhedron too large for shared memory"; return -2; }
+    h->stats.warps_per_sm = w_solve;
+    const size_t ntri = (size_t)n * (n + 1) / 2;
+    const size_t per_poly = ((size_t)n * ldm + (size_t)m * ldn + ldm + ntri) * sizeof(T) + 4 * 256;
+    const size_t per_ldp = ((size_t)2 * ldm + n + 1) * sizeof(T) + ldm + 3 * sizeof(int);
+    const size_t per = per_poly + (size_t)m * per_ldp;
+    int chunk = (int)std::min<long long>(P, std::max<long long>(1, (h->scratch_limit - (8 << 20)) / (long long)per));
+    chunk = (int)std::min<long long>(chunk, (long long)(INT_MAX / 2) / m); // LDP indices are ints
+    const int grid_max = h->num_sms;
+    const size_t pst = (size_t)grid_max * 16 * cap * (sizeof(int) + sizeof(T)) + 4096;
+    int rc = ensure(&h->arena, &h->arena_bytes, (size_t)chunk * per + pst + (1 << 20));
+    if (rc) return rc;
+    const DevSettings<T> st = to_dev_settings<T>(settings);
+    for (int q0 = 0; q0 < P; q0 += chunk) {
+        const int Q = std::min(chunk, P - q0);
+        const size_t NL = (size_t)Q * m;
+        Carver cv(h->arena);
+        int* counters = cv.take<int>(64);
+        MinrepArgs ma;
+        ma.P = Q; ma.n = n; ma.m = m; ma.ms = ms; ma.ldm = ldm; ma.ldn = ldn;
+        ma.A = dA + (size_t)q0 * mA * n; ma.b = db + (size_t)q0 * m;
+        ma.dropped = ddropped ? ddropped + (size_t)q0 * m : nullptr;
+        ma.Mt = cv.take<T>((size_t)Q * n * ldm); ma.Mr = cv.take<T>((size_t)Q * m * ldn);
+        ma.scaling = cv.take<T>((size_t)Q * ldm); ma.Rinv = cv.take<T>((size_t)Q * ntri);
+        ma.dupper = cv.take<T>(NL * ldm); ma.dlower = cv.take<T>(NL * ldm);
+        ma.sense = cv.take<unsigned char>(NL * ldm);
+        ma.setup_flag = cv.take<int>(NL);
+        ma.exitflag = dflag_out ? dflag_out + (size_t)q0 * m : cv.take<int>(NL);
+        ma.iter = diter_out ? diter_out + (size_t)q0 * m : cv.take<int>(NL);
+        T* xs = cv.take<T>(NL * n);
+        T* fv = cv.take<T>(NL);
+        int* pst_id = cv.take<int>((size_t)grid_max * 16 * cap);
+        T* pst_lam = cv.take<T>((size_t)grid_max * 16 * cap);
+
+        EventTriple ev;
+        rc = get_events(h, &ev);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
+        CK(cudaEventRecord(ev.e0, stream));
+        minrep_prep_kernel<<<std::min(Q, 8 * grid_max), 256, 0, stream>>>(ma);
+        CK(cudaGetLastError());
+        h->stats.setup_launches++;
+        CK(cudaEventRecord(ev.e1, stream));
+
+        la.P = (int)NL; la.grp = m;
+        la.Mt = ma.Mt; la.Mr = ma.Mr; la.Mt32 = nullptr; la.scaling = ma.scaling; la.Rinv = ma.Rinv; la.v = nullptr;
+        la.dupper = ma.dupper; la.dlower = ma.dlower; la.sense = ma.sense; la.setup_flag = ma.setup_flag;
+        la.x = xs; la.lam = nullptr; la.fval = fv; la.exitflag = ma.exitflag; la.iter = ma.iter;
+        la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
+        const int grid = (int)std::min<size_t>(grid_max, (NL + w_solve - 1) / w_solve);
+        const size_t smem = smem_w * w_solve;
+        cudaError_t e = cudaErrorInvalidValue;
+        switch (nv) {
+#ifndef DAQP_B200_FAST_BUILD
+            case 1: e = launch_solve<T, 1>(la, grid, 32 * w_solve, smem, stream); break;
+#endif
+            case 2: e = launch_solve<T, 2>(la, grid, 32 * w_solve, smem, stream); break;
+#ifndef DAQP_B200_FAST_BUILD
+            case 3: e = launch_solve<T, 3>(la, grid, 32 * w_solve, smem, stream); break;
+            case 4: e = launch_solve<T, 4>(la, grid, 32 * w_solve, smem, stream); break;
+            case 5: e = launch_solve<T, 5>(la, grid, 32 * w_solve, smem, stream); break;
+            case 6: e = launch_solve<T, 6>(la, grid, 32 * w_solve, smem, stream); break;
+            case 7: e = launch_solve<T, 7>(la, grid, 32 * w_solve, smem, stream); break;
+            default: e = launch_solve<T, 8>(la, grid, 32 * w_solve, smem, stream); break;
+#endif
+        }
+        if (e != cudaSuccess) return fail("ldp_solve_kernel launch (minrep)", e, __LINE__);
+        h->stats.solve_launches++;
+        minrep_finish_kernel<<<(int)std::min<size_t>(1024, (NL + 255) / 256), 256, 0, stream>>>(ma.exitflag, dred + (size_t)q0 * m, NL);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev.e2, stream));
+        h->pending.push_back(ev);
+        if (q0 + chunk < P) CK(cudaStreamSynchronize(stream)); // the next chunk reuses the scratch
+    }
+    return 0;
+}
+
+extern "C" int daqp_b200_minrep_device(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA,
+                                       const c_float* db, const DAQPSettings* settings, int* dis_redundant,
+                                       int* dexitflag, int* diter, void* stream) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return minrep_device_impl(h, P, n, m, ms, dA, db, settings, dis_redundant, dexitflag, diter,
+                              stream ? (cudaStream_t)stream : h->compute);
+}
+
+// One round on host arrays: stage, run, copy back. `dropped` ([P][m] bytes) may be NULL.
+static int minrep_host_round(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* A, const c_float* b,
+                             const unsigned char* dropped, const DAQPSettings* settings, int* is_redundant,
+                             int* exitflag, int* iter) {
+    const size_t mA = (size_t)(m - ms), nA = (size_t)P * mA * n, nb = (size_t)P * m;
+    int rc = ensure(&h->stage, &h->stage_bytes, (nA + nb) * sizeof(c_float) + 3 * nb * sizeof(int) + nb + 8 * 256);
+    if (rc) return rc;
+    Carver cv(h->stage);
+    c_float* dA = cv.take<c_float>(nA);
+    c_float* db = cv.take<c_float>(nb);
+    int* dred = cv.take<int>(nb);
+    int* dflag = cv.take<int>(nb);
+    int* dit = cv.take<int>(nb);
+    unsigned char* ddr = cv.take<unsigned char>(nb);
+    cudaStream_t s = h->compute;
+    if (nA) CK(cudaMemcpyAsync(dA, A, nA * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(db, b, nb * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    if (dropped) CK(cudaMemcpyAsync(ddr, dropped, nb, cudaMemcpyHostToDevice, s));
+    rc = minrep_device_impl(h, P, n, m, ms, dA, db, settings, dred, dflag, dit, s, dropped ? ddr : nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(is_redundant, dred, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(exitflag, dflag, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(iter, dit, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int daqp_b200_minrep_batch(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* A,
+                                      const c_float* b, const DAQPSettings* settings, int* is_redundant,
+                                      int* exitflag, int* iter) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (P <= 0 || m <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid polyhedron dimensions"; return -2; }
+    const size_t mA = (size_t)(m - ms), nb = (size_t)P * m;
+    std::vector<int> flag_own, iter_own;
+    if (!exitflag) { flag_own.resize(nb); exitflag = flag_own.data(); }
+    if (!iter) { iter_own.resize(nb); iter = iter_own.data(); }
+    int rc = minrep_host_round(h, P, n, m, ms, A, b, nullptr, settings, is_redundant, exitflag, iter);
+    if (rc) return rc;
+    // Empty polyhedra (every probe infeasible): the reference's answer is the one its probing ORDER produces -- constraints
+    // are dropped from the front until the rest is non-empty (utils.c:814-824). Re-run those polyhedra with their first
+    // remaining constraint dropped until a probe is feasible; everything else is final after the first round.
+    std::vector<int> todo;
+    std::vector<unsigned char> dropped; // [todo.size()][m]
+    for (int q = 0; q < P; q++) {
+        bool all = true;
+        for (int i = 0; i < m && all; i++) all = is_redundant[(size_t)q * m + i] == 1;
+        if (all) todo.push_back(q);
+    }
+    dropped.assign(todo.size() * (size_t)m, 0);
+    std::vector<c_float> As, bs;
+    std::vector<int> rs, fs, is;
+    while (!todo.empty()) {
+        // drop the first remaining constraint of every polyhedron still undecided
+        std::vector<int> next;
+        std::vector<unsigned char> ndrop;
+        for (size_t t = 0; t < todo.size(); t++) {
+            unsigned char* d = &dropped[t * m];
+            int first = 0;
+            while (first < m && d[first]) first++;
+            if (first >= m - 1) continue; // one constraint (or none) left: it keeps the value of its last probe
+            d[first] = 1;
+            next.push_back(todo[t]);
+            ndrop.insert(ndrop.end(), d, d + m);
+        }
+        todo.swap(next); dropped.swap(ndrop);
+        if (todo.empty()) break;
+        const size_t T = todo.size();
+        As.resize(T * mA * n); bs.resize(T * m); rs.resize(T * m); fs.resize(T * m); is.resize(T * m);
+        for (size_t t = 0; t < T; t++) {
+            if (mA) memcpy(&As[t * mA * n], A + (size_t)todo[t] * mA * n, mA * n * sizeof(c_float));
+            memcpy(&bs[t * m], b + (size_t)todo[t] * m, (size_t)m * sizeof(c_float));
+        }
+        rc = minrep_host_round(h, (int)T, n, m, ms, As.data(), bs.data(), dropped.data(), settings, rs.data(), fs.data(), is.data());
+        if (rc) return rc;
+        next.clear(); ndrop.clear();
+        for (size_t t = 0; t < T; t++) {
+            const size_t o = (size_t)todo[t] * m;
+            bool all = true;
+            for (int i = 0; i < m; i++) {
+                is_redundant[o + i] = rs[t * m + i];
+                if (!dropped[t * m + i]) { exitflag[o + i] = fs[t * m + i]; iter[o + i] = is[t * m + i]; }
+                all = all && rs[t * m + i] == 1;
+            }
+            if (all) { next.push_back(todo[t]); ndrop.insert(ndrop.end(), &dropped[t * m], &dropped[t * m] + m); }
+        }
+        todo.swap(next); dropped.swap(ndrop);
+    }
+    return 0;
+}
+
+// Drop-in for the reference's daqp_minrep (include/api.h:54, src/api.c:531-556): one polyhedron, its m LDPs in one launch.
+// Like the reference it has no way to report an error; on failure is_redundant is filled with -1 (the reference's
+// "not decided" marker, src/utils.c:811-812) and daqp_b200_last_error() says why.
+extern "C" void daqp_minrep(int* is_redundant, c_float* A, c_float* b, int n, int m, int ms) {
+    if (daqp_b200_minrep_batch(nullptr, 1, n, m, ms, A, b, nullptr, is_redundant, nullptr, nullptr) != 0)
+        for (int i = 0; i < m; i++) is_redundant[i] = -1;
 }
 
 // ---- persistent batch workspace: setup once, update(f, b) + solve many (reference setup_daqp / daqp_update_ldp /

@@ -85,6 +85,10 @@ struct LdpArgs {
     unsigned state_stride;    // bytes per problem: oarena rounded up to 16, plus 16 for {k, lsw, valid}
     int state_load, state_save;
     int ns_max;               // most soft constraints (sense & 8) any problem of the batch carries; cap = n + ns_max + 1
+    // shared-matrix mode (EXT instantiation only; daqp_b200_minrep_*): `grp` consecutive problems are LDPs over ONE
+    // constraint matrix -- Mt / Mr / Mt32 / scaling / Rinv / v are indexed by p / grp, bounds and sense stay per problem.
+    // The m LDPs of a polyhedron (reference daqp_minrep_work, src/utils.c:808-835) then stream the same matrix out of L2.
+    int grp;                  // 0 or 1: every problem owns its matrices
     int* exitflag;            // [P]
     int* iter;                // [P]
     int* ws_out;              // [P][cap] or nullptr : final working set (factor order)
@@ -182,6 +186,7 @@ struct Warp {
     const LdpArgs<T>& a; // kernel parameters (constant bank): sizes, layout offsets, array bases
     T* S;                // this warp's shared memory
     int lane, p;         // lane id, problem index
+    int pm;              // EXT: index of the problem's matrix set (p / grp in shared-matrix mode, else p)
     int k, reuse, sing;  // warp-uniform solver state (n_active, reuse_ind, sing_ind)
     int lsw;             // which of the two lambda buffers currently is `lam` (the reference swaps pointers)
     T fval, soft_slack;
@@ -206,11 +211,12 @@ struct Warp {
     __device__ __forceinline__ int* WS() const { return reinterpret_cast<int*>(S) + a.oWS; }
     __device__ __forceinline__ int* cnt() const { return reinterpret_cast<int*>(S) + a.ocnt; }
     __device__ __forceinline__ unsigned char* sense() const { return reinterpret_cast<unsigned char*>(S) + a.osense; }
-    __device__ __forceinline__ const char* Mt() const { return reinterpret_cast<const char*>(a.Mt) + (size_t)p * a.sMt; }
-    __device__ __forceinline__ const char* Mr() const { return reinterpret_cast<const char*>(a.Mr) + (size_t)p * a.sMr; }
+    __device__ __forceinline__ int pmat() const { if constexpr (EXT) return pm; else return p; }
+    __device__ __forceinline__ const char* Mt() const { return reinterpret_cast<const char*>(a.Mt) + (size_t)pmat() * a.sMt; }
+    __device__ __forceinline__ const char* Mr() const { return reinterpret_cast<const char*>(a.Mr) + (size_t)pmat() * a.sMr; }
     __device__ __forceinline__ const T* du() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.dupper) + (size_t)p * a.sVec); }
     __device__ __forceinline__ const T* dl() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.dlower) + (size_t)p * a.sVec); }
-    __device__ __forceinline__ const T* sc() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.scaling) + (size_t)p * a.sVec); }
+    __device__ __forceinline__ const T* sc() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.scaling) + (size_t)pmat() * a.sVec); }
     __device__ __forceinline__ void count(int which) { if (lane == 0) cnt()[which]++; }
 
     __device__ __forceinline__ void reset() { sing = EMPTY_IND; k = 0; reuse = 0; } // daqp.c:142-146
@@ -787,7 +793,7 @@ struct Warp {
             }
         }
         const unsigned slab = (unsigned)a.m * 16u; // bytes of one quad of columns
-        const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 + 16 * lane;
+        const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)pmat() * a.sMt32 + 16 * lane;
         const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane;
         const int nq = (a.n + 3) >> 2;
         // Ring slots are static (the quad loop is unrolled QRING times) and the loop is rotated: the trip that consumes
@@ -1136,6 +1142,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
         pq = uni(pq); // lanes other than 0 hold 0 and queue indices are non-negative
         if (pq >= a.P) break;
         w.p = pq;
+        if constexpr (EXT) w.pm = a.grp > 1 ? pq / a.grp : pq;
         const int sflag = uni(a.setup_flag[pq]); // loaded values are divergent in ptxas' eyes until proven otherwise
         if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) {
             if (a.nact_out && lane == 0) a.nact_out[pq] = 0;
@@ -1206,13 +1213,13 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             if (lane == 0) { a.exitflag[p] = exitflag; a.iter[p] = 0; }
         } else {
             // ---- a15/a16: ldp2qp_solution (daqp.c:111-139) + daqp_extract_result (api.c:455-495)
-            const T* vv = a.v ? reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.v) + (size_t)p * a.sv) : nullptr;
+            const T* vv = a.v ? reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.v) + (size_t)w.pmat() * a.sv) : nullptr;
             T* xo = a.x + (size_t)p * a.n;
             T* up = w.u();
             T vnorm = 0;
             if (vv) { LANE_LOOP(i, 0, a.n) { const T t = vv[i]; vnorm += t * t; } vnorm = warp_sum(vnorm); }
             if (exitflag > 0) {
-                const T* Ri = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.Rinv) + (size_t)p * a.sRinv);
+                const T* Ri = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.Rinv) + (size_t)w.pmat() * a.sRinv);
                 if (vv) LANE_LOOP(i, 0, a.n) up[i] -= vv[i];
                 __syncwarp();
                 for (int i = 0; i < a.n; i++) { // x_i = sum_{j>=i} Rinv[i][j] (u-v)_j ; rows are independent

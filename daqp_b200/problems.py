@@ -218,3 +218,23 @@ def soften(b, frac: float, shift: float, seed: int):
     b.bupper[pick] += d[pick]
     b.blower[pick] += d[pick]
     return b
+
+
+def generate_polyhedra(P: int, n: int, m: int, ms: int = 0, seed: int = 0, redundant_frac: float = 0.4):
+    """P random bounded-looking polyhedra {x : [I(ms); A] x <= b} for the minimal-representation path
+    (``daqp.minrep``, reference interfaces/daqp-python/daqp.pyx:636-652). Every row is a half-space that contains a ball
+    around a random centre c: b_i = a_i'c + |a_i| r_i with r_i in [0.5, 1.5] for the "tight" rows and r_i in [4, 9] for a
+    ``redundant_frac`` share of pushed-out rows (most of which end up redundant once enough tight rows exist; whether a
+    given row is redundant is for the solver to say). Rows are NOT normalised: |a_i| spans [0.2, 5]. The first ms
+    constraints are upper bounds on x_0..x_{ms-1} (unit rows). Returns (A[P, m-ms, n], b[P, m])."""
+    rng = np.random.default_rng(seed)
+    mA = m - ms
+    A = rng.standard_normal((P, mA, n))
+    A *= np.exp(rng.uniform(np.log(0.2), np.log(5.0), (P, mA, 1))) / np.linalg.norm(A, axis=2, keepdims=True)
+    c = rng.standard_normal((P, n))
+    pushed = rng.random((P, m)) < redundant_frac
+    r = np.where(pushed, rng.uniform(4.0, 9.0, (P, m)), rng.uniform(0.5, 1.5, (P, m)))
+    b = np.empty((P, m))
+    b[:, :ms] = c[:, :ms] + r[:, :ms]
+    b[:, ms:] = np.einsum("pmn,pn->pm", A, c) + np.linalg.norm(A, axis=2) * r[:, ms:]
+    return np.ascontiguousarray(A), np.ascontiguousarray(b)

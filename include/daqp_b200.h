@@ -10,6 +10,8 @@
  *   daqp_quadprog_batch()    NEW: N independent daqp_quadprog() calls in one launch (the reference has no batch API)
  *   daqp_b200_solve_packed() NEW: same for a homogeneous batch in strided host arrays (no per-problem pointers)
  *   daqp_b200_solve_device() NEW: same with device-resident arrays, asynchronous on a caller stream
+ *   daqp_minrep()            replaces reference include/api.h:54 / src/api.c:531-556 (its m LDPs run concurrently)
+ *   daqp_b200_minrep_batch() NEW: P polyhedra per call
  *
  * Exit flags are the reference's (include/constants.h:42-51). Problems outside the hot-path scope (binary
  * constraints, hierarchies, AVI, H == NULL, singular H that needs the proximal-point driver) return
@@ -192,6 +194,26 @@ int daqp_b200_workspace_update_device(DAQPB200Workspace* w, const c_float* df, c
 int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, c_float* dx, c_float* dlam, c_float* dfval,
                                      int* dexitflag, int* diter, void* stream);
 void daqp_b200_workspace_free(DAQPB200Workspace* w);
+
+/* ---- minimal representation of polyhedra (batched LDP consumer) ---------------------------------------------
+ * reference include/api.h:54 (src/api.c:531-556, src/utils.c:808-835): is_redundant[i] = 1 iff constraint i of
+ * {x : [I(ms); A] x <= b} is redundant (the LDP with row i turned into an active equality is infeasible), else 0.
+ * Drop-in signature; the m LDPs run concurrently on the GPU instead of one after the other. On a CUDA-side failure
+ * every entry is set to -1. */
+void daqp_minrep(int* is_redundant, c_float* A, c_float* b, int n, int m, int ms);
+
+/* NEW: P polyhedra of one shape in one call -- A[P][m-ms][n], b[P][m] -> is_redundant[P][m]; all P*m LDPs are solved
+ * concurrently (one warp each), the m LDPs of a polyhedron sharing one device copy of its matrix. exitflag / iter
+ * ([P][m], may be NULL) return the exit flag and iteration count of every LDP (what daqp_ldp returns for it in the
+ * reference when no earlier constraint was found redundant). HOST arrays; blocks until the results are in place.
+ * An EMPTY polyhedron (every probe infeasible) is answered like the reference answers it -- constraints dropped from the
+ * front until the rest is non-empty -- by re-running it with those constraints taken out. */
+int daqp_b200_minrep_batch(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* A, const c_float* b,
+                           const DAQPSettings* settings, int* is_redundant, int* exitflag, int* iter);
+/* Same with DEVICE arrays, asynchronous on `stream` (a cudaStream_t; NULL = the engine's own stream). One round, no
+ * host synchronisation: an empty polyhedron comes back with every entry 1 (the caller can see that and decide). */
+int daqp_b200_minrep_device(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA, const c_float* db,
+                            const DAQPSettings* settings, int* dis_redundant, int* dexitflag, int* diter, void* stream);
 
 /* Device-time accounting of the engine since the last reset (CUDA events on the launching stream). */
 typedef struct {

@@ -762,6 +762,87 @@ setup_failed: /* api.c:69-72: exit flag only, res->x untouched */
     ldp_free(w);
 }
 
+/* ---- minimal representation: daqp_minrep (api.c:531-556) + daqp_minrep_work (utils.c:808-835) ------------- */
+/* The reference wraps the polyhedron in a bare workspace: M = A as given (no normalisation, scaling == NULL so the
+ * violation threshold is -primal_tol itself, auxiliary.c:110,136), Rinv == NULL (simple bounds are unit rows),
+ * v == NULL, dlower = -inf, sense = 0, default settings. scaling == NULL is restated as scaling = 1 (ep * 1 == ep). */
+static void minrep_open(Ldp *w, OrcSettings *st, const real *A, const real *b, int n, int m, int ms) {
+    const int mA = m - ms;
+    memset(w, 0, sizeof(*w));
+    orc_default_settings(st);
+    w->n = n; w->m = m; w->ms = ms; w->cap = n + 1; w->st = st;
+    w->lam = malloc(sizeof(real) * w->cap); w->lam_star = malloc(sizeof(real) * w->cap);
+    w->D = malloc(sizeof(real) * w->cap); w->xl = malloc(sizeof(real) * w->cap); w->zl = malloc(sizeof(real) * w->cap);
+    w->L = malloc(sizeof(real) * (size_t)w->cap * w->cap); w->WS = malloc(sizeof(int) * w->cap);
+    w->pstack_id = malloc(sizeof(int) * w->cap); w->pstack_lam = malloc(sizeof(real) * w->cap);
+    w->u = calloc(n, sizeof(real)); w->xunc = malloc(sizeof(real) * n);
+    w->scaling = malloc(sizeof(real) * m);
+    w->M = malloc(sizeof(real) * (size_t)(mA > 0 ? mA : 1) * n);
+    w->Mu = malloc(sizeof(real) * (mA > 0 ? mA : 1));
+    w->dupper = malloc(sizeof(real) * m); w->dlower = malloc(sizeof(real) * m);
+    w->sense = malloc(sizeof(int) * m);
+    memcpy(w->M, A, sizeof(real) * (size_t)mA * n);
+    for (int i = 0; i < m; i++) { w->scaling[i] = 1; w->dupper[i] = b[i]; w->dlower[i] = -ORC_INF; w->sense[i] = 0; }
+    reset_ws(w);
+}
+
+/* One pass of the loop body of daqp_minrep_work (utils.c:816-822): constraint i as an active equality, then daqp_ldp */
+static int minrep_probe(Ldp *w, int i) {
+    reset_ws(w);
+    w->sense[i] = B_ACTIVE + B_IMMUTABLE;
+    add_constraint(w, i, (real)1);
+    return ldp_solve(w);
+}
+
+/* auxiliary.c:482-488 */
+static void deactivate_all(Ldp *w) {
+    for (int j = 0; j < w->k; j++)
+        if (!(w->sense[w->WS[j]] & B_IMMUTABLE)) w->sense[w->WS[j]] &= ~B_ACTIVE;
+}
+
+/* Reference order: one constraint after the other; a redundant constraint stays IMMUTABLE (ignored from then on), a
+ * constraint active at an optimum is marked non-redundant and never probed (utils.c:808-835). */
+void orc_minrep(int *is_redundant, const orc_real *A, const orc_real *b, int n, int m, int ms) {
+    Ldp W, *w = &W;
+    OrcSettings st;
+    if (m <= 0) return;
+    minrep_open(w, &st, A, b, n, m, ms);
+    for (int i = 0; i < m; i++) is_redundant[i] = -1;
+    for (int i = 0; i < m; i++) {
+        if (is_redundant[i] != -1 || (w->sense[i] & B_IMMUTABLE)) continue;
+        int flag = minrep_probe(w, i);
+        if (flag == EXIT_INFEASIBLE) {
+            is_redundant[i] = 1;
+            w->sense[i] &= ~B_ACTIVE;
+        } else {
+            is_redundant[i] = 0;
+            w->sense[i] &= ~B_IMMUTABLE;
+            if (flag == EXIT_OPTIMAL)
+                for (int j = 0; j < w->k; j++) is_redundant[w->WS[j]] = 0;
+        }
+        deactivate_all(w);
+    }
+    ldp_free(w);
+}
+
+/* The same m probes, each against the FULL polyhedron (no constraint dropped, none skipped): what the batched GPU
+ * path computes. Returns exit flag and iteration count of every LDP; is_redundant[i] = (flag == INFEASIBLE). */
+void orc_minrep_independent(int *is_redundant, int *exitflag, int *iter, const orc_real *A, const orc_real *b,
+                            int n, int m, int ms) {
+    Ldp W, *w = &W;
+    OrcSettings st;
+    if (m <= 0) return;
+    minrep_open(w, &st, A, b, n, m, ms);
+    for (int i = 0; i < m; i++) {
+        for (int j = 0; j < m; j++) w->sense[j] = 0;
+        int flag = minrep_probe(w, i);
+        is_redundant[i] = flag == EXIT_INFEASIBLE ? 1 : 0;
+        if (exitflag) exitflag[i] = flag;
+        if (iter) iter[i] = w->iterations;
+    }
+    ldp_free(w);
+}
+
 typedef struct {
     int N, n, m, ms;
     const orc_real *H, *f, *A, *bupper, *blower;

@@ -83,6 +83,14 @@ double orc_solve_packed(int N, int n, int m, int ms,
                         int *trace_counts /* [N][4] scan,add,remove,csp or NULL */,
                         int nthreads);
 
+/* daqp_minrep (api.c:531-556, utils.c:808-835): is_redundant[m] for {x : [I(ms); A] x <= b}, constraints probed one
+ * after the other exactly like the reference. */
+void orc_minrep(int *is_redundant, const orc_real *A, const orc_real *b, int n, int m, int ms);
+/* The same probes run independently of each other (nothing dropped, nothing skipped): the batched GPU semantics.
+ * exitflag / iter may be NULL. */
+void orc_minrep_independent(int *is_redundant, int *exitflag, int *iter, const orc_real *A, const orc_real *b,
+                            int n, int m, int ms);
+
 #ifdef __cplusplus
 }
 #endif

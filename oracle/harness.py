@@ -301,3 +301,43 @@ class OracleLib:
             _ptr(x, real), _ptr(lam, real), _ptr(fval, real), flag.ctypes.data_as(C.POINTER(C.c_int)),
             it.ctypes.data_as(C.POINTER(C.c_int)), counts.ctypes.data_as(C.POINTER(C.c_int)), nthreads)
         return Solution(x, lam, fval, flag, it, None, None, counts, secs)
+
+    # ---- minimal representation (oracle restatement of daqp_minrep, fp64 only) --------------------------------
+    def minrep(self, A, b) -> np.ndarray:
+        """Reference order (one probe after the other): orc_minrep. A[m-ms, n], b[m]."""
+        assert not self.single
+        A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+        mA, n = A.shape
+        m = b.shape[0]
+        red = np.zeros(m, np.int32)
+        self.lib.orc_minrep.restype = None
+        self.lib.orc_minrep(red.ctypes.data_as(C.POINTER(C.c_int)), _ptr(A, self.real), _ptr(b, self.real),
+                            C.c_int(n), C.c_int(m), C.c_int(m - mA))
+        return red
+
+    def minrep_independent(self, A, b):
+        """Every probe against the full polyhedron (the batched semantics): (is_redundant, exitflag, iter)."""
+        assert not self.single
+        A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+        mA, n = A.shape
+        m = b.shape[0]
+        red = np.zeros(m, np.int32); flag = np.zeros(m, np.int32); it = np.zeros(m, np.int32)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self.lib.orc_minrep_independent.restype = None
+        self.lib.orc_minrep_independent(ip(red), ip(flag), ip(it), _ptr(A, self.real), _ptr(b, self.real),
+                                        C.c_int(n), C.c_int(m), C.c_int(m - mA))
+        return red, flag, it
+
+
+def ref_minrep(A, b, name: str = "libdaqp_ref.so") -> np.ndarray:
+    """The reference's own daqp_minrep (include/api.h:54) from oracle/_ref. A[m-ms, n], b[m]."""
+    lib = C.CDLL(os.path.join(REF_DIR, name))
+    lib.daqp_minrep.restype = None
+    A = np.ascontiguousarray(A, np.float64).copy(); b = np.ascontiguousarray(b, np.float64).copy()
+    mA, n = A.shape
+    m = b.shape[0]
+    red = np.zeros(m, np.int32)
+    dp = C.POINTER(C.c_double)
+    lib.daqp_minrep(red.ctypes.data_as(C.POINTER(C.c_int)), A.ctypes.data_as(dp), b.ctypes.data_as(dp),
+                    C.c_int(n), C.c_int(m), C.c_int(m - mA))
+    return red

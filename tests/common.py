@@ -18,7 +18,18 @@ X_TOL, F_TOL, L_TOL = 1e-9, 1e-9, 1e-7
 def golden_names():
     """Single-solve fixtures (the wsseq_* files hold workspace sequences: see test_workspace_sequence_matches_reference)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith("wsseq_")]
+    return [n for n in names if not n.startswith(("wsseq_", "minrep_"))]
+
+
+def minrep_golden_names():
+    """Polyhedra with the reference's own daqp_minrep output (tests/golden/make_golden_minrep.py)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "minrep_n*.npz")))
+    return names
+
+
+def load_minrep_special():
+    d = np.load(os.path.join(GOLDEN_DIR, "minrep_special.npz"))
+    return {str(k): (d[str(k) + "_A"], d[str(k) + "_b"], d[str(k) + "_red"]) for k in d["names"]}
 
 
 def load_golden(name):
