@@ -279,6 +279,7 @@ def main():
     # ---- end to end through the host C ABI (pinned host buffers, copies inside the timed region)
     e2e = None
     wsp = None
+    shw = None
     if not args.no_e2e:
         pin = lambda x: x.cpu().pin_memory()
         h = {k: pin(t[k]) for k in ("H", "f", "A", "bupper", "blower")}
@@ -350,6 +351,44 @@ def main():
                 mdl.close()
             except Exception as ex:  # the leg is informative: never lose the headline line over it
                 wsp = {"error": repr(ex)[:200]}
+        # ---- shared workspace (one controller, many states): G matrix sets, P / G problems per set that differ only in
+        # f and the bounds; every step is a COLD solve of all P problems with f / bounds copied from pinned host memory.
+        shw = None
+        if rank == 0 and world == 1 and not args.no_workspace:
+            try:
+                rng = np.random.default_rng(11)
+                G = 16
+                K = P // G
+                NS = G * K
+                mdl = daqp_b200.BatchModel(eng).setup_shared(hn["H"][:G], hn["A"][:G], K, ms=ms, m=m)
+
+                def draw():
+                    sh = 0.05 * rng.standard_normal((NS, m))
+                    arrs = (np.repeat(hn["f"][:G], K, axis=0) * (1 + 0.3 * rng.standard_normal((NS, n))),
+                            np.repeat(hn["bupper"][:G], K, axis=0) + sh, np.repeat(hn["blower"][:G], K, axis=0) + sh)
+                    return tuple(torch.from_numpy(a).pin_memory().numpy() for a in arrs)
+
+                draws = [draw() for _ in range(3)]
+                res_s = daqp_b200.BatchResult(x=res.x[:NS], lam=res.lam[:NS], fval=res.fval[:NS],
+                                              exitflag=res.exitflag[:NS], iter=res.iter[:NS])
+                mdl.update(*draws[0]); mdl.solve(warm=False, out=res_s)  # warm-up step
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                its, opt = [], []
+                for fk, buk, blk in draws[1:]:
+                    mdl.update(fk, buk, blk)
+                    rk = mdl.solve(warm=False, out=res_s)
+                    its.append(float(rk.iter.mean())); opt.append(float((rk.exitflag == 1).mean()))
+                dts = (time.perf_counter() - t0) / (len(draws) - 1)
+                shw = {"value": NS / dts, "unit": "QP/s per cold step (f,b from host + solve + results to host)",
+                       "ms_per_step": 1e3 * dts, "matrix_sets": G, "problems_per_set": K,
+                       "h2d_bytes_per_step": sum(a.nbytes for a in draws[0]), "mean_iterations": sum(its) / len(its),
+                       "optimal_fraction": sum(opt) / len(opt),
+                       "perturbation": "f * (1 + 0.3 N(0,1)), bounds + 0.05 N(0,1) around the set's base problem",
+                       "api": "daqp_b200_workspace_setup_shared, then daqp_b200_workspace_update + _solve(warm=0)"}
+                mdl.close()
+            except Exception as ex:
+                shw = {"error": repr(ex)[:200]}
         del h, hn
 
     # ---- the reference CPU solver on a bounded sample of the SAME problems (rank 0, N=1 only)
@@ -380,6 +419,7 @@ def main():
                 "config": config_dict(args, P), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": st["setup_launches"] + st["solve_launches"], "clocks": clocks,
                 "workspace": wsp if not args.no_e2e else None,
+                "shared_workspace": shw if not args.no_e2e else None,
                 "parity": {"max_abs_x_err_vs_constructed_optimum": err, "all_optimal": True,
                            "active_set_differs_from_construction": as_mismatch}}
         print(json.dumps(line), flush=True)

@@ -385,6 +385,36 @@ class BatchModel:
         self.shape = (N, n, m, ms, ns)
         return self
 
+    def setup_shared(self, H, A, K: int, sense=None, ms: int | None = None, m: int | None = None, **settings):
+        """Shared workspace (``daqp_b200_workspace_setup_shared``): G matrix sets H[G,n,n], A[G,m-ms,n] (sense[G,m] or
+        None), K problems per set -- the parametric / MPC case of ONE controller evaluated for many states, where only
+        f and the bounds differ. The QP -> LDP transform runs once per set and the K problems of a set stream the same
+        matrices out of L2. Problem p = g * K + k; ``update(f[G*K,n], bupper[G*K,m], blower[G*K,m])`` must give all
+        three arrays before the first ``solve``. Every problem gets the result of the reference's
+        ``setup_daqp(H_g, f_p, A_g, b_p)`` + ``daqp_solve``. ``m`` is only needed when A is empty (m == ms)."""
+        L = lib()
+        L.daqp_b200_workspace_setup_shared.restype = C.c_int
+        L.daqp_b200_workspace_update.restype = C.c_int
+        L.daqp_b200_workspace_solve.restype = C.c_int
+        L.daqp_b200_workspace_free.restype = None
+        self.close()
+        H = _f64(H); A = _f64(A)
+        G, n = H.shape[0], H.shape[1]
+        mA = A.shape[1] if A is not None and A.size else 0
+        if sense is not None:
+            sense = np.ascontiguousarray(sense, dtype=np.intc)
+            m = sense.shape[1]
+        if m is None:
+            m = mA + (0 if ms is None else ms)
+        ms = m - mA if ms is None else ms
+        ns = 0 if sense is None else int(((sense & SOFT) != 0).sum(axis=1).max(initial=0))
+        st = default_settings(**settings)
+        h = self._eng._h if self._eng is not None else None
+        _check(L.daqp_b200_workspace_setup_shared(h, G, int(K), n, m, ms, _p(H), _p(A), _p(sense, _ip), C.byref(st),
+                                                  C.byref(self._w)))
+        self.shape = (G * int(K), n, m, ms, ns)
+        return self
+
     def update(self, f=None, bupper=None, blower=None):
         f = _f64(f); bupper = _f64(bupper); blower = _f64(blower)
         _check(lib().daqp_b200_workspace_update(self._w, _p(f), _p(bupper), _p(blower)))

@@ -239,6 +239,7 @@ struct Persist {
     unsigned state_stride = 0;
     int phase = 0;      // 1 = QP -> LDP only (no shortcut), 2 = solve only
     int state_load = 0; // phase 2: continue from the saved factor / working set
+    int grp = 0;        // shared workspace: problems per matrix set (the matrix arrays hold N / grp sets); 0 = own matrices
 };
 
 // Device-resident batch: the core of every entry point.
@@ -355,7 +356,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
         la.soft_slack = sa.soft_slack; la.ns_max = ns_max;
         la.tune = tune;
-        if (ps) { la.state = ps->state; la.state_stride = ps->state_stride; la.state_load = ps->state_load; la.state_save = 1; }
+        if (ps) { la.state = ps->state; la.state_stride = ps->state_stride; la.state_load = ps->state_load; la.state_save = 1; la.grp = ps->grp; }
         if (!ps || ps->phase == 2) {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
             const size_t smem = smem_solve_w * w_solve;
@@ -750,6 +751,7 @@ struct DAQPB200Workspace {
     DAQPB200Handle* h = nullptr;
     int N = 0, n = 0, m = 0, ms = 0, ldm = 0, ns_max = 0, cap = 0;
     bool has_f = false, has_sense = false;
+    bool need_data = false; // shared workspace: f and both bounds have not been given yet
     DAQPSettings settings{};
     Persist<c_float> ps;
     std::vector<void*> owned; // every device allocation of the workspace
@@ -774,21 +776,27 @@ extern "C" void daqp_b200_workspace_free(DAQPB200Workspace* w) {
     delete w;
 }
 
-extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* H,
-                                         const c_float* f, const c_float* A, const c_float* bupper,
-                                         const c_float* blower, const int* sense, const DAQPSettings* settings,
-                                         DAQPB200Workspace** out) {
+// K == 0: N problems, each with its own H / A / f / bounds (the plain workspace). K > 0: N matrix sets (H, A, sense), K
+// problems per set whose f / bounds arrive with the first update (shared workspace).
+static int workspace_setup_impl(DAQPB200Handle* h, int N, int K, int n, int m, int ms, const c_float* H,
+                                const c_float* f, const c_float* A, const c_float* bupper,
+                                const c_float* blower, const int* sense, const DAQPSettings* settings,
+                                DAQPB200Workspace** out) {
     typedef c_float T;
     if (!h) { int rc = default_handle(&h); if (rc) return rc; }
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
-    if (N <= 0 || n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
+    if (N <= 0 || K < 0 || n < 1 || m < ms || ms < 0 || ms > n || (K > 0 && (long long)N * K > INT_MAX / 2)) {
+        g_last_error = "daqp_b200: invalid problem dimensions"; return -2;
+    }
+    const int G = N;           // matrix sets
+    if (K > 0) N = G * K;      // problems
     DAQPB200Workspace* w = new DAQPB200Workspace();
     w->h = h; w->N = N; w->n = n; w->m = m; w->ms = ms; w->ldm = round_up(std::max(m, 1), 4);
-    w->has_f = f != nullptr; w->has_sense = sense != nullptr;
+    w->has_f = K > 0 || f != nullptr; w->has_sense = sense != nullptr; w->need_data = K > 0;
     if (settings) w->settings = *settings; else daqp_default_settings(&w->settings);
     if (sense)
-        for (int p = 0; p < N; p++) {
+        for (int p = 0; p < G; p++) {
             int c = 0;
             for (int i = 0; i < m; i++) c += (sense[(size_t)p * m + i] & DAQP_SOFT) ? 1 : 0;
             w->ns_max = std::max(w->ns_max, c);
@@ -801,16 +809,18 @@ extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m,
     ldp_layout<T>(la);
     Persist<T>& ps = w->ps;
     ps.state_stride = (unsigned)round_up(la.oarena, 16) + 16;
+    ps.grp = K;
     int rc = 0;
     T *dH = nullptr, *dA = nullptr;
 #define WS_TRY(call) do { rc = (call); if (rc) { daqp_b200_workspace_free(w); return rc; } } while (0)
-    WS_TRY(ws_alloc(w, &ps.Mt, (size_t)N * n * ldm));
-    WS_TRY(ws_alloc(w, &ps.Mr, (size_t)N * m * ldn));
-    if (m <= 256) WS_TRY(ws_alloc(w, &ps.Mt32, (size_t)N * ((n + 3) / 4) * m * 4));
+    // the matrix arrays hold G sets, everything else N problems
+    WS_TRY(ws_alloc(w, &ps.Mt, (size_t)G * n * ldm));
+    WS_TRY(ws_alloc(w, &ps.Mr, (size_t)G * m * ldn));
+    if (m <= 256) WS_TRY(ws_alloc(w, &ps.Mt32, (size_t)G * ((n + 3) / 4) * m * 4));
     WS_TRY(ws_alloc(w, &ps.du, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.dl, (size_t)N * ldm));
-    WS_TRY(ws_alloc(w, &ps.sc, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.Ri, (size_t)N * n * (n + 1) / 2));
+    WS_TRY(ws_alloc(w, &ps.sc, (size_t)G * ldm)); WS_TRY(ws_alloc(w, &ps.Ri, (size_t)G * n * (n + 1) / 2));
     WS_TRY(ws_alloc(w, &ps.vv, (size_t)N * n)); WS_TRY(ws_alloc(w, &ps.sense8, (size_t)N * ldm));
-    WS_TRY(ws_alloc(w, &ps.sense_static, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.sflag, (size_t)N));
+    WS_TRY(ws_alloc(w, &ps.sense_static, (size_t)G * ldm)); WS_TRY(ws_alloc(w, &ps.sflag, (size_t)N));
     WS_TRY(ws_alloc(w, &ps.state, (size_t)N * ps.state_stride));
     WS_TRY(ws_alloc(w, &w->d_f, (size_t)N * n)); WS_TRY(ws_alloc(w, &w->d_bu, (size_t)N * m)); WS_TRY(ws_alloc(w, &w->d_bl, (size_t)N * m));
     WS_TRY(ws_alloc(w, &w->d_x, (size_t)N * n)); WS_TRY(ws_alloc(w, &w->d_lam, (size_t)N * m));
@@ -818,25 +828,63 @@ extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m,
     WS_TRY(ws_alloc(w, &w->d_flag, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_iter, (size_t)N));
     WS_TRY(ws_alloc(w, &w->d_nact, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_ws, (size_t)N * w->cap));
     WS_TRY(ws_alloc(w, &w->d_counts, (size_t)N * 4)); WS_TRY(ws_alloc(w, &w->d_so, (size_t)N * ldm));
-    if (sense) WS_TRY(ws_alloc(w, &w->d_sense, (size_t)N * m));
-    WS_TRY(ws_alloc(w, &dH, (size_t)N * n * n)); WS_TRY(ws_alloc(w, &dA, (size_t)N * std::max(mA, 1) * n));
+    if (sense) WS_TRY(ws_alloc(w, &w->d_sense, (size_t)G * m));
+    WS_TRY(ws_alloc(w, &dH, (size_t)G * n * n)); WS_TRY(ws_alloc(w, &dA, (size_t)G * std::max(mA, 1) * n));
     cudaStream_t st = h->compute;
 #define WS_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { daqp_b200_workspace_free(w); return fail(#call, e_, __LINE__); } } while (0)
     WS_CK(cudaMemsetAsync(ps.state, 0, (size_t)N * ps.state_stride, st));
     WS_CK(cudaMemsetAsync(w->d_fval, 0, (size_t)N * sizeof(T), st));
     WS_CK(cudaMemsetAsync(w->d_flag, 0, (size_t)N * sizeof(int), st));
     WS_CK(cudaMemsetAsync(w->d_iter, 0, (size_t)N * sizeof(int), st));
-    WS_CK(cudaMemcpyAsync(dH, H, (size_t)N * n * n * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (mA > 0) WS_CK(cudaMemcpyAsync(dA, A, (size_t)N * mA * n * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (f) WS_CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (m > 0) {
-        WS_CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
-        WS_CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
-        if (sense) WS_CK(cudaMemcpyAsync(w->d_sense, sense, (size_t)N * m * sizeof(int), cudaMemcpyHostToDevice, st));
+    WS_CK(cudaMemcpyAsync(dH, H, (size_t)G * n * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (mA > 0) WS_CK(cudaMemcpyAsync(dA, A, (size_t)G * mA * n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (m > 0 && sense) WS_CK(cudaMemcpyAsync(w->d_sense, sense, (size_t)G * m * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (K == 0) {
+        if (f) WS_CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (m > 0) {
+            WS_CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+            WS_CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), cudaMemcpyHostToDevice, st));
+        }
+        ps.phase = 1;
+        WS_TRY(solve_device_impl<T>(h, N, n, m, ms, dH, f ? w->d_f : nullptr, dA, w->d_bu, w->d_bl, w->d_sense, &w->settings,
+                                    w->d_x, w->d_lam, w->d_fval, w->d_flag, w->d_iter, nullptr, st, w->ns_max, &ps));
+    } else {
+        // Shared workspace: the QP -> LDP transform runs once per matrix set, with open bounds and no linear term; what it
+        // writes per PROBLEM (d, v, sense, flags) goes to scratch -- the first update produces the real ones. Only the flags
+        // the Hessian raises (non-convex, singular) are kept: they hold for every problem of the set.
+        T *tbu = nullptr, *tbl = nullptr, *tdu = nullptr, *tdl = nullptr, *tv = nullptr, *tx = nullptr, *tlam = nullptr, *tfv = nullptr;
+        unsigned char* tse = nullptr;
+        int *tsf = nullptr, *tfl = nullptr, *tit = nullptr;
+        WS_TRY(ws_alloc(w, &tbu, (size_t)G * m)); WS_TRY(ws_alloc(w, &tbl, (size_t)G * m));
+        WS_TRY(ws_alloc(w, &tdu, (size_t)G * ldm)); WS_TRY(ws_alloc(w, &tdl, (size_t)G * ldm));
+        WS_TRY(ws_alloc(w, &tv, (size_t)G * n)); WS_TRY(ws_alloc(w, &tx, (size_t)G * n));
+        WS_TRY(ws_alloc(w, &tlam, (size_t)G * m)); WS_TRY(ws_alloc(w, &tfv, (size_t)G));
+        WS_TRY(ws_alloc(w, &tse, (size_t)G * ldm)); WS_TRY(ws_alloc(w, &tsf, (size_t)G));
+        WS_TRY(ws_alloc(w, &tfl, (size_t)G)); WS_TRY(ws_alloc(w, &tit, (size_t)G));
+        std::vector<T> open_u((size_t)G * std::max(m, 1), (T)DAQP_INF), open_l((size_t)G * std::max(m, 1), (T)-DAQP_INF);
+        if (m > 0) {
+            WS_CK(cudaMemcpyAsync(tbu, open_u.data(), (size_t)G * m * sizeof(T), cudaMemcpyHostToDevice, st));
+            WS_CK(cudaMemcpyAsync(tbl, open_l.data(), (size_t)G * m * sizeof(T), cudaMemcpyHostToDevice, st));
+        }
+        WS_CK(cudaMemsetAsync(tfl, 0, (size_t)G * sizeof(int), st));
+        Persist<T> p1 = ps;
+        p1.du = tdu; p1.dl = tdl; p1.vv = tv; p1.sense8 = tse; p1.sflag = tsf; p1.grp = 0; p1.phase = 1;
+        WS_TRY(solve_device_impl<T>(h, G, n, m, ms, dH, nullptr, dA, tbu, tbl, w->d_sense, &w->settings, tx, tlam, tfv, tfl,
+                                    tit, nullptr, st, w->ns_max, &p1));
+        std::vector<int> gflag(G), pflag((size_t)N);
+        WS_CK(cudaMemcpyAsync(gflag.data(), tfl, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, st));
+        WS_CK(cudaStreamSynchronize(st));
+        for (int g = 0; g < G; g++)
+            for (int k = 0; k < K; k++)
+                pflag[(size_t)g * K + k] = (gflag[g] == DAQP_EXIT_NONCONVEX || gflag[g] == DAQP_EXIT_UNSUPPORTED) ? gflag[g] : 0;
+        WS_CK(cudaMemcpyAsync(w->d_flag, pflag.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st));
+        for (void* t : {(void*)tbu, (void*)tbl, (void*)tdu, (void*)tdl, (void*)tv, (void*)tx, (void*)tlam, (void*)tfv,
+                        (void*)tse, (void*)tsf, (void*)tfl, (void*)tit}) {
+            WS_CK(cudaStreamSynchronize(st));
+            cudaFree(t);
+            w->owned.erase(std::remove(w->owned.begin(), w->owned.end(), t), w->owned.end());
+        }
     }
-    ps.phase = 1;
-    WS_TRY(solve_device_impl<T>(h, N, n, m, ms, dH, f ? w->d_f : nullptr, dA, w->d_bu, w->d_bl, w->d_sense, &w->settings,
-                                w->d_x, w->d_lam, w->d_fval, w->d_flag, w->d_iter, nullptr, st, w->ns_max, &ps));
     WS_CK(cudaStreamSynchronize(st));
     // H and A are not needed again: the LDP is what the workspace keeps
     cudaFree(dH); cudaFree(dA);
@@ -848,6 +896,20 @@ extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m,
     return 0;
 }
 
+extern "C" int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* H,
+                                         const c_float* f, const c_float* A, const c_float* bupper,
+                                         const c_float* blower, const int* sense, const DAQPSettings* settings,
+                                         DAQPB200Workspace** out) {
+    return workspace_setup_impl(h, N, 0, n, m, ms, H, f, A, bupper, blower, sense, settings, out);
+}
+
+extern "C" int daqp_b200_workspace_setup_shared(DAQPB200Handle* h, int G, int K, int n, int m, int ms, const c_float* H,
+                                                const c_float* A, const int* sense, const DAQPSettings* settings,
+                                                DAQPB200Workspace** out) {
+    if (K < 1) { g_last_error = "daqp_b200: a shared workspace needs K >= 1 problems per matrix set"; return -2; }
+    return workspace_setup_impl(h, G, K, n, m, ms, H, nullptr, A, nullptr, nullptr, sense, settings, out);
+}
+
 // kind: host arrays are staged with cudaMemcpyHostToDevice, device arrays with DeviceToDevice (the workspace keeps its
 // own copy of the current f / bounds either way: a later update may replace only some of them)
 static int workspace_update_impl(DAQPB200Workspace* w, const c_float* f, const c_float* bupper, const c_float* blower,
@@ -856,11 +918,17 @@ static int workspace_update_impl(DAQPB200Workspace* w, const c_float* f, const c
     DAQPB200Handle* h = w->h;
     const int N = w->N, n = w->n, m = w->m;
     if (f && !w->has_f) { g_last_error = "daqp_b200: the workspace was set up without a linear term"; return -2; }
+    if (w->need_data) {
+        if (!f || !bupper || !blower) {
+            g_last_error = "daqp_b200: the first update of a shared workspace must give f, bupper and blower"; return -2;
+        }
+        w->need_data = false;
+    }
     if (f) CK(cudaMemcpyAsync(w->d_f, f, (size_t)N * n * sizeof(T), kind, st));
     if (bupper) CK(cudaMemcpyAsync(w->d_bu, bupper, (size_t)N * m * sizeof(T), kind, st));
     if (blower) CK(cudaMemcpyAsync(w->d_bl, blower, (size_t)N * m * sizeof(T), kind, st));
     UpdateArgs<T> ua;
-    ua.P = N; ua.n = n; ua.m = m; ua.ms = w->ms; ua.ldm = w->ldm;
+    ua.P = N; ua.n = n; ua.m = m; ua.ms = w->ms; ua.ldm = w->ldm; ua.grp = w->ps.grp;
     ua.f = f ? w->d_f : nullptr; ua.bupper = w->d_bu; ua.blower = w->d_bl;
     ua.Rinv = w->ps.Ri; ua.Mt = w->ps.Mt; ua.scaling = w->ps.sc; ua.sense_static = w->ps.sense_static;
     ua.v = w->ps.vv; ua.dupper = w->ps.du; ua.dlower = w->ps.dl; ua.sense = w->ps.sense8;
@@ -899,6 +967,7 @@ extern "C" int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->compute;
     const int N = w->N, n = w->n, m = w->m;
+    if (w->need_data) { g_last_error = "daqp_b200: shared workspace has no f / bounds yet (call update first)"; return -2; }
     DAQPB200Diag dd{};
     dd.n_active = w->d_nact; dd.ws = w->d_ws; dd.counts = w->d_counts; dd.sense = w->d_so; dd.soft_slack = w->d_slack;
     w->ps.phase = 2; w->ps.state_load = warm ? 1 : 0;
@@ -932,6 +1001,7 @@ extern "C" int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, 
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->compute;
+    if (w->need_data) { g_last_error = "daqp_b200: shared workspace has no f / bounds yet (call update first)"; return -2; }
     // the update kernel records setup failures (infeasible bounds) in the workspace's own flag / iter arrays: carry them over
     CK(cudaMemcpyAsync(dexitflag, w->d_flag, (size_t)w->N * sizeof(int), cudaMemcpyDeviceToDevice, st));
     if (diter) CK(cudaMemcpyAsync(diter, w->d_iter, (size_t)w->N * sizeof(int), cudaMemcpyDeviceToDevice, st));

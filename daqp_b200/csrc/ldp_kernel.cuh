@@ -85,9 +85,10 @@ struct LdpArgs {
     unsigned state_stride;    // bytes per problem: oarena rounded up to 16, plus 16 for {k, lsw, valid}
     int state_load, state_save;
     int ns_max;               // most soft constraints (sense & 8) any problem of the batch carries; cap = n + ns_max + 1
-    // shared-matrix mode (EXT instantiation only; daqp_b200_minrep_*): `grp` consecutive problems are LDPs over ONE
-    // constraint matrix -- Mt / Mr / Mt32 / scaling / Rinv / v are indexed by p / grp, bounds and sense stay per problem.
-    // The m LDPs of a polyhedron (reference daqp_minrep_work, src/utils.c:808-835) then stream the same matrix out of L2.
+    // shared-matrix mode (EXT instantiation only): `grp` consecutive problems are LDPs over ONE constraint matrix --
+    // Mt / Mr / Mt32 / scaling / Rinv are indexed by p / grp; bounds, sense, v and the saved state stay per problem. Used
+    // by daqp_b200_minrep_* (the m LDPs of a polyhedron, reference daqp_minrep_work, src/utils.c:808-835) and by shared
+    // workspaces (one H / A, many f / b: daqp_b200_workspace_setup_shared). The group then streams one matrix out of L2.
     int grp;                  // 0 or 1: every problem owns its matrices
     int* exitflag;            // [P]
     int* iter;                // [P]
@@ -1213,7 +1214,7 @@ __global__ void __launch_bounds__(512, 1) ldp_solve_kernel(const __grid_constant
             if (lane == 0) { a.exitflag[p] = exitflag; a.iter[p] = 0; }
         } else {
             // ---- a15/a16: ldp2qp_solution (daqp.c:111-139) + daqp_extract_result (api.c:455-495)
-            const T* vv = a.v ? reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.v) + (size_t)w.pmat() * a.sv) : nullptr;
+            const T* vv = a.v ? reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.v) + (size_t)p * a.sv) : nullptr;
             T* xo = a.x + (size_t)p * a.n;
             T* up = w.u();
             T vnorm = 0;

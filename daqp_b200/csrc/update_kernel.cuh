@@ -14,6 +14,7 @@ namespace dq {
 template <typename T>
 struct UpdateArgs {
     int P, n, m, ms, ldm;
+    int grp;                           // shared workspace: Rinv / Mt / scaling / sense_static are those of set p / grp (0, 1: own)
     const T *f, *bupper, *blower;      // new data: [P][n] (nullptr keeps v), [P][m], [P][m]
     const T *Rinv, *Mt, *scaling;      // kept LDP: packed R^-1 (simple-bound rows normalised), Mt [P][n][ldm], scaling [P][ldm]
     const unsigned char* sense_static; // [P][ldm] user sense bits, zero rows IMMUTABLE, no equality marks
@@ -35,10 +36,11 @@ __global__ void __launch_bounds__(512) ldp_update_kernel(const UpdateArgs<T> a) 
         // flags are only ever raised by the setup (utils.c:356-377), new f / b cannot cure them
         const int prev = a.exitflag[p];
         if (prev == EXIT_NONCONVEX || prev == EXIT_UNSUPPORTED) continue;
-        const T* sc = a.scaling + (size_t)p * ldm;
+        const int pm = a.grp > 1 ? p / a.grp : p;
+        const T* sc = a.scaling + (size_t)pm * ldm;
         const T* bu = a.bupper + (size_t)p * m;
         const T* bl = a.blower + (size_t)p * m;
-        const T* Ri = a.Rinv + (size_t)p * n * (n + 1) / 2;
+        const T* Ri = a.Rinv + (size_t)pm * n * (n + 1) / 2;
         T* vg = a.v + (size_t)p * n;
         // ---- v = R^-T f (utils.c:474-497): column j < ms of the normalised R^-1 carries 1 / scaling[j]
         if (a.f) {
@@ -57,12 +59,12 @@ __global__ void __launch_bounds__(512) ldp_update_kernel(const UpdateArgs<T> a) 
         __syncwarp();
         // ---- check_bounds on the new bounds (utils.c:546-567) and d = b * scaling + M v (utils.c:499-544)
         int bad = 0, any_active = 0;
-        const T* Mt = a.Mt + (size_t)p * n * ldm;
+        const T* Mt = a.Mt + (size_t)pm * n * ldm;
         for (int r = lane; r < ldm; r += 32) {
             int s = 0;
             T du = 0, dl = 0;
             if (r < m) {
-                s = a.sense_static[(size_t)p * ldm + r];
+                s = a.sense_static[(size_t)pm * ldm + r];
                 const T u_ = bu[r], l_ = bl[r];
                 if (!(s & B_IMMUTABLE)) {
                     const T diff = u_ - l_;

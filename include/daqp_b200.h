@@ -181,6 +181,15 @@ int daqp_b200_workspace_setup(DAQPB200Handle* h, int N, int n, int m, int ms,
                               const c_float* H, const c_float* f, const c_float* A,
                               const c_float* bupper, const c_float* blower, const int* sense,
                               const DAQPSettings* settings, DAQPB200Workspace** out);
+/* Shared workspace: G matrix sets -- H[G][n][n], A[G][m-ms][n], sense[G][m] (or NULL) -- and K problems per set that
+ * differ only in f and the bounds (one MPC controller evaluated for many states; the reference would run setup_daqp(H_g,
+ * f_p, A_g, b_p) + daqp_solve per problem, src/api.c:88-160). The QP -> LDP transform runs ONCE per set and the K
+ * problems of a set stream the same device copy of R^-1 / M out of L2. Problem p = g * K + k everywhere below:
+ * daqp_b200_workspace_update must give f[G*K][n], bupper[G*K][m] and blower[G*K][m] before the first solve; update / solve
+ * / free (and the _device variants) are the calls of the plain workspace with N = G * K. */
+int daqp_b200_workspace_setup_shared(DAQPB200Handle* h, int G, int K, int n, int m, int ms,
+                                     const c_float* H, const c_float* A, const int* sense,
+                                     const DAQPSettings* settings, DAQPB200Workspace** out);
 /* New linear term and / or bounds (NULL keeps the current one). Asynchronous; the next solve is ordered after it. */
 int daqp_b200_workspace_update(DAQPB200Workspace* w, const c_float* f, const c_float* bupper, const c_float* blower);
 /* Active-set loop + result extraction. warm = 0: start from the sense bits; warm != 0: continue from the previous solve.

@@ -254,6 +254,59 @@ def test_workspace_sequence_matches_reference(cuda_lib, name):
     mdl.close()
 
 
+WS_SHARED = ["wsshared_n10_m30", "wsshared_n20_m60_ms5", "wsshared_n50_m150"]
+
+
+@pytest.mark.parametrize("name", WS_SHARED)
+def test_shared_workspace_matches_reference(cuda_lib, name):
+    """Shared workspace: G matrix sets, K problems per set that differ only in f and the bounds. Every problem must get
+    what the UNMODIFIED reference gives it through its own workspace -- setup_daqp(H_g, f_p, A_g, b_p) + daqp_solve, then
+    update + warm solve per step (tests/golden/make_golden_shared.py): exit flags, iteration counts and working sets equal
+    for as long as the problem's previous solves ended optimal. The same sequence through a PLAIN workspace on the
+    replicated matrices must agree (same kernels; only the matrix indexing and the place where d is summed differ)."""
+    import os
+    import daqp_b200
+    from common import GOLDEN_DIR
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    G, K, ms = int(d["G"]), int(d["Kp"]), int(d["ms"])
+    N = G * K
+    mdl = daqp_b200.BatchModel().setup_shared(d["H"], d["A"], K, ms=ms, m=int(d["m"]))
+    with pytest.raises(RuntimeError, match="update first"):
+        mdl.solve()
+    plain = daqp_b200.BatchModel().setup(np.repeat(d["H"], K, axis=0), d["f"], np.repeat(d["A"], K, axis=0), d["bupper"],
+                                         d["blower"], None, ms=ms)
+    live = np.ones(N, bool)
+    checked = 0
+    for k in range(int(d["K"]) + 1):
+        if k == 0:
+            mdl.update(f=d["f"], bupper=d["bupper"], blower=d["blower"])
+        else:
+            mdl.update(f=d[f"f{k-1}"], bupper=d[f"bu{k-1}"], blower=d[f"bl{k-1}"])
+            plain.update(f=d[f"f{k-1}"], bupper=d[f"bu{k-1}"], blower=d[f"bl{k-1}"])
+        r = mdl.solve(warm=True, diag=True)
+        q = plain.solve(warm=True, diag=True)
+        np.testing.assert_array_equal(r.exitflag, q.exitflag)
+        np.testing.assert_array_equal(r.iter, q.iter)
+        okq = q.exitflag > 0
+        # (d = b * scaling + M v is summed by the setup kernel in the plain workspace's first solve and by the update kernel
+        # here: same value up to the summation order)
+        np.testing.assert_allclose(r.x[okq], q.x[okq], rtol=0, atol=1e-11 * (1 + np.abs(q.x[okq]).max()))
+        np.testing.assert_allclose(r.lam[okq], q.lam[okq], rtol=0, atol=1e-9 * (1 + np.abs(q.lam[okq]).max()))
+        flag, it = d[f"flag_{k}"], d[f"iter_{k}"]
+        np.testing.assert_array_equal(r.exitflag[live], flag[live], err_msg=f"{name} solve {k}: exit flags")
+        np.testing.assert_array_equal(r.iter[live], it[live], err_msg=f"{name} solve {k}: iteration counts")
+        ok = live & (flag > 0)
+        got = r.working_sets()
+        for p in np.nonzero(ok)[0]:
+            assert got[p] == d[f"ws_{k}"][p, : d[f"nact_{k}"][p]].tolist(), f"{name} solve {k} problem {p}: working set"
+        assert_parity(d[f"x_{k}"][ok], d[f"lam_{k}"][ok], d[f"fval_{k}"][ok], flag[ok], it[ok], r.x[ok], r.lam[ok],
+                      r.fval[ok], r.exitflag[ok], r.iter[ok], f"{name} solve {k}")
+        checked += int(ok.sum())
+        live &= flag > 0
+    assert checked >= N
+    mdl.close(); plain.close()
+
+
 def test_workspace_device_entry_points(cuda_lib):
     """update_device / solve_device (torch CUDA tensors, asynchronous) give the same sequence as the host entry points."""
     import os
