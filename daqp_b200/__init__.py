@@ -103,7 +103,7 @@ def _p(a, t=_dp):
     return None if a is None else a.ctypes.data_as(t)
 
 
-def solve(H, f, A, bupper, blower=None, sense=None, **settings):
+def solve(H, f, A, bupper, blower=None, sense=None, primal_start=None, dual_start=None, **settings):
     """Single QP through the drop-in ``daqp_quadprog`` symbol (same call shape and return value as the
     reference's ``daqp.solve``: ``x, fval, exitflag, info``). bupper/blower longer than A's row count means the
     leading entries are simple bounds (reference daqp.pyx:96-104)."""
@@ -116,6 +116,14 @@ def solve(H, f, A, bupper, blower=None, sense=None, **settings):
     x = np.empty(n); lam = np.empty(m)
     qp = DAQPProblem(n, m, m - mA, _p(H), _p(f), _p(A) if mA else None, _p(bupper), _p(blower), _p(sense, _ip),
                      None, 0, 0)
+    if (primal_start is not None or dual_start is not None) and m > 0:  # daqp.pyx:24-38 (sense is a private copy here)
+        sense = sense.copy(); qp.sense = _p(sense, _ip)
+        L = lib()
+        L.daqp_dual_init_active.restype = None; L.daqp_primal_init_active.restype = None
+        if dual_start is not None:
+            L.daqp_dual_init_active(C.byref(qp), _p(_f64(dual_start)))
+        else:
+            L.daqp_primal_init_active(C.byref(qp), _p(_f64(primal_start)))
     st = default_settings(**settings)
     res = DAQPResult(_p(x), _p(lam) if m else None, 0, 0, 0, 0, 0, 0, 0)
     lib().daqp_quadprog(C.byref(res), C.byref(qp), C.byref(st))
@@ -163,10 +171,17 @@ class Engine:
 
     # -- host arrays -----------------------------------------------------------------------------------------
     def solve_batch(self, H, f, A, bupper, blower, sense=None, ms: int | None = None, diag: bool = False,
-                    out: BatchResult | None = None, **settings) -> BatchResult:
+                    out: BatchResult | None = None, primal_start=None, dual_start=None, **settings) -> BatchResult:
         """Homogeneous batch in host memory: H[N,n,n], f[N,n]|None, A[N,m-ms,n], bupper/blower[N,m],
-        sense[N,m]|None (``daqp_b200_solve_packed``). Pass pinned arrays for asynchronous copies."""
+        sense[N,m]|None (``daqp_b200_solve_packed``). Pass pinned arrays for asynchronous copies.
+        ``primal_start[N,n]`` / ``dual_start[N,m]`` warm-start the working sets like the reference's
+        ``daqp.solve(..., primal_start=, dual_start=)`` (daqp.pyx:24-38): the init helpers set the ACTIVE bits of a copy of
+        ``sense`` (dual_start wins when both are given, as in the reference)."""
         H = _f64(H); f = _f64(f); A = _f64(A); bupper = _f64(bupper); blower = _f64(blower)
+        if dual_start is not None:
+            sense = self.init_active_batch(A, bupper, blower, sense, lam=dual_start, ms=ms)
+        elif primal_start is not None:
+            sense = self.init_active_batch(A, bupper, blower, sense, x=primal_start, ms=ms)
         N, n = H.shape[0], H.shape[1]
         m = bupper.shape[1]
         mA = A.shape[1] if A is not None and A.size else 0
@@ -297,6 +312,44 @@ class Engine:
                                             ptr(out["fval"]), ptr(out["exitflag"], _ip), ptr(out["iter"], _ip),
                                             None, C.c_void_p(stream)))
         return out
+
+    # -- warm-start initialisers (reference daqp_primal_init_active / daqp_dual_init_active) ------------------------------
+    def init_active_batch(self, A, bupper, blower, sense=None, x=None, lam=None, ms: int | None = None) -> np.ndarray:
+        """New ``sense[N, m]`` with the ACTIVE / LOWER bits the reference's init helpers would set from the primal iterate
+        ``x[N, n]`` or the dual iterate ``lam[N, m]`` (``daqp_b200_init_active``). ``sense`` (or zeros) is not modified."""
+        L = lib()
+        L.daqp_b200_init_active.restype = C.c_int
+        A = _f64(A); bupper = _f64(bupper); blower = _f64(blower); x = _f64(x); lam = _f64(lam)
+        N, m = bupper.shape
+        mA = A.shape[1] if A is not None and A.size else 0
+        n = A.shape[2] if mA else x.shape[1]
+        ms = m - mA if ms is None else ms
+        out = np.zeros((N, m), np.intc) if sense is None else np.ascontiguousarray(sense, dtype=np.intc).copy()
+        _check(L.daqp_b200_init_active(self._h, N, n, m, ms, _p(x), _p(lam), _p(A), _p(bupper), _p(blower), _p(out, _ip)))
+        return out
+
+    def init_active_device(self, sense, A, bupper, blower, x=None, lam=None, ms: int | None = None, stream=None):
+        """CUDA tensors; ``sense`` (int32 [N, m]) is updated IN PLACE, asynchronously on the current torch stream
+        (``daqp_b200_init_active_device``)."""
+        import torch
+        L = lib()
+        L.daqp_b200_init_active_device.restype = C.c_int
+        N, m = bupper.shape
+        mA = A.shape[1] if A is not None and A.numel() else 0
+        n = A.shape[2] if mA else x.shape[1]
+        ms = m - mA if ms is None else ms
+        assert sense.is_cuda and sense.dtype == torch.int32 and sense.is_contiguous()
+        for t in (A, bupper, blower, x, lam):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(bupper.device).cuda_stream
+        if stream == 0:
+            stream = 1
+        ptr = lambda t, ty=_dp: None if t is None else C.cast(t.data_ptr(), ty)
+        _check(L.daqp_b200_init_active_device(self._h, N, n, m, ms, ptr(x), ptr(lam), ptr(A), ptr(bupper), ptr(blower),
+                                              ptr(sense, _ip), C.c_void_p(stream)))
+        return sense
 
     # -- minimal representation of polyhedra (batched LDP consumer) ----------------------------------------------
     def minrep_batch(self, A, b, ms: int | None = None, info: bool = False, **settings):

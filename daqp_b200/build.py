@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdaqp_b200.so")
 SOURCES = ["daqp_b200.cu"]
-HEADERS = ["common.cuh", "ldp_kernel.cuh", "setup_kernel.cuh", "update_kernel.cuh", "minrep_kernel.cuh", os.path.join("..", "..", "include", "daqp_b200.h")]
+HEADERS = ["common.cuh", "ldp_kernel.cuh", "setup_kernel.cuh", "update_kernel.cuh", "minrep_kernel.cuh", "warmstart_kernel.cuh", os.path.join("..", "..", "include", "daqp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

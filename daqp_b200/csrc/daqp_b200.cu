@@ -9,6 +9,7 @@
 #include "setup_kernel.cuh"
 #include "update_kernel.cuh"
 #include "minrep_kernel.cuh"
+#include "warmstart_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -743,6 +744,75 @@ extern "C" int daqp_b200_minrep_batch(DAQPB200Handle* h, int P, int n, int m, in
 extern "C" void daqp_minrep(int* is_redundant, c_float* A, c_float* b, int n, int m, int ms) {
     if (daqp_b200_minrep_batch(nullptr, 1, n, m, ms, A, b, nullptr, is_redundant, nullptr, nullptr) != 0)
         for (int i = 0; i < m; i++) is_redundant[i] = -1;
+}
+
+// ---- warm-start initialisers (reference daqp_primal_init_active / daqp_dual_init_active, src/api.c:577-631) --------
+static int init_active_launch(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* dx, const c_float* dlam,
+                              const c_float* dA, const c_float* dbu, const c_float* dbl, int* dsense, cudaStream_t s) {
+    if (N <= 0 || m <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
+    if (!dx && !dlam) { g_last_error = "daqp_b200: init_active needs a primal or a dual iterate"; return -2; }
+    InitActiveArgs ia;
+    ia.N = N; ia.n = n; ia.m = m; ia.ms = ms; ia.x = dx; ia.lam = dlam; ia.A = dA; ia.bupper = dbu; ia.blower = dbl;
+    ia.sense = dsense;
+    const size_t smem = (size_t)IA_WARPS * (32 * IA_PITCH + n) * sizeof(double);
+    CK(cudaFuncSetAttribute(init_active_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    init_active_kernel<<<std::min(h->num_sms * 3, (N + IA_WARPS - 1) / IA_WARPS), 32 * IA_WARPS, smem, s>>>(ia);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int daqp_b200_init_active_device(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* dx,
+                                            const c_float* dlam, const c_float* dA, const c_float* dbupper,
+                                            const c_float* dblower, int* dsense, void* stream) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return init_active_launch(h, N, n, m, ms, dx, dlam, dA, dbupper, dblower, dsense,
+                              stream ? (cudaStream_t)stream : h->compute);
+}
+
+extern "C" int daqp_b200_init_active(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* x,
+                                     const c_float* lam, const c_float* A, const c_float* bupper,
+                                     const c_float* blower, int* sense) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (N <= 0 || m <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid problem dimensions"; return -2; }
+    if (!x && !lam) { g_last_error = "daqp_b200: init_active needs a primal or a dual iterate"; return -2; }
+    const size_t mA = (size_t)(m - ms), nA = x ? (size_t)N * mA * n : 0, nb = (size_t)N * m, nx = x ? (size_t)N * n : 0;
+    int rc = ensure(&h->stage, &h->stage_bytes, (nA + 3 * nb + nx) * sizeof(c_float) + nb * sizeof(int) + 8 * 256);
+    if (rc) return rc;
+    Carver cv(h->stage);
+    c_float* dA = cv.take<c_float>(nA); c_float* dx = cv.take<c_float>(nx); c_float* dl = cv.take<c_float>(nb);
+    c_float* dbu = cv.take<c_float>(nb); c_float* dbl = cv.take<c_float>(nb); int* dse = cv.take<int>(nb);
+    cudaStream_t s = h->compute;
+    if (x) {
+        if (nA) CK(cudaMemcpyAsync(dA, A, nA * sizeof(c_float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dx, x, nx * sizeof(c_float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dbu, bupper, nb * sizeof(c_float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dbl, blower, nb * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    } else {
+        CK(cudaMemcpyAsync(dl, lam, nb * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemcpyAsync(dse, sense, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+    rc = init_active_launch(h, N, n, m, ms, x ? dx : nullptr, x ? nullptr : dl, dA, dbu, dbl, dse, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sense, dse, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Drop-ins (reference include/api.h:57-58): one problem, qp->sense updated in place. Like the reference they return
+// nothing; without a CUDA device qp->sense is left untouched and daqp_b200_last_error() says why.
+extern "C" void daqp_primal_init_active(DAQPProblem* qp, c_float* x) {
+    if (!qp || !qp->sense || !x) return;
+    daqp_b200_init_active(nullptr, 1, qp->n, qp->m, qp->ms, x, nullptr, qp->A, qp->bupper, qp->blower, qp->sense);
+}
+extern "C" void daqp_dual_init_active(DAQPProblem* qp, c_float* lam) {
+    if (!qp || !qp->sense || !lam) return;
+    daqp_b200_init_active(nullptr, 1, qp->n, qp->m, qp->ms, nullptr, lam, qp->A, qp->bupper, qp->blower, qp->sense);
 }
 
 // ---- persistent batch workspace: setup once, update(f, b) + solve many (reference setup_daqp / daqp_update_ldp /

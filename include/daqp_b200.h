@@ -204,6 +204,23 @@ int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, c_float* dx
                                      int* dexitflag, int* diter, void* stream);
 void daqp_b200_workspace_free(DAQPB200Workspace* w);
 
+/* ---- warm-start initialisers (the callers on the input side of the path) -----------------------------------------
+ * reference include/api.h:57-58 (src/api.c:577-631): set the ACTIVE / LOWER bits of qp->sense from a primal iterate
+ * (rows with |a_i'x - bound_i| < 1e-9) or from a dual iterate (|lam_i| > 1e-12); IMMUTABLE rows are left alone. The
+ * next solve activates those rows first. Drop-in signatures; one problem, qp->sense updated in place. */
+void daqp_primal_init_active(DAQPProblem* qp, c_float* x);
+void daqp_dual_init_active(DAQPProblem* qp, c_float* lam);
+
+/* NEW: the same for N problems of one shape. Exactly one of x ([N][n]) and lam ([N][m]) is given (x wins when both
+ * are); A / bupper / blower are read only with x. sense ([N][m] ints) is updated in place. HOST arrays, blocking. */
+int daqp_b200_init_active(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* x, const c_float* lam,
+                          const c_float* A, const c_float* bupper, const c_float* blower, int* sense);
+/* DEVICE arrays, asynchronous on `stream`: lets a closed loop derive the next step's warm start from the previous
+ * step's x or lam without leaving the GPU (solve_device -> init_active_device -> solve_device). */
+int daqp_b200_init_active_device(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* dx, const c_float* dlam,
+                                 const c_float* dA, const c_float* dbupper, const c_float* dblower, int* dsense,
+                                 void* stream);
+
 /* ---- minimal representation of polyhedra (batched LDP consumer) ---------------------------------------------
  * reference include/api.h:54 (src/api.c:531-556, src/utils.c:808-835): is_redundant[i] = 1 iff constraint i of
  * {x : [I(ms); A] x <= b} is redundant (the LDP with row i turned into an active equality is infeasible), else 0.

@@ -762,6 +762,33 @@ setup_failed: /* api.c:69-72: exit flag only, res->x untouched */
     ldp_free(w);
 }
 
+/* ---- warm-start initialisers: api.c:577-631 ----------------------------------------------------------------------- */
+/* api.c:579-617: tol = 1e-9; simple bounds compare x[i], general rows the left-to-right sum of factorization.h:13-17 */
+void orc_primal_init_active(OrcProblem *qp, const orc_real *x) {
+    const real tol = (real)1e-9;
+    for (int i = 0; i < qp->m; i++) {
+        real ax, slack;
+        if (qp->sense[i] & B_IMMUTABLE) continue;
+        ax = i < qp->ms ? x[i] : dot1(x, qp->A + (size_t)(i - qp->ms) * qp->n, qp->n);
+        slack = ax - qp->bupper[i];
+        if (slack < tol && slack > -tol) { qp->sense[i] |= B_ACTIVE; qp->sense[i] &= ~B_LOWER; }
+        else {
+            slack = ax - qp->blower[i];
+            if (slack < tol && slack > -tol) qp->sense[i] |= B_ACTIVE + B_LOWER;
+        }
+    }
+}
+
+/* api.c:620-631: tol = 1e-12 */
+void orc_dual_init_active(OrcProblem *qp, const orc_real *lam) {
+    const real tol = (real)1e-12;
+    for (int i = 0; i < qp->m; i++) {
+        if (qp->sense[i] & B_IMMUTABLE) continue;
+        if (lam[i] > tol) { qp->sense[i] |= B_ACTIVE; qp->sense[i] &= ~B_LOWER; }
+        else if (lam[i] < -tol) qp->sense[i] |= B_ACTIVE + B_LOWER;
+    }
+}
+
 /* ---- minimal representation: daqp_minrep (api.c:531-556) + daqp_minrep_work (utils.c:808-835) ------------- */
 /* The reference wraps the polyhedron in a bare workspace: M = A as given (no normalisation, scaling == NULL so the
  * violation threshold is -primal_tol itself, auxiliary.c:110,136), Rinv == NULL (simple bounds are unit rows),

@@ -83,6 +83,10 @@ double orc_solve_packed(int N, int n, int m, int ms,
                         int *trace_counts /* [N][4] scan,add,remove,csp or NULL */,
                         int nthreads);
 
+/* daqp_primal_init_active / daqp_dual_init_active (api.c:577-631): warm-start bits of qp->sense from an iterate. */
+void orc_primal_init_active(OrcProblem *qp, const orc_real *x);
+void orc_dual_init_active(OrcProblem *qp, const orc_real *lam);
+
 /* daqp_minrep (api.c:531-556, utils.c:808-835): is_redundant[m] for {x : [I(ms); A] x <= b}, constraints probed one
  * after the other exactly like the reference. */
 void orc_minrep(int *is_redundant, const orc_real *A, const orc_real *b, int n, int m, int ms);

@@ -341,3 +341,30 @@ def ref_minrep(A, b, name: str = "libdaqp_ref.so") -> np.ndarray:
     lib.daqp_minrep(red.ctypes.data_as(C.POINTER(C.c_int)), A.ctypes.data_as(dp), b.ctypes.data_as(dp),
                     C.c_int(n), C.c_int(m), C.c_int(m - mA))
     return red
+
+
+def init_active(b, x=None, lam=None, sense=None, which: str = "oracle", name: str = "libdaqp_ref.so") -> np.ndarray:
+    """daqp_primal_init_active (x given) / daqp_dual_init_active (lam given) per problem of the batch, through the oracle
+    restatement (which="oracle") or the reference itself (which="ref", oracle/_ref). Returns the new sense [N, m]."""
+    Problem = _F64[0]
+    if which == "ref":
+        lib = C.CDLL(os.path.join(REF_DIR, name))
+        fp, fd = lib.daqp_primal_init_active, lib.daqp_dual_init_active
+    else:
+        lib = C.CDLL(os.path.join(HERE, "libdaqp_oracle.so"))
+        fp, fd = lib.orc_primal_init_active, lib.orc_dual_init_active
+    fp.restype = None; fd.restype = None
+    out = np.ascontiguousarray(b.sense if sense is None else sense, dtype=np.int32).copy()
+    real = C.c_double
+    mA = b.m - b.ms
+    for p in range(b.N):
+        qp = Problem(b.n, b.m, b.ms, _ptr(b.H[p], real), _ptr(b.f[p], real), _ptr(b.A[p], real) if mA > 0 else None,
+                     _ptr(b.bupper[p], real), _ptr(b.blower[p], real), out[p].ctypes.data_as(C.POINTER(C.c_int)),
+                     None, 0, 0)
+        if x is not None:
+            v = np.ascontiguousarray(x[p], np.float64)
+            fp(C.byref(qp), _ptr(v, real))
+        else:
+            v = np.ascontiguousarray(lam[p], np.float64)
+            fd(C.byref(qp), _ptr(v, real))
+    return out

@@ -18,7 +18,7 @@ X_TOL, F_TOL, L_TOL = 1e-9, 1e-9, 1e-7
 def golden_names():
     """Single-solve fixtures (the wsseq_* files hold workspace sequences: see test_workspace_sequence_matches_reference)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_"))]
+    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_"))]
 
 
 def minrep_golden_names():
