@@ -90,6 +90,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE line: the JSON result. Libraries loaded later write there too (NCCL prints its version banner to
+    stdout when NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the rest of the run and the
+    result line goes to a private duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def dist_setup(gpus: int):
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,7 +174,7 @@ def run_reference(args, rank, world):
                              "sample": f"{b.N} problems of the C3 batch per step x {args.steps} steps"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, per_gpu, note=None):
@@ -167,6 +189,7 @@ def config_dict(args, per_gpu, note=None):
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -422,7 +445,7 @@ def main():
                 "shared_workspace": shw if not args.no_e2e else None,
                 "parity": {"max_abs_x_err_vs_constructed_optimum": err, "all_optimal": True,
                            "active_set_differs_from_construction": as_mismatch}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
