@@ -74,12 +74,14 @@ def test_no_gpu_means_error_not_fallback(cuda_lib):
 
 
 def test_product_does_not_reference_oracle():
-    """The shipped package must not import, link or call anything under oracle/."""
-    pkg = os.path.join(ROOT, "daqp_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, fn)).read()
-                for needle in ("import oracle", "from oracle", "oracle/", "oracle.harness", "libdaqp_oracle",
-                               "daqp_oracle", "libdaqp_ref", "orc_quadprog"):
-                    assert needle not in txt, f"{fn} reaches into the oracle ({needle})"
+    """The shipped package (and the helper scripts) must not import, link or call anything under oracle/: only tests/,
+    __graft_entry__.smoke() and bench.py's CPU legs may."""
+    needles = ("import oracle", "from oracle", "oracle/", "oracle.harness", "libdaqp_oracle", "daqp_oracle",
+               "libdaqp_ref", "orc_quadprog")
+    for pkg in ("daqp_b200", "scripts", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                    txt = open(os.path.join(dirpath, fn)).read()
+                    for needle in needles:
+                        assert needle not in txt, f"{pkg}/{fn} reaches into the oracle ({needle})"

@@ -163,3 +163,48 @@ def test_cuda_minrep_properties_at_scale(engine):
     A2 = np.stack([A[q][red[q] == 0] for q in sel]); b2 = np.stack([b[q][red[q] == 0] for q in sel])
     red2 = engine.minrep_batch(A2, b2)
     assert red2.sum() == 0
+
+
+@pytest.mark.gpu
+def test_cuda_minrep_throughput_report(cuda_lib, oracle_libs):
+    """Informational: device time of the batched path (CUDA events, device arrays) next to the reference's own
+    daqp_minrep on one host thread (oracle/_ref when it travelled with the snapshot, else the oracle restatement) for a
+    sample of the same polyhedra. Written to gpurun_out/minrep.json (copied to profiles/minrep_r01.json by hand); the
+    only assertion is that both agree on the sample."""
+    import json
+    import time
+    import torch
+    import daqp_b200
+    eng = daqp_b200.Engine()
+    dev = torch.device("cuda:0")
+    orc = oracle_libs.OracleLib()
+    rows = []
+    for (P, n, m, ms) in [(4096, 8, 64, 0), (2048, 10, 100, 0), (512, 20, 150, 0), (128, 50, 300, 0)]:
+        A, b = generate_polyhedra(P, n, m, ms, seed=31 + n)
+        dA, db = torch.from_numpy(A).to(dev), torch.from_numpy(b).to(dev)
+        out = eng.minrep_batch_device(dA, db, ms=ms)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            out = eng.minrep_batch_device(dA, db, ms=ms, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dev = e0.elapsed_time(e1) / reps
+        red = out["is_redundant"].cpu().numpy()
+        sample = min(P, 16)
+        use_ref = oracle_libs.have_ref()
+        t0 = time.perf_counter()
+        ref = np.stack([oracle_libs.ref_minrep(A[q], b[q]) if use_ref else orc.minrep(A[q], b[q]) for q in range(sample)])
+        cpu_s = time.perf_counter() - t0
+        np.testing.assert_array_equal(red[:sample], ref)
+        rows.append({"P": P, "n": n, "m": m, "ms": ms, "ldps": P * m, "device_ms": ms_dev,
+                     "polyhedra_per_s_device": P / ms_dev * 1e3, "ldps_per_s_device": P * m / ms_dev * 1e3,
+                     "mean_iterations": float(out["iter"].float().mean()), "redundant_fraction": float(red.mean()),
+                     "cpu_polyhedra_per_s_1thread": sample / cpu_s, "cpu_kind": "reference" if use_ref else "port"})
+    eng.close()
+    os.makedirs(os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out", "minrep.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    print(json.dumps(rows))
