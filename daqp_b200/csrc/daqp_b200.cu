@@ -755,9 +755,11 @@ static int init_active_launch(DAQPB200Handle* h, int N, int n, int m, int ms, co
     InitActiveArgs ia;
     ia.N = N; ia.n = n; ia.m = m; ia.ms = ms; ia.x = dx; ia.lam = dlam; ia.A = dA; ia.bupper = dbu; ia.blower = dbl;
     ia.sense = dsense;
-    const size_t smem = (size_t)IA_WARPS * (32 * IA_PITCH + n) * sizeof(double);
+    const size_t smem = ia_smem_per_warp(n) * IA_WARPS;
+    if (smem > h->smem_optin) { g_last_error = "daqp_b200: n too large for the init_active tile"; return -2; }
     CK(cudaFuncSetAttribute(init_active_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    init_active_kernel<<<std::min(h->num_sms * 3, (N + IA_WARPS - 1) / IA_WARPS), 32 * IA_WARPS, smem, s>>>(ia);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, h->smem_optin / (smem + 1024)));
+    init_active_kernel<<<std::min(h->num_sms * per_sm, (N + IA_WARPS - 1) / IA_WARPS), 32 * IA_WARPS, smem, s>>>(ia);
     CK(cudaGetLastError());
     return 0;
 }

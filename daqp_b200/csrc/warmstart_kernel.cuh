@@ -13,13 +13,19 @@
 //                           separate multiply and add so that the bits match the reference built without contraction.
 //   dual   (api.c:620-631): lam_i > 1e-12 -> ACTIVE (upper), lam_i < -1e-12 -> ACTIVE + LOWER.
 //
-// One warp per problem. The primal pass is a single read of A (HBM-bound: m-ms rows of n doubles per problem): 32 x 32
-// tiles go through a padded shared-memory tile with coalesced 256-byte row segments, then lane r walks row r of the tile
-// left to right -- the reference's summation order with coalesced global loads.
-// Measured on 100k C3 problems (scripts/ia_probe.cu, B200): tile loads through registers, 1 / 4 / 8 / 16 / 32 loads in
-// flight per warp: 3.90 / 2.25 / 1.95 / 1.60 / 1.80 ms; cp.async straight into the tile (all rows in flight, no staging
-// registers): 1.46 ms = 4.4 TB/s, 67 % of the measured HBM peak; 24 resident warps per SM in both (16: 2.2 ms). What is
-// left is the per-warp alternation of a copy phase and a compute phase (next: double-buffered tiles).
+// One warp per problem. The primal pass is a single read of A (HBM-bound: m-ms rows of n doubles per problem). Tiles of
+// IA_ROWS rows x up to 64 columns -- for n <= 64 a tile is IA_ROWS WHOLE rows, one contiguous piece of A -- are copied
+// with cp.async straight into a padded shared-memory tile (no staging registers, every row of the tile in flight), then
+// lane r walks row r of the tile left to right: the reference's summation order with coalesced global traffic.
+//
+// Measured on 100k C3 problems (n = 50, 150 rows; scripts/ia_probe.cu on a B200, algorithmic bytes 6.4 GB per launch):
+//   32 x 32 tiles, loads through registers, 1 / 4 / 8 / 16 / 32 loads in flight per warp   3.90 / 2.25 / 1.95 / 1.60 / 1.80 ms
+//   32 x 32 tiles, cp.async                                                                 1.46 ms
+//   whole-row tiles, cp.async, 32 / 24 / 16 / 8 rows per tile                               1.30 / 1.14 / 1.32 / 1.33 ms
+//   whole-row tiles, two or three tile buffers per warp (copy of tile t+1 behind the walk of tile t)  1.44 / 2.10 ms
+// i.e. resident warps beat per-warp overlap (a second buffer halves the warps per SM), and 24 rows per tile is the sweet
+// spot between the number of copies a lane has in flight and the number of tile phases: 5.6 TB/s in the probe (zero-filled
+// arrays), 1.24 ms = 5.2 TB/s = 79 % of the measured HBM peak (6553 GB/s) with random data through the product entry point.
 #pragma once
 #include "common.cuh"
 
@@ -37,15 +43,14 @@ struct InitActiveArgs {
 #ifndef IA_WARPS_N
 #define IA_WARPS_N 8
 #endif
-#ifndef IA_UNROLL
-#define IA_UNROLL 4 // loads of a tile kept in flight per warp (experiment knob, scripts/ia_probe.cu)
-#endif
-#ifndef IA_MODE
-#define IA_MODE 1 // 0: tile loads through registers, 1: cp.async into the tile
+#ifndef IA_ROWS
+#define IA_ROWS 24 // rows per tile; lanes >= IA_ROWS idle in the row walk (experiment knob, scripts/ia_probe.cu)
 #endif
 constexpr int IA_WARPS = IA_WARPS_N;
-constexpr int IA_UNROLL_C = IA_UNROLL;
-constexpr int IA_PITCH = 33; // doubles per tile row: odd, so that the 32 lanes, each walking its own row, hit different banks
+
+// doubles per tile row: odd, so that the lanes, each walking its own row, hit different banks
+__host__ __device__ inline int ia_pitch(int n) { return (n < 64 ? n : 64) | 1; }
+__host__ __device__ inline size_t ia_smem_per_warp(int n) { return ((size_t)IA_ROWS * ia_pitch(n) + n) * sizeof(double); }
 
 __device__ __forceinline__ int init_active_bits(int s, double ax, double bu, double bl) {
     const double tol = 1e-9; // api.c:582
@@ -60,9 +65,10 @@ __device__ __forceinline__ int init_active_bits(int s, double ax, double bu, dou
 __global__ void __launch_bounds__(32 * IA_WARPS) init_active_kernel(const InitActiveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int n = a.n, m = a.m, ms = a.ms, mA = m - ms;
-    double* tile = reinterpret_cast<double*>(smem_raw) + (size_t)wib * (32 * IA_PITCH + n);
-    double* xs = tile + 32 * IA_PITCH;
+    const int n = a.n, m = a.m, ms = a.ms, mA = m - ms, pitch = ia_pitch(n);
+    double* tile = reinterpret_cast<double*>(smem_raw + ia_smem_per_warp(n) * wib);
+    double* xs = tile + (size_t)IA_ROWS * pitch;
+    const int nchunk = (n + 63) >> 6;
     for (int p = blockIdx.x * IA_WARPS + wib; p < a.N; p += gridDim.x * IA_WARPS) {
         int* se = a.sense + (size_t)p * m;
         if (a.x == nullptr) { // dual iterate: api.c:620-631
@@ -81,37 +87,33 @@ __global__ void __launch_bounds__(32 * IA_WARPS) init_active_kernel(const InitAc
         const double* x = a.x + (size_t)p * n;
         const double* bu = a.bupper + (size_t)p * m;
         const double* bl = a.blower + (size_t)p * m;
+        const double* A = a.A + (size_t)p * mA * n;
         for (int i = lane; i < n; i += 32) xs[i] = x[i];
         __syncwarp();
         for (int i = lane; i < ms; i += 32) se[i] = init_active_bits(se[i], xs[i], bu[i], bl[i]); // api.c:585-598
-        const double* A = a.A + (size_t)p * mA * n;
-        for (int r0 = 0; r0 < mA; r0 += 32) {
-            const int nr = min(32, mA - r0);
+        for (int r0 = 0; r0 < mA; r0 += IA_ROWS) {
+            const int nr = min(IA_ROWS, mA - r0);
             double acc = 0.0;
-            for (int c0 = 0; c0 < n; c0 += 32) {
-                const int nc = min(32, n - c0);
-                // rows r0 .. r0+nr-1, columns c0 .. c0+nc-1: one coalesced segment per row. (Issuing all 32 loads of a tile
-                // before the first store -- fully unrolled -- measured SLOWER: 2.20 ms vs 1.75 ms per 100k C3 problems.)
-#if IA_MODE == 0
-#pragma unroll IA_UNROLL_C
-                for (int rr = 0; rr < nr; rr++)
-                    if (lane < nc) tile[rr * IA_PITCH + lane] = __ldg(A + (size_t)(r0 + rr) * n + c0 + lane);
-#else
-                // asynchronous copies straight into the tile (LDGSTS): no staging registers, so all rows of the tile are in
-                // flight at once
+            for (int ch = 0; ch < nchunk; ch++) {
+                const int c0 = ch << 6, nc = min(64, n - c0);
+                // rows r0 .. r0+nr-1, columns c0 .. c0+nc-1: asynchronous copies straight into the tile
                 {
-                    const unsigned dst = smem_u32(tile) + 8u * lane;
-                    const double* src = A + (size_t)r0 * n + c0 + lane;
-                    if (lane < nc)
-                        for (int rr = 0; rr < nr; rr++)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * IA_PITCH * rr), "l"(src + (size_t)rr * n) : "memory");
+                    const unsigned dst = smem_u32(tile);
+                    const double* src = A + (size_t)r0 * n + c0;
+                    for (int rr = 0; rr < nr; rr++) {
+                        if (lane < nc)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (rr * pitch + lane)), "l"(src + (size_t)rr * n + lane) : "memory");
+                        if (lane + 32 < nc)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (rr * pitch + lane + 32)), "l"(src + (size_t)rr * n + lane + 32) : "memory");
+                    }
                     cp_async_commit();
                     cp_async_wait<0>();
                 }
-#endif
                 __syncwarp();
-                if (lane < nr)
-                    for (int c = 0; c < nc; c++) acc = __dadd_rn(acc, __dmul_rn(xs[c0 + c], tile[lane * IA_PITCH + c]));
+                if (lane < nr) {
+                    const double* row = tile + lane * pitch;
+                    for (int c = 0; c < nc; c++) acc = __dadd_rn(acc, __dmul_rn(xs[c0 + c], row[c]));
+                }
                 __syncwarp();
             }
             if (lane < nr) { // api.c:601-616
