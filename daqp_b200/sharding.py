@@ -83,3 +83,45 @@ def scatter_solve_gather(arrays: dict | None, n: int, m: int, ms: int, solve_loc
         if rank == src:
             out[key] = torch.cat([g[: b - a] for g, (a, b) in zip(gathered, blocks)])
     return out
+
+
+def scatter_apply_gather(arrays: dict | None, apply_local: Callable[[dict], dict], src: int = 0, device=None) -> dict | None:
+    """Generic form of the same plumbing for the other batched entry points (polyhedra for ``minrep_batch``, iterates for
+    ``init_active_batch``): rank ``src`` holds a dict of torch tensors that share their leading dimension N; every rank
+    receives its contiguous block of each, runs ``apply_local`` on the block and the tensors it returns (leading
+    dimension = the block's length) are gathered back on ``src``. Other ranks pass ``arrays=None`` and get ``None``."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    meta = [None]
+    if rank == src:
+        meta = [{k: (tuple(v.shape), v.dtype) for k, v in arrays.items()}]
+    dist.broadcast_object_list(meta, src=src)
+    meta = meta[0]
+    N = next(iter(meta.values()))[0][0]
+    blocks = partition(N, world)
+    lo, hi = blocks[rank]
+    width = max(b - a for a, b in blocks)
+    dev = device if device is not None else (next(iter(arrays.values())).device if rank == src else torch.device("cpu"))
+    local = {}
+    for key, (shape, dtype) in meta.items():
+        buf = torch.empty((width,) + shape[1:], dtype=dtype, device=dev)
+        padded = None
+        if rank == src:
+            padded = []
+            for a, b in blocks:  # scatter needs equally sized chunks: pad the short ones, receivers trim
+                c = arrays[key][a:b].contiguous().to(dev)
+                padded.append(torch.cat([c, c.new_zeros((width - c.shape[0],) + shape[1:])]) if c.shape[0] < width else c)
+        dist.scatter(buf, padded, src=src)
+        local[key] = buf[: hi - lo].clone()
+    res = apply_local(local)
+    out = {} if rank == src else None
+    for key in sorted(res):
+        t = res[key]
+        pad = t.new_zeros((width,) + tuple(t.shape[1:]))
+        pad[: t.shape[0]] = t
+        gathered = [torch.empty_like(pad) for _ in range(world)] if rank == src else None
+        dist.gather(pad, gathered, dst=src)
+        if rank == src:
+            out[key] = torch.cat([g[: b - a] for g, (a, b) in zip(gathered, blocks)])
+    return out

@@ -72,3 +72,42 @@ def test_scatter_solve_gather_world2_gloo(oracle_libs, tmp_path):
     marker = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(2, 29517, marker), nprocs=2, join=True)
     assert open(marker).read() == "ok"
+
+
+def _worker_minrep(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from daqp_b200.problems import generate_polyhedra
+    from daqp_b200.sharding import scatter_apply_gather
+    from oracle import harness
+    arrays = None
+    if rank == 0:
+        A, b = generate_polyhedra(11, 4, 18, 0, seed=5)  # 11 polyhedra: uneven split
+        arrays = {"A": torch.from_numpy(A), "b": torch.from_numpy(b)}
+
+    def minrep_local(loc):  # on the GPU box: Engine.minrep_batch_device(loc["A"], loc["b"])
+        o = harness.OracleLib()
+        red = np.stack([o.minrep(loc["A"][q].numpy(), loc["b"][q].numpy()) for q in range(loc["A"].shape[0])])
+        return {"is_redundant": torch.from_numpy(red)}
+
+    out = scatter_apply_gather(arrays, minrep_local, src=0)
+    if rank == 0:
+        o = harness.OracleLib()
+        whole = np.stack([o.minrep(A[q], b[q]) for q in range(A.shape[0])])
+        open(tmp, "w").write("ok" if np.array_equal(out["is_redundant"].numpy(), whole) else "mismatch")
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_minrep_gather_world2_gloo(oracle_libs, tmp_path):
+    """The generic scatter -> apply -> gather plumbing with the polyhedra of the minimal-representation path."""
+    import torch.multiprocessing as mp
+    marker = str(tmp_path / "result_minrep.txt")
+    mp.spawn(_worker_minrep, args=(2, 29523, marker), nprocs=2, join=True)
+    assert open(marker).read() == "ok"
