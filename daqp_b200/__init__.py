@@ -322,8 +322,8 @@ class Engine:
         A = _f64(A); bupper = _f64(bupper); blower = _f64(blower); x = _f64(x); lam = _f64(lam)
         N, m = bupper.shape
         mA = A.shape[1] if A is not None and A.size else 0
-        n = A.shape[2] if mA else x.shape[1]
         ms = m - mA if ms is None else ms
+        n = A.shape[2] if mA else (x.shape[1] if x is not None else max(ms, 1))  # n is not used by the dual pass
         out = np.zeros((N, m), np.intc) if sense is None else np.ascontiguousarray(sense, dtype=np.intc).copy()
         _check(L.daqp_b200_init_active(self._h, N, n, m, ms, _p(x), _p(lam), _p(A), _p(bupper), _p(blower), _p(out, _ip)))
         return out
@@ -336,8 +336,8 @@ class Engine:
         L.daqp_b200_init_active_device.restype = C.c_int
         N, m = bupper.shape
         mA = A.shape[1] if A is not None and A.numel() else 0
-        n = A.shape[2] if mA else x.shape[1]
         ms = m - mA if ms is None else ms
+        n = A.shape[2] if mA else (x.shape[1] if x is not None else max(ms, 1))
         assert sense.is_cuda and sense.dtype == torch.int32 and sense.is_contiguous()
         for t in (A, bupper, blower, x, lam):
             if t is not None:
