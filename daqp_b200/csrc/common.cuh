@@ -144,7 +144,7 @@ template <typename T> __device__ __noinline__ T warp_sum(T v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-__device__ __noinline__ double fdiv(double a, double b) { return a / b; }
+static __device__ __noinline__ double fdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 // correctly rounded reciprocal: bit-identical to 1/x (IEEE division is correctly rounded too) at a third of the
 // instructions of the general division, and short enough to inline

@@ -208,6 +208,9 @@ static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t
                                          : launch_solve_x<T, NV, false>(a, grid, block, smem, s);
     }
 }
+// team mode (n > 64, plain fp64 path): instantiated in team_launch.cu (separate translation unit: compiled in parallel)
+cudaError_t daqp_b200_launch_solve_team(const LdpArgs<double>& a, int nv, int grid, size_t smem, cudaStream_t s);
+
 template <typename T, int NGS>
 static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(qp_setup_kernel<T, NGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -271,9 +274,15 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     LdpArgs<T> la;
     memset(&la, 0, sizeof(la));
     la.n = n; la.m = m; la.ms = ms; la.ldm = ldm; la.ldn = ldn; la.cap = cap;
-    const size_t smem_solve_w = ldp_layout<T>(la), smem_setup_w = setup_smem_per_warp<T>(n);
+    // n > 64: a warp per problem leaves the SM nearly empty (three problems fit at n = 120) -- a team of four warps per
+    // problem instead (plain fp64 path; soft constraints / workspaces / shared matrices stay on the warp kernel)
+    int team = 0;
+    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 128 && m <= 1024) team = 4;
+    if (const char* tenv = getenv("DAQP_B200_TEAM")) { if (atoi(tenv) == 0) team = 0; }
+    const size_t smem_solve_w = ldp_layout<T>(la, team), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
     int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
+    if (team) w_solve = (int)std::min<size_t>(TEAM_MAX_CTAS, (budget + 1024) / (smem_solve_w + 1024)); // CTAs (= problems) per SM
     if (w_solve < 1 || w_setup < 1) { g_last_error = "daqp_b200: problem too large for shared memory"; return -2; }
     if (const char* wenv = getenv("DAQP_B200_WARPS")) w_solve = std::max(1, std::min(w_solve, atoi(wenv))); // tuning knob
     h->stats.warps_per_sm = w_solve;
@@ -289,7 +298,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     const DevSettings<T> st = to_dev_settings<T>(settings);
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
-    const bool screening = sizeof(T) == 8 && !(tune & 2) && m <= 256;
+    const bool screening = sizeof(T) == 8 && !(tune & 2) && (m <= 256 || team);
     for (int p0 = 0; p0 < N; p0 += chunk) {
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);
@@ -358,7 +367,13 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.soft_slack = sa.soft_slack; la.ns_max = ns_max;
         la.tune = tune;
         if (ps) { la.state = ps->state; la.state_stride = ps->state_stride; la.state_load = ps->state_load; la.state_save = 1; la.grp = ps->grp; }
-        if (!ps || ps->phase == 2) {
+        if (team) {
+            cudaError_t e = cudaErrorNotSupported;
+            if constexpr (sizeof(T) == 8)
+                e = daqp_b200_launch_solve_team(la, nv, std::min(grid_max * w_solve, P), smem_solve_w, stream);
+            if (e != cudaSuccess) return fail("ldp_solve_kernel (team) launch", e, __LINE__);
+            h->stats.solve_launches++;
+        } else if (!ps || ps->phase == 2) {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);
             const size_t smem = smem_solve_w * w_solve;
             cudaError_t e = cudaErrorInvalidValue;
@@ -427,7 +442,7 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     first_chunk = std::min(first_chunk, chunk);
     const size_t in_b = ((size_t)n * n + n + (size_t)mA * n + 2 * (size_t)m) * sizeof(T) + (size_t)m * sizeof(int);
     const size_t out_b = ((size_t)n + m + 2) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
-    const size_t per_buf = (size_t)chunk * (in_b + out_b) + 17 * 256;
+    const size_t per_buf = ((size_t)chunk * (in_b + out_b) + 17 * 256 + 255) / 256 * 256; // buffer bases stay 256-byte aligned
     // three staging buffers: the copy-in of chunk c+2 does not have to wait for the solve of chunk c
     constexpr int NB = 3;
     int rc = ensure(&h->stage, &h->stage_bytes, NB * per_buf);

@@ -163,6 +163,66 @@ def test_c4_mpc_step_warm_start(engine, oracle):
     assert (r.exitflag == 1).all() and r.iter.mean() < 0.5 * cold.iter.mean()  # the warm start pays (287 -> 23)
 
 
+def test_c4_at_scale_cold_and_warm(engine, oracle):
+    """BASELINE.json config 4 (n=120, m=400, ms=120) at N = 2000, cold and warm-started from a neighbour's active set:
+    the team mode of the solve kernel (one CTA of four warps per problem, n > 64). Exit flags, iteration counts,
+    working sets in factor order, operation counts equal to the oracle's; x / lam / fval to the fp64 tolerances."""
+    N = 2000
+    b = generate_g1(N, 120, 400, 120, 96, seed=4404)
+    o, r = check_vs_oracle(engine, oracle, b, "C4 cold, N=2000")
+    assert (r.exitflag == 1).all() and np.abs(r.x - b.xref).max() < 1e-7
+    nb = generate_g1(N, 120, 400, 120, 96, seed=4404)
+    rng = np.random.default_rng(45)
+    nb.f = nb.f * (1 + 0.05 * rng.standard_normal(nb.f.shape))
+    rn = run_gpu(engine, nb)  # the neighbour's optimum (checked against the oracle on a sample)
+    on = oracle.solve(nb.slice(0, 100))
+    np.testing.assert_array_equal(rn.iter[:100], on.iter)
+    assert (rn.exitflag == 1).all()
+    b.sense[rn.lam > 1e-12] = 1
+    b.sense[rn.lam < -1e-12] = 3
+    o2, r2 = check_vs_oracle(engine, oracle, b, "C4 warm, N=2000", use_sense=True)
+    assert (r2.exitflag == 1).all() and r2.iter.mean() < 0.5 * r.iter.mean()
+
+
+@pytest.mark.parametrize("shape", [(66, 140, 0, 50), (95, 300, 40, 70), (96, 200, 96, 80), (127, 260, 3, 100),
+                                   (100, 600, 0, 75)])
+def test_team_mode_shapes(engine, oracle, shape):
+    """Sizes on both sides of the team kernel's three / four row segments (n + 1 = 67 .. 128), with m beyond 512."""
+    n, m, ms, na = shape
+    check_vs_oracle(engine, oracle, generate_g1(120, n, m, ms, na, seed=7000 + n + ms), f"team G1{shape}")
+
+
+def test_team_mode_rare_paths(engine, oracle):
+    """Singular steps, infeasibility, warm starts (incl. over-determined ones) and equalities at n > 64."""
+    b = generate_g1(100, 70, 160, 0, 50, seed=7101)
+    b.A[:, 80:160] = b.A[:, 0:80]; b.bupper[:, 80:160] = b.bupper[:, 0:80]; b.blower[:, 80:160] = b.blower[:, 0:80]
+    check_vs_oracle(engine, oracle, b, "team: duplicate rows")
+    b = generate_g1(60, 80, 200, 10, 60, seed=7102)
+    b.A[:, 1] = b.A[:, 0]; b.bupper[:, 1] = b.blower[:, 0] - 1.0; b.blower[:, 1] = b.blower[:, 0] - 2.0
+    o, r = check_vs_oracle(engine, oracle, b, "team: infeasible")
+    assert (r.exitflag == -1).all()
+    b = generate_g1(80, 72, 180, 12, 72, seed=7103)
+    check_vs_oracle(engine, oracle, b, "team: vertex (nact = n)")
+    rng = np.random.default_rng(7)
+    b.sense[:] = np.where(rng.random(b.sense.shape) < 0.5, rng.choice([1, 3], b.sense.shape), 0)
+    check_vs_oracle(engine, oracle, b, "team: over-determined warm start", use_sense=True)
+    b = generate_g1(80, 90, 220, 0, 60, seed=7104)
+    for p in range(b.N):
+        b.sense[p, np.nonzero(b.active_ref[p])[0][:5]] = 5
+    check_vs_oracle(engine, oracle, b, "team: equalities", use_sense=True)
+    check_vs_oracle(engine, oracle, generate_g1(60, 100, 250, 20, 80, kappa=1e8, seed=7105), "team: kappa 1e8", x_tol=1e-6)
+
+
+def test_odd_batch_sizes_keep_staging_aligned(engine, oracle):
+    """Host entry with odd N between the first-chunk and chunk sizes: every staging buffer must stay 8-byte aligned
+    (per-problem bytes = 3228 at n=10, m=20)."""
+    for N in (2001, 1025, 6143):
+        b = generate_g1(N, 10, 20, 0, 8, seed=900 + N)
+        r = run_gpu(engine, b)
+        assert (r.exitflag == 1).all() and np.abs(r.x - b.xref).max() < 1e-8
+    check_vs_oracle(engine, oracle, generate_g1(1031, 10, 20, 0, 8, seed=77), "odd N")
+
+
 def test_c5_mixed_sizes_one_call(cuda_lib, oracle):
     """BASELINE.json config 5 size mix through daqp_quadprog_batch: n in {8,16,...,128}, m = 4 n, the number of active
     constraints at the optimum drawn from U{0..n} (divergent iteration counts), one call for all shapes. fp64 (the
