@@ -277,7 +277,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     // n > 64: a warp per problem leaves the SM nearly empty (three problems fit at n = 120) -- a team of four warps per
     // problem instead (plain fp64 path; soft constraints / workspaces / shared matrices stay on the warp kernel)
     int team = 0;
-    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 128 && m <= 1024) team = 4;
+    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 32 * TEAM_WARPS) team = TEAM_WARPS;
     if (const char* tenv = getenv("DAQP_B200_TEAM")) { if (atoi(tenv) == 0) team = 0; }
     const size_t smem_solve_w = ldp_layout<T>(la, team), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
@@ -298,7 +298,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     const DevSettings<T> st = to_dev_settings<T>(settings);
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
-    const bool screening = sizeof(T) == 8 && !(tune & 2) && (m <= 256 || team);
+    const bool screening = sizeof(T) == 8 && !(tune & 2) && (team ? (m + 31) / 32 <= TEAM_SCREEN_MAX_GROUPS * TEAM_WARPS : m <= 256);
     for (int p0 = 0; p0 < N; p0 += chunk) {
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);

@@ -30,6 +30,7 @@
 //    that twelve problems stay resident per SM.
 #pragma once
 #include "common.cuh"
+#include "team_ops.cuh"
 #include <limits.h>
 #include <algorithm>
 
@@ -108,20 +109,6 @@ struct LdpArgs {
 };
 
 // Fills the layout fields of LdpArgs; returns the bytes of shared memory one warp needs.
-// Mailbox + scratch of a team (TW warps solving one problem): the leader warp runs the active-set state machine and
-// posts the heavy phases as commands; see the team section of Warp.
-struct TeamBox {
-    int cmd, a0, a1, p;
-    double alpha, fval;      // C1 recurrence carried between diagonal blocks of a removal; |u|^2 for the screening bound
-    double rv[8], rv2[8];    // per-warp partial results (values)
-    int rk[8], rs[8];        // per-warp partial results (keys / flags)
-};
-constexpr int TEAM_BOX_BYTES = 256;
-constexpr int TEAM_WARPS = 4;    // warps per problem in team mode (factor rows <= 128)
-constexpr int TEAM_MAX_CTAS = 3; // resident teams per SM the kernel is compiled for (__launch_bounds__)
-static_assert(sizeof(TeamBox) <= TEAM_BOX_BYTES, "TeamBox grew past its slot");
-enum { TC_EXIT = 0, TC_FWD, TC_BWD, TC_REMOVE, TC_DOTS, TC_PRIMAL, TC_SCAN32, TC_SCAN64 };
-
 template <typename T>
 inline size_t ldp_layout(LdpArgs<T>& a, int team = 0) {
     const int V = VecOf<T>::N, cap = a.cap;
@@ -222,8 +209,6 @@ struct Warp {
     int lsw;             // which of the two lambda buffers currently is `lam` (the reference swaps pointers)
     T fval, soft_slack;
     int* pst_id; T* pst_lam;
-    int wid;             // team mode: this warp's index in the team (0 = leader)
-    TeamBox* box;        // team mode: mailbox at the start of the CTA's shared memory
     // daqp_ldp loop state (daqp.c:7-10), kept across step() calls
     int iter, tried_repair, cycle_counter;
     bool do_activate;
@@ -283,9 +268,7 @@ struct Warp {
     __device__ __forceinline__ void forward_sweep(T (&x)[NV], int rlo, int len) {
         if constexpr (TW > 1) { // the vector goes through the team's scratch: thread i of the CTA owns element i
             vstore(x, team_tmp(), 0, len);
-            post(TC_FWD, rlo, len);
-            team_forward(rlo, len);
-            team_bar();
+            team_run(TC_FWD, rlo, len);
             vload(x, team_tmp(), len);
         } else {
         const T* row[NV]; // &L[i][0] for this lane's rows
@@ -313,9 +296,7 @@ struct Warp {
     __device__ __forceinline__ void backward_sweep(T (&x)[NV], int len) {
         if constexpr (TW > 1) {
             vstore(x, team_tmp(), 0, len);
-            post(TC_BWD, len, 0);
-            team_backward(len);
-            team_bar();
+            team_run(TC_BWD, len, 0);
             vload(x, team_tmp(), len);
         } else
 #pragma unroll
@@ -385,7 +366,7 @@ struct Warp {
             }
         }
         if (kk > 0) {
-            if constexpr (TW > 1) { post(TC_DOTS, add, kk); team_dots(add, kk); team_bar(); }
+            if constexpr (TW > 1) team_run(TC_DOTS, add, kk);
             // l_j = M_{WS[j]} . m_add: per-lane partial products of a chunk's rows are parked in the consumed buffer and
             // summed with a transposed read (lane = (row, quarter)) instead of RB full shuffle reductions.
             if constexpr (TW == 1) {
@@ -461,7 +442,7 @@ struct Warp {
         int* ws = WS();
         if (lane == 0) sense()[ws[r]] &= ~B_ACTIVE;
         if constexpr (TW > 1) {
-            if (r != kk - 1) { post(TC_REMOVE, r, kk); team_remove(r, kk); team_bar(); }
+            if (r != kk - 1) team_run(TC_REMOVE, r, kk);
         } else
         if (r != kk - 1) {
             const int nu = kk - r - 1; // trailing rows; trailing row s is old row r+1+s and becomes row r+s
@@ -683,12 +664,10 @@ struct Warp {
     __device__ __forceinline__ void compute_primal() {
         if constexpr (TW > 1) {
             const int kq = uni(k);
-            post(TC_PRIMAL, kq, lsw);
-            team_primal(kq, lsw);
-            team_bar();
+            team_run(TC_PRIMAL, kq, lsw);
             T s = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < TW; w2++) s += (T)box->rv[w2]; // fixed order: every run sums the same way
+            for (int w2 = 0; w2 < TW; w2++) s += (T)tbox()->rv[w2]; // fixed order: every run sums the same way
             fval = uni(s);
             __syncwarp();
             return;
@@ -971,357 +950,54 @@ struct Warp {
         return key == INT_MAX ? -1 : key;
     }
 
-    // =====================================================================================================================
-    // Team mode (TW > 1): the phases below are executed by ALL warps of the CTA. Thread tid = 32 wid + lane owns row tid
-    // of the factor and element tid of the vectors; a named barrier (id 1, 32 TW threads) separates the stages. Every
-    // recurrence keeps the per-element operation order of the single-warp code above (and so of the reference): only
-    // WHICH thread executes an update changes.
-    // =====================================================================================================================
-    __device__ __forceinline__ void team_bar() const { asm volatile("bar.sync 1, %0;" ::"n"(32 * TW) : "memory"); }
-    __device__ __forceinline__ T* team_tmp() const { return reinterpret_cast<T*>(reinterpret_cast<char*>(box) + a.otmp); }
-    __device__ __forceinline__ T* team_pv() const { return reinterpret_cast<T*>(reinterpret_cast<char*>(box) + a.opv); }
-    __device__ __forceinline__ T* team_bv() const { return reinterpret_cast<T*>(reinterpret_cast<char*>(box) + a.obv); }
-    __device__ __forceinline__ T* team_side() const { return reinterpret_cast<T*>(reinterpret_cast<char*>(box) + a.oside); }
-    // leader: publish a command, then meet the helpers at the barrier that starts the phase
-    __device__ __forceinline__ void post(int cmd, int a0, int a1) {
-        if (lane == 0) { volatile TeamBox* b = box; b->cmd = cmd; b->a0 = a0; b->a1 = a1; }
-        team_bar();
+    // ---- team mode (TW > 1), leader side: the heavy phases live in team_ops.cuh; the leader posts a command, runs its own
+    // share of the phase (wid = 0) and meets the helpers at the closing barrier.
+    static __device__ __forceinline__ TeamBox* tbox() {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        return reinterpret_cast<TeamBox*>(smem_raw);
     }
-    // helpers (warps 1 .. TW-1): wait for a command, run this warp's share, meet the leader at the closing barrier
-    __device__ __noinline__ void helper_loop() {
-        for (;;) {
-            team_bar();
-            const volatile TeamBox* b = box;
-            const int cmd = b->cmd, a0 = b->a0, a1 = b->a1;
-            if (cmd == TC_EXIT) return;
-            p = b->p;
-            switch (cmd) {
-                case TC_FWD: team_forward(a0, a1); break;
-                case TC_BWD: team_backward(a0); break;
-                case TC_REMOVE: team_remove(a0, a1); break;
-                case TC_DOTS: team_dots(a0, a1); break;
-                case TC_PRIMAL: team_primal(a0, a1); break;
-                case TC_SCAN32: team_scan32(); break;
-                default: team_scan64(); break;
-            }
-            team_bar();
+    __device__ __forceinline__ T* team_tmp() const {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        return reinterpret_cast<T*>(smem_raw + a.otmp);
+    }
+    __device__ __forceinline__ void team_run(int cmd, int a0, int a1) {
+        if (lane == 0) { TeamBox* b = tbox(); b->cmd = cmd; b->a0 = a0; b->a1 = a1; }
+        team_bar<TW>();
+        team_dispatch<T, TW, NG>(cmd, lane, 0, a0, a1);
+        team_bar<TW>();
+    }
+    __device__ __forceinline__ void team_exit() {
+        if (lane == 0) tbox()->cmd = TC_EXIT;
+        team_bar<TW>();
+    }
+    // once per launch: where the per-problem block lives (byte offsets from the start of the CTA's shared memory)
+    __device__ __forceinline__ void team_publish_layout() {
+        if (lane == 0) {
+            TeamBox* b = tbox();
+            const int w = (int)sizeof(T), o = (int)a.team_prefix;
+            b->oL = o; b->oD = o + a.oD * w; b->olamA = o + a.olamA * w; b->olamB = o + a.olamB * w;
+            b->oWS = o + a.oWS * 4; b->osense = o + a.osense; b->ou = o + a.ou * w; b->ou32 = o + a.ou32 * 4;
+            b->otmp = (int)a.otmp; b->opv = (int)a.opv; b->obv = (int)a.obv; b->oside = (int)a.oside;
+            b->cap = a.cap; b->n = a.n; b->m = a.m; b->ldm = a.ldm; b->ldn = a.ldn; b->tune = a.tune;
+            b->primal_tol = (double)a.st.primal_tol;
         }
     }
-
-    // tmp <- L^-1 tmp on rows [rlo, len) (rows < rlo hold the solution already). Blocked by 32: the warp that owns the
-    // rows of block b finishes them with shuffle-broadcast pivots, publishes them, and the warps below apply the block's
-    // pivots to their own rows -- ascending pivots per row, the order of factorization.c:86-92 / auxiliary.c:334-337.
-    __device__ __forceinline__ void team_forward(int rlo, int len) {
-        T* tmp = team_tmp();
-        const int i = 32 * wid + lane;
-        const bool mine = i >= rlo && i < len;
-        T x = (i < len) ? tmp[i] : (T)0;
-        const T* Li = L() + loff(min(i, a.cap - 1));
-        const int nb = (len + 30) >> 5; // blocks of the pivots 0 .. len-2
-        for (int b = 0; b < nb; b++) {
-            const int j0 = 32 * b, j1 = min(j0 + 32, len - 1);
-            if (j0 + 32 > rlo) { // the block holds unsolved rows (uniform)
-                if (wid == b) {
-                    for (int j = j0; j < j1; j++) {
-                        const T xj = __shfl_sync(FULL, x, j - j0);
-                        if (mine && i > j) x -= Li[j] * xj;
-                    }
-                    if (mine) tmp[i] = x;
-                }
-                team_bar();
-            }
-            if (wid > b && mine) {
-#pragma unroll 4
-                for (int j = j0; j < j1; j++) x -= Li[j] * tmp[j];
-            }
+    // once per problem: its global arrays (the helpers see them with the first command of the problem)
+    __device__ __forceinline__ void team_publish_problem() {
+        if (lane == 0) {
+            TeamBox* b = tbox();
+            b->p = p;
+            b->Mr = Mr(); b->Mt = Mt(); b->du = du(); b->dl = dl(); b->sc = sc();
+            b->Mt32 = a.Mt32 ? reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32 : nullptr;
         }
-        if (mine && wid >= nb) tmp[i] = x; // rows below the last pivot block (the others were stored by their own block)
-    }
-
-    // tmp <- L^-T tmp ; descending pivots (auxiliary.c:343-352, 363-370)
-    __device__ __forceinline__ void team_backward(int len) {
-        T* tmp = team_tmp();
-        const int i = 32 * wid + lane;
-        T x = (i < len) ? tmp[i] : (T)0;
-        const T* Lp = L();
-        for (int b = (len - 1) >> 5; b >= 0; b--) {
-            const int j1 = min(32 * b + 31, len - 1), j0 = max(32 * b, 1); // pivots j1 .. j0 of this block
-            if (wid == b) {
-                const T* Lj = Lp + loff(j1) + i;
-                for (int j = j1; j >= j0; j--) {
-                    const T xj = __shfl_sync(FULL, x, j - 32 * b);
-                    if (i < j) x -= Lj[0] * xj;
-                    Lj -= j - 1;
-                }
-                if (i < len) tmp[i] = x;
-            }
-            if (b > 0) {
-                team_bar();
-                if (wid < b) {
-                    const T* Lj = Lp + loff(j1) + i;
-#pragma unroll 4
-                    for (int j = j1; j >= j0; j--) { x -= Lj[0] * tmp[j]; Lj -= j - 1; }
-                }
-            }
-        }
-    }
-
-    // a3 for a team: delete row / column r of the factor of size kk (factorization.c:112-151). Thread s owns trailing row
-    // s (old row r+1+s), walks along it and writes every element straight to its compacted position (one row up, one
-    // column left). The pivots of block b are finished by warp b (Gill-Golub-Murray-Saunders C1 recurrences in the
-    // reference's order, lock-step), published (p_t, beta_t), and applied by the warps below. The first thread of a warp
-    // writes into the row of the LAST thread of the warp above, which runs unsynchronised: its 32 values of a stage are
-    // parked in a side buffer and put in place after the next barrier, when that row's reads of the stage are over.
-    __device__ __forceinline__ void team_remove(int r, int kk) {
-        T* Lp = L();
-        T* Dp = D();
-        T* pv = team_pv();
-        T* bv = team_bv();
-        const int nu = kk - r - 1, s = 32 * wid + lane;
-        const bool act = s < nu;
-        const int io = min(r + 1 + s, a.cap - 1);
-        const T* src = Lp + loff(io) + r + 1; // old element (s, t) = src[t]
-        T* dst = Lp + loff(io - 1) + r;       // its compacted position = dst[t]
-        T w = act ? src[-1] : (T)0;           // removed column
-        // columns left of the removed one: row i moves up by one; thread j moves column j of every row
-        if (s < r) {
-            T* f = Lp + loff(r + 1) + s;
-            for (int i = r + 1; i < kk; i++) { f[-(i - 1)] = f[0]; f += i; }
-        }
-        team_bar(); // every removed-column element is in a register before its slot is overwritten
-        const bool boundary = wid > 0 && lane == 0;
-        T* side = team_side() + 32 * (wid > 0 ? wid - 1 : 0);
-        int pend0 = -1, pend1 = 0; // parked stage [pend0, pend1)
-        const int nblk = (nu + 31) >> 5;
-        for (int b = 0; b < nblk; b++) {
-            const int t0 = 32 * b, t1 = min(t0 + 32, nu);
-            if (wid == b) {
-                T alpha = (b == 0) ? Dp[r] : (T)box->alpha;
-                __syncwarp();
-                for (int t = t0; t < t1; t++) {
-                    const T pvt = __shfl_sync(FULL, w, t - t0);
-                    const T Dold = Dp[r + 1 + t];
-                    const T dbar = Dold + alpha * pvt * pvt;
-                    const T rdb = frcp(dbar);
-                    const T beta = pvt * alpha * rdb;
-                    alpha = Dold * alpha * rdb;
-                    if (lane == 0) Dp[r + t] = dbar;
-                    if (lane == t - t0) { pv[t] = pvt; bv[t] = beta; }
-                    if (act && t < s) {
-                        const T lv = src[t];
-                        const T qs = w - pvt * lv;
-                        w = qs;
-                        dst[t] = lv + beta * qs;
-                    }
-                    __syncwarp();
-                }
-                if (lane == 0) box->alpha = (double)alpha;
-            }
-            team_bar();
-            if (boundary && pend0 >= 0) { for (int t = pend0; t < pend1; t++) dst[t] = side[t - pend0]; pend0 = -1; }
-            if (wid > b) { // whole warp: uniform trip count, lanes beyond the trailing rows idle
-                for (int c0 = t0; c0 < t1; c0 += 8) {
-                    T lv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e++) lv[e] = (act && c0 + e < t1) ? src[c0 + e] : (T)0;
-                    __syncwarp(); // the lane above has read these columns of its row before this lane overwrites them
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const int t = c0 + e;
-                        if (act && t < t1) {
-                            const T qs = w - pv[t] * lv[e];
-                            w = qs;
-                            const T out = lv[e] + bv[t] * qs;
-                            if (boundary) side[t - t0] = out; else dst[t] = out;
-                        }
-                    }
-                }
-                if (boundary && act) { pend0 = t0; pend1 = t1; }
-            }
-        }
-        team_bar();
-        if (boundary && pend0 >= 0) for (int t = pend0; t < pend1; t++) dst[t] = side[t - pend0];
-    }
-
-    // l_j = M_{WS[j]} . m_add for j < kk, into row kk of the factor (factorization.c:59-84): the rows are dealt to the
-    // warps in batches of DB, every batch one transposed butterfly instead of DB full reductions.
-    __device__ __forceinline__ void team_dots(int add, int kk) {
-        constexpr int DB = 8;
-        const char* M = Mr() + (size_t)(V * lane) * sizeof(T);
-        const unsigned rstride = a.ldn * (unsigned)sizeof(T);
-        T mi[NG][V];
-        bool okg[NG];
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-            okg[g] = V * (lane + 32 * g) < a.ldn;
-#pragma unroll
-            for (int e = 0; e < V; e++) mi[g][e] = 0;
-            if (okg[g]) ldg_vec<T>(reinterpret_cast<const T*>(M + (size_t)add * rstride) + 32 * V * g, mi[g]);
-        }
-        const int* ws = WS();
-        T* Lk = L() + loff(kk);
-        for (int j0 = DB * wid; j0 < kk; j0 += DB * TW) {
-            T t[DB][NG][V];
-#pragma unroll
-            for (int rr = 0; rr < DB; rr++) {
-                const char* row = M + (size_t)(unsigned)ws[min(j0 + rr, kk - 1)] * rstride;
-#pragma unroll
-                for (int g = 0; g < NG; g++) {
-#pragma unroll
-                    for (int e = 0; e < V; e++) t[rr][g][e] = 0;
-                    if (okg[g]) ldg_vec<T>(reinterpret_cast<const T*>(row) + 32 * V * g, t[rr][g]);
-                }
-            }
-            T pj[DB];
-#pragma unroll
-            for (int rr = 0; rr < DB; rr++) {
-                pj[rr] = 0;
-#pragma unroll
-                for (int g = 0; g < NG; g++)
-#pragma unroll
-                    for (int e = 0; e < V; e++) pj[rr] += t[rr][g][e] * mi[g][e];
-            }
-            const T total = warp_sum_multi<DB>(pj, lane);
-            const int jr = j0 + multi_index<DB>(lane);
-            if ((lane & (32 / DB - 1)) == 0 && jr < kk) Lk[jr] = total;
-        }
-    }
-
-    // a7 for a team: u = -sum_i lam*_i row(WS[i]), thread c owns column c and adds the rows in index order (the order of
-    // auxiliary.c:54-68); UNR rows in flight per thread. Per-warp partial |u|^2 goes to the box.
-    __device__ __forceinline__ void team_primal(int kk, int lsw_) {
-        constexpr int UNR = 16;
-        const int c = 32 * wid + lane;
-        const bool have = c < a.ldn;
-        const T* ls = S + (lsw_ ? a.olamA : a.olamB);
-        const int* ws = WS();
-        const T* col = reinterpret_cast<const T*>(Mr()) + min(c, a.ldn - 1);
-        T acc = 0;
-        for (int i0 = 0; i0 < kk; i0 += UNR) {
-            T v[UNR];
-#pragma unroll
-            for (int e = 0; e < UNR; e++) v[e] = (have && i0 + e < kk) ? __ldg(col + (size_t)(unsigned)ws[min(i0 + e, kk - 1)] * a.ldn) : (T)0;
-#pragma unroll
-            for (int e = 0; e < UNR; e++) if (i0 + e < kk) acc -= v[e] * ls[i0 + e];
-        }
-        if (have) { u()[c] = acc; u32()[c] = (float)acc; }
-        const T part = warp_sum(have ? acc * acc : (T)0);
-        if (lane == 0) box->rv[wid] = (double)part;
-    }
-
-    // a8 for a team, fp32 screening (see scan_screen for the error bound and the decision rule): the 32-row groups are
-    // dealt round-robin to the warps (group g = wid + TW r, row = 32 g + lane); quads of columns stream through PF
-    // register buffers per lane. Per-warp result -> box: rv = best, rk = key (INT_MAX: none), rv2 = runner-up, rs = sure.
-    template <int NR>
-    __device__ __forceinline__ void team_scan32_n() {
-        constexpr int PF = 3;
-        int rowi[NR];
-        bool own[NR];
-        float acc[NR];
-        double bu[NR], bl[NR], bs[NR];
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-            rowi[r] = 32 * (wid + TW * r) + lane;
-            own[r] = rowi[r] < a.m;
-            acc[r] = 0.f;
-            bu[r] = bl[r] = bs[r] = 0;
-            if (own[r]) { bu[r] = __ldg(du() + rowi[r]); bl[r] = __ldg(dl() + rowi[r]); bs[r] = __ldg(sc() + rowi[r]); }
-        }
-        const unsigned slab = (unsigned)a.m * 16u; // bytes of one quad of columns
-        const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)pmat() * a.sMt32;
-        const int nq = (a.n + 3) >> 2;
-        const uint64_t pol = (a.tune & 8) ? policy_evict_first() : policy_evict_last();
-        float buf[PF][NR][4];
-#pragma unroll
-        for (int i = 0; i < PF; i++)
-#pragma unroll
-            for (int r = 0; r < NR; r++) {
-#pragma unroll
-                for (int e = 0; e < 4; e++) buf[i][r][e] = 0.f;
-                ldg_vec_pred<float>(src + (size_t)min(i, nq - 1) * slab + 16u * rowi[r], buf[i][r], pol, own[r] && i < nq);
-            }
-        const unsigned ub = smem_u32(u32());
-        for (int q0 = 0; q0 < nq; q0 += PF) {
-#pragma unroll
-            for (int i = 0; i < PF; i++) {
-                const int q = q0 + i;
-                if (q < nq) {
-                    float uq[4];
-                    lds_vec<float>(ub + 16 * q, uq);
-                    const bool more = q + PF < nq;
-                    const char* nx = src + (size_t)min(q + PF, nq - 1) * slab;
-#pragma unroll
-                    for (int r = 0; r < NR; r++) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) acc[r] += buf[i][r][e] * uq[e];
-                        ldg_vec_pred<float>(nx + 16u * rowi[r], buf[i][r], pol, own[r] && more);
-                    }
-                }
-            }
-        }
-        const double unorm = (double)sqrtf((float)box->fval) * 1.0001 + 1e-22;
-        const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * unorm;
-        const double ep = -(double)a.st.primal_tol;
-        const unsigned char* se = sense();
-        double best = 1e300, second = 1e300;
-        int key = INT_MAX;
-        bool best_sure = false;
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-            const double mu = (double)acc[r];
-            const double cu = bu[r] - mu, cl = mu - bl[r];
-            const bool lower = cl < cu;
-            const double cand = lower ? cl : cu;
-            const double bound = ep * bs[r];
-            const bool possible = own[r] && !(se[min(rowi[r], a.m - 1)] & (B_ACTIVE + B_IMMUTABLE)) && cand - delta < bound;
-            const bool nb = possible && (cand < best || (cand == best && 2 * rowi[r] < key)); // groups are not in row order per lane
-            second = nb ? best : ((possible && cand < second) ? cand : second);
-            best_sure = nb ? (cand + delta < bound) : best_sure;
-            key = nb ? 2 * rowi[r] + (int)lower : key;
-            best = nb ? cand : best;
-        }
-        double wbest = best;
-        int wkey = key;
-        warp_argmin(wbest, wkey);
-        wkey = uni(wkey);
-        wbest = uni(wbest);
-        double other = (key == wkey) ? second : best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) other = fmin(other, __shfl_xor_sync(FULL, other, o));
-        const bool sure = __any_sync(FULL, key == wkey && best_sure);
-        if (lane == 0) { box->rv[wid] = wbest; box->rk[wid] = wkey; box->rv2[wid] = other; box->rs[wid] = sure ? 1 : 0; }
-    }
-    __device__ __forceinline__ void team_scan32() {
-        if constexpr (sizeof(T) == 8) {
-            switch ((((a.m + 31) >> 5) + TW - 1) / TW) {
-                case 1: team_scan32_n<1>(); break;
-                case 2: team_scan32_n<2>(); break;
-                case 3: team_scan32_n<3>(); break;
-                case 4: team_scan32_n<4>(); break;
-                case 5: team_scan32_n<5>(); break;
-                case 6: team_scan32_n<6>(); break;
-                case 7: team_scan32_n<7>(); break;
-                default: team_scan32_n<8>(); break;
-            }
-        }
-    }
-    // exact scan in T: groups of 32 V rows of the column-major matrix, dealt round-robin to the warps
-    __device__ __forceinline__ void team_scan64() {
-        constexpr int GR = 32 * V;
-        T best = 0;
-        int key = INT_MAX;
-        for (int base = wid * GR; base < a.m; base += TW * GR) scan_rows<1, 8>(base, best, key);
-        warp_argmin(best, key);
-        if (lane == 0) { box->rv[wid] = (double)best; box->rk[wid] = key; }
     }
     // leader: run the screening (then, if it cannot name the row, the exact scan) on the whole team and combine
     __device__ __forceinline__ int team_scan_leader() {
+        TeamBox* box = tbox();
         if constexpr (sizeof(T) == 8) {
             if (a.Mt32 != nullptr) {
                 if (lane == 0) box->fval = (double)fval;
-                post(TC_SCAN32, 0, 0);
-                team_scan32();
-                team_bar();
+                team_run(TC_SCAN32, 0, 0);
                 double wb = 1e300, other = 1e300;
                 int wk = INT_MAX, win = 0;
 #pragma unroll
@@ -1342,9 +1018,7 @@ struct Warp {
                 if (ok) return wk;
             }
         }
-        post(TC_SCAN64, 0, 0);
-        team_scan64();
-        team_bar();
+        team_run(TC_SCAN64, 0, 0);
         T wb = 0;
         int wk = INT_MAX;
 #pragma unroll
@@ -1590,10 +1264,18 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
     w.S = reinterpret_cast<T*>(smem_raw + (TW > 1 ? (size_t)a.team_prefix : (size_t)a.per_warp_bytes * wib));
     w.pst_id = a.pst_id + (size_t)gw * a.cap;
     w.pst_lam = a.pst_lam + (size_t)gw * a.cap;
-    w.wid = wib;
-    w.box = reinterpret_cast<TeamBox*>(smem_raw);
     if constexpr (TW > 1) {
-        if (wib != 0) { w.helper_loop(); return; }
+        if (wib != 0) { // helper warp: wait for a command, run this warp's share, meet the leader at the closing barrier
+            const volatile TeamBox* b = reinterpret_cast<const volatile TeamBox*>(smem_raw);
+            for (;;) {
+                team_bar<TW>();
+                const int cmd = b->cmd, a0 = b->a0, a1 = b->a1;
+                if (cmd == TC_EXIT) return;
+                team_dispatch<T, TW, (NV + 1) / 2>(cmd, lane, wib, a0, a1);
+                team_bar<TW>();
+            }
+        }
+        w.team_publish_layout();
     }
 
     // Structured on purpose (see modify()): a problem loop around an iteration loop, no loop-carried control flags.
@@ -1604,7 +1286,7 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
         pq = uni(pq); // lanes other than 0 hold 0 and queue indices are non-negative
         if (pq >= a.P) break;
         w.p = pq;
-        if constexpr (TW > 1) { if (lane == 0) w.box->p = pq; } // the helpers read it with the next command
+        if constexpr (TW > 1) w.team_publish_problem(); // the helpers read it with the next command
         if constexpr (EXT) w.pm = a.grp > 1 ? pq / a.grp : pq;
         const int sflag = uni(a.setup_flag[pq]); // loaded values are divergent in ptxas' eyes until proven otherwise
         if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) {
@@ -1731,7 +1413,7 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
         }
         }
     }
-    if constexpr (TW > 1) w.post(TC_EXIT, 0, 0); // releases the helpers
+    if constexpr (TW > 1) w.team_exit(); // releases the helpers
 }
 
 } // namespace dq

@@ -59,9 +59,12 @@ def _rng(seed: int) -> np.random.Generator:
 
 
 def generate_g1(N: int, n: int, m: int, ms: int, n_active: int, kappa: float = 100.0, seed: int = SEED_BASE,
-                random_nactive: bool = False) -> QPBatch:
+                random_nactive: bool = False, near_parallel: tuple | None = None) -> QPBatch:
     """Batched ``generate_test_QP`` (utils.jl:3-53). ``random_nactive`` draws nActive ~ U{0..n_active} per problem
-    (config C5: divergent iteration counts)."""
+    (config C5: divergent iteration counts). ``near_parallel = (pairs, eps)`` makes `pairs` general rows that are active
+    at the constructed optimum copies of another active row plus eps * N(0,1): the optimum sits on nearly dependent
+    constraints, which is what drives the reference's ill-conditioning repairs (pivot swaps, refactor-on-exit,
+    refinement: daqp.c:28-56, auxiliary.c:379-396)."""
     assert m >= ms and n >= 2 and n_active <= m
     rng = _rng(seed)
     eig = np.ones((N, n))
@@ -88,6 +91,16 @@ def generate_g1(N: int, n: int, m: int, ms: int, n_active: int, kappa: float = 1
     is_lo = (pos >= nau[:, None]) & (pos < nact[:, None])
     inactive = pos >= nact[:, None]
     sgn = is_up.astype(np.float64) - is_lo.astype(np.float64)
+
+    if near_parallel is not None:
+        pairs, eps = near_parallel
+        for p in range(N):
+            act = np.nonzero((sgn[p] != 0) & (np.arange(m) >= ms))[0]
+            for q in range(min(pairs, len(act) // 2)):
+                i, j = act[2 * q], act[2 * q + 1]
+                M[p, j] = M[p, i] + eps * rng.standard_normal(n)
+                sgn[p, j] = sgn[p, i]  # both on the same side, or the pair would pin a slab of width ~eps
+        is_up, is_lo = sgn > 0, sgn < 0
 
     lam = rng.random((N, m)) * (sgn != 0)
     u = -np.einsum("bmn,bm->bn", M, sgn * lam)           # u = -Ma' lam

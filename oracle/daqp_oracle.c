@@ -55,6 +55,7 @@ typedef struct {
     /* pivoting stack (replaces the recursion of auxiliary.c:379-396) */
     int *pstack_id; real *pstack_lam;
     int n_scan, n_add, n_remove, n_csp;
+    int n_pivot, n_refine, n_refactor, n_cycle; /* rare paths: pivot_last swaps, refinements, refactor-on-exit, cycle repairs */
 } Ldp;
 
 #define Lij(w, i, j) ((w)->L[(size_t)(i) * (w)->cap + (j)])
@@ -211,6 +212,7 @@ static void pivot_last(Ldp *w) {
             w->pstack_id[depth] = w->WS[r];
             w->pstack_lam[depth] = w->lam[r];
             depth++;
+            w->n_pivot++;
             if (!raw_remove(w, r)) continue; /* nested pivot_last inside remove_constraint */
         }
         /* a pivot_last invocation (or a remove_constraint that turned singular) returns here */
@@ -425,6 +427,7 @@ static int ldp_solve(Ldp *w) {
                     for (int i = 1; i < w->k; i++) if (w->D[i] < min_D) min_D = w->D[i];
                     if (w->k > 2 && tried_repair != 1 && min_D < w->st->refactor_tol) {
                         tried_repair = 1;
+                        w->n_refactor++;
                         for (int i = 0; i < w->k; i++) {
                             if (w->lam[i] >= 0) w->sense[w->WS[i]] &= ~B_LOWER;
                             else w->sense[w->WS[i]] |= B_LOWER;
@@ -434,6 +437,7 @@ static int ldp_solve(Ldp *w) {
                         continue;
                     }
                     if (w->k > 0 && min_D < w->st->pivot_tol) {
+                        w->n_refine++;
                         refine_active(w);
                         if (add_infeasible(w)) continue;
                     }
@@ -444,6 +448,7 @@ static int ldp_solve(Ldp *w) {
                     if (cycle_counter++ > w->st->cycle_tol) {
                         if (tried_repair == 1) { exitflag = EXIT_CYCLE; break; }
                         tried_repair = 1;
+                        w->n_cycle++;
                         reset_ws(w);
                         activate_constraints(w);
                         cycle_counter = 0;
@@ -604,14 +609,19 @@ void orc_quadprog(OrcResult *res, const OrcProblem *qp, const OrcSettings *setti
     memset(w, 0, sizeof(W));
     if (settings == NULL) { orc_default_settings(&defaults); settings = &defaults; }
     res->setup_time = 0; res->solve_time = 0;
-    if (trace) { trace->n_active = 0; trace->n_scan = trace->n_add = trace->n_remove = trace->n_csp = 0; }
+    if (trace) {
+        trace->n_active = 0; trace->n_scan = trace->n_add = trace->n_remove = trace->n_csp = 0;
+        trace->n_pivot = trace->n_refine = trace->n_refactor = trace->n_cycle = 0;
+    }
 
     if (qp->sense != NULL)
         for (int i = 0; i < m; i++) { if (qp->sense[i] & B_SOFT) ns++; if (qp->sense[i] & B_BINARY) nb++; }
     if (nb > 0 || qp->nh > 1 || qp->problem_type != 0 || qp->H == NULL) { res->exitflag = EXIT_UNSUPPORTED; return; }
 
     w->n = n; w->m = m; w->ms = ms; w->cap = n + ns + 1; w->st = settings;
-    w->lam = malloc(sizeof(real) * w->cap); w->lam_star = malloc(sizeof(real) * w->cap);
+    /* zeroed: after an exit inside the add branch (EXIT_CYCLE) the reference reports the entry of the entering row from
+     * the multiplier buffer it has not written yet (api.c:463-466 reads lam_star after the swap of auxiliary.c:159-160) */
+    w->lam = calloc(w->cap, sizeof(real)); w->lam_star = calloc(w->cap, sizeof(real));
     w->D = malloc(sizeof(real) * w->cap); w->xl = malloc(sizeof(real) * w->cap); w->zl = malloc(sizeof(real) * w->cap);
     w->L = malloc(sizeof(real) * (size_t)w->cap * w->cap); w->WS = malloc(sizeof(int) * w->cap);
     w->pstack_id = malloc(sizeof(int) * w->cap); w->pstack_lam = malloc(sizeof(real) * w->cap);
@@ -753,6 +763,7 @@ solve: /* api.c:8-59 */
         if (trace->ws) for (int i = 0; i < w->k; i++) trace->ws[i] = w->WS[i];
         if (trace->sense_out) for (int i = 0; i < m; i++) trace->sense_out[i] = w->sense[i];
         trace->n_scan = w->n_scan; trace->n_add = w->n_add; trace->n_remove = w->n_remove; trace->n_csp = w->n_csp;
+        trace->n_pivot = w->n_pivot; trace->n_refine = w->n_refine; trace->n_refactor = w->n_refactor; trace->n_cycle = w->n_cycle;
     }
     ldp_free(w);
     return;
@@ -798,7 +809,9 @@ static void minrep_open(Ldp *w, OrcSettings *st, const real *A, const real *b, i
     memset(w, 0, sizeof(*w));
     orc_default_settings(st);
     w->n = n; w->m = m; w->ms = ms; w->cap = n + 1; w->st = st;
-    w->lam = malloc(sizeof(real) * w->cap); w->lam_star = malloc(sizeof(real) * w->cap);
+    /* zeroed: after an exit inside the add branch (EXIT_CYCLE) the reference reports the entry of the entering row from
+     * the multiplier buffer it has not written yet (api.c:463-466 reads lam_star after the swap of auxiliary.c:159-160) */
+    w->lam = calloc(w->cap, sizeof(real)); w->lam_star = calloc(w->cap, sizeof(real));
     w->D = malloc(sizeof(real) * w->cap); w->xl = malloc(sizeof(real) * w->cap); w->zl = malloc(sizeof(real) * w->cap);
     w->L = malloc(sizeof(real) * (size_t)w->cap * w->cap); w->WS = malloc(sizeof(int) * w->cap);
     w->pstack_id = malloc(sizeof(int) * w->cap); w->pstack_lam = malloc(sizeof(real) * w->cap);
@@ -903,8 +916,9 @@ static void packed_one(PackedJob *J, int p) {
     J->exitflag[p] = r.exitflag;
     if (J->iter) J->iter[p] = r.iter;
     if (J->trace_counts) {
-        J->trace_counts[4 * p + 0] = tr.n_scan; J->trace_counts[4 * p + 1] = tr.n_add;
-        J->trace_counts[4 * p + 2] = tr.n_remove; J->trace_counts[4 * p + 3] = tr.n_csp;
+        int *tc = J->trace_counts + 8 * (size_t)p;
+        tc[0] = tr.n_scan; tc[1] = tr.n_add; tc[2] = tr.n_remove; tc[3] = tr.n_csp;
+        tc[4] = tr.n_pivot; tc[5] = tr.n_refine; tc[6] = tr.n_refactor; tc[7] = tr.n_cycle;
     }
 }
 

@@ -64,6 +64,11 @@ typedef struct {
     int n_add;        /* LDL row appends (daqp_update_LDL_add)                        */
     int n_remove;     /* LDL row deletions (daqp_update_LDL_remove incl. last-row)    */
     int n_csp;        /* CSP solves                                                    */
+    /* rare control paths of daqp_ldp (so that a test can assert they were taken) */
+    int n_pivot;      /* daqp_pivot_last swaps (auxiliary.c:379-396)                   */
+    int n_refine;     /* daqp_refine_active calls (daqp.c:52-56)                       */
+    int n_refactor;   /* refactor-on-exit repairs (daqp.c:33-46)                       */
+    int n_cycle;      /* cycle-guard repairs (daqp.c:67-81)                            */
 } OrcTrace;
 
 void orc_default_settings(OrcSettings *s);
@@ -80,7 +85,7 @@ double orc_solve_packed(int N, int n, int m, int ms,
                         const orc_real *bupper, const orc_real *blower, const int *sense,
                         const OrcSettings *settings,
                         orc_real *x, orc_real *lam, orc_real *fval, int *exitflag, int *iter,
-                        int *trace_counts /* [N][4] scan,add,remove,csp or NULL */,
+                        int *trace_counts /* [N][8] scan,add,remove,csp,pivot,refine,refactor,cycle or NULL */,
                         int nthreads);
 
 /* daqp_primal_init_active / daqp_dual_init_active (api.c:577-631): warm-start bits of qp->sense from an iterate. */

@@ -51,7 +51,8 @@ def _structs(real):
 
     class Trace(C.Structure):
         _fields_ = [("n_active", C.c_int), ("ws", P(C.c_int)), ("sense_out", P(C.c_int)), ("n_scan", C.c_int),
-                    ("n_add", C.c_int), ("n_remove", C.c_int), ("n_csp", C.c_int)]
+                    ("n_add", C.c_int), ("n_remove", C.c_int), ("n_csp", C.c_int), ("n_pivot", C.c_int),
+                    ("n_refine", C.c_int), ("n_refactor", C.c_int), ("n_cycle", C.c_int)]
 
     return Problem, Settings, Result, Workspace, Trace
 
@@ -79,7 +80,7 @@ class Solution:
     iter: np.ndarray
     ws: list | None = None        # per problem: working-set indices in factor order
     sense: np.ndarray | None = None  # [N, m] final sense bits
-    counts: np.ndarray | None = None  # [N,4] scan, add, remove, csp (oracle only)
+    counts: np.ndarray | None = None  # [N,8] scan, add, remove, csp, pivot, refine, refactor, cycle repair (oracle only)
     seconds: float = 0.0
     soft_slack: np.ndarray | None = None
 
@@ -258,7 +259,7 @@ class OracleLib:
         real = self.real
         x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
         fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
-        counts = np.zeros((N, 4), np.int32)
+        counts = np.zeros((N, 8), np.int32)
         slack = np.zeros(N, self.dtype)
         sense_out = np.zeros((N, m), np.int32)
         ws = []
@@ -276,11 +277,11 @@ class OracleLib:
                               sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)
             res = self.Result(_ptr(x[p], real), _ptr(lam[p], real), 0, 0, 0, 0, 0, 0, 0)
             tr = self.Trace(0, wsbuf.ctypes.data_as(C.POINTER(C.c_int)),
-                            sense_out[p].ctypes.data_as(C.POINTER(C.c_int)), 0, 0, 0, 0)
+                            sense_out[p].ctypes.data_as(C.POINTER(C.c_int)), 0, 0, 0, 0, 0, 0, 0, 0)
             self.lib.orc_quadprog(C.byref(res), C.byref(qp), sp, C.byref(tr))
             fval[p], flag[p], it[p] = res.fval, res.exitflag, res.iter
             slack[p] = res.soft_slack
-            counts[p] = (tr.n_scan, tr.n_add, tr.n_remove, tr.n_csp)
+            counts[p] = (tr.n_scan, tr.n_add, tr.n_remove, tr.n_csp, tr.n_pivot, tr.n_refine, tr.n_refactor, tr.n_cycle)
             ws.append(wsbuf[:tr.n_active].tolist())
         return Solution(x, lam, fval, flag, it, ws, sense_out, counts, time.perf_counter() - t0, slack)
 
@@ -291,7 +292,7 @@ class OracleLib:
         real = self.real
         x = np.zeros((N, n), self.dtype); lam = np.zeros((N, m), self.dtype)
         fval = np.zeros(N, self.dtype); flag = np.zeros(N, np.int32); it = np.zeros(N, np.int32)
-        counts = np.zeros((N, 4), np.int32)
+        counts = np.zeros((N, 8), np.int32)
         if use_sense is None:
             use_sense = bool(np.any(b.sense))
         sp = C.byref(settings) if settings is not None else None

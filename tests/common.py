@@ -18,7 +18,24 @@ X_TOL, F_TOL, L_TOL = 1e-9, 1e-9, 1e-7
 def golden_names():
     """Single-solve fixtures (the wsseq_* files hold workspace sequences: see test_workspace_sequence_matches_reference)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_"))]
+    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_", "rare_"))]
+
+
+def rare_golden_names():
+    """Inputs that drive the rare control paths of daqp_ldp (tests/golden/make_golden_rare.py): outputs of the reference
+    built without reassociation, non-default settings, and the oracle's path counters."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "rare_*.npz")))
+
+
+def rare_settings(d):
+    return {str(k): (int(v) if str(k) in ("cycle_tol", "iter_limit") else float(v))
+            for k, v in zip(d["settings_keys"], d["settings_vals"])}
+
+
+# which of the eight path counters (scan, add, remove, csp, pivot, refine, refactor, cycle repair) a fixture must hit
+RARE_MUST_HIT = {"rare_eqpairs_n20": (4, 5, 6, 7), "rare_eqpairs_n12_ms4": (4, 5, 6, 7), "rare_eqpairs_n50": (4, 5, 6, 7),
+                 "rare_eqpairs_n70": (4, 5, 6), "rare_parallel_1e-3": (4, 5), "rare_cycle_guard": (7,),
+                 "rare_cycle_exit": (7,)}
 
 
 def minrep_golden_names():

@@ -1,0 +1,108 @@
+"""Fixtures for the RARE control paths of daqp_ldp (reference src/daqp.c:28-85, src/auxiliary.c:379-396,498-593,
+src/utils.c:246-377,595-606): pivot swaps, refactor-on-exit, iterative refinement, the cycle guard with its repair and
+EXIT_CYCLE, non-convex Hessians, zero rows.
+
+Run in the build container (needs /root/reference):   python tests/golden/make_golden_rare.py
+
+Outputs come from the reference compiled WITHOUT reassociation (oracle/_ref/libdaqp_ref_strict.so: same sources, -O2
+-ffp-contract=off). On these ill-conditioned inputs the path depends on the last bits of a few pivots, so the fixture
+pins the build whose arithmetic is defined by the source; the oracle restatement must reproduce it bit for bit
+(tests/test_oracle.py::test_rare_paths_*), and the CUDA path must reproduce the oracle's exit flags, iteration counts,
+working sets and path counters (tests/test_gpu_parity.py::test_rare_paths_*).
+
+Each file holds the inputs, the settings that differ from the defaults, the reference's outputs, and `counts`: the
+oracle's eight path counters (scan, add, remove, csp, pivot, refine, refactor, cycle repair) for the same run -- the
+reference has no such counters; they are only kept if every other output of the oracle equals the reference's.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from daqp_b200.problems import QPBatch, generate_g1  # noqa: E402
+from oracle import harness  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+NAMES = ["scan", "add", "remove", "csp", "pivot", "refine", "refactor", "cycle"]
+
+
+def near_dependent_equalities(N, n, m, ms, na, eps, seed, neq=4):
+    """Two pairs of nearly parallel general rows (angle ~ eps) that are active at the constructed optimum, the first
+    `neq` active general rows turned into equalities (bl == bu): the pairs cannot leave the working set, so the factor
+    keeps pivots around eps^2 -- between sing_tol (3.7e-11) and refactor_tol (1e-9) for eps = 3e-5."""
+    b = generate_g1(N, n, m, ms, na, seed=seed, near_parallel=(2, eps))
+    for p in range(b.N):
+        act = np.nonzero((b.active_ref[p] != 0) & (np.arange(m) >= ms))[0][:neq]
+        for i in act:
+            if b.active_ref[p, i] > 0: b.blower[p, i] = b.bupper[p, i]
+            else: b.bupper[p, i] = b.blower[p, i]
+    return b
+
+
+def cases():
+    """name -> (batch, settings overrides, use_sense, note)"""
+    c = {}
+    c["rare_eqpairs_n20"] = (near_dependent_equalities(48, 20, 60, 0, 16, 3e-5, 123), {}, False,
+                             "near-dependent equalities: pivot_last, refactor-on-exit, refine, cycle repair, EXIT_CYCLE (plain path)")
+    c["rare_eqpairs_n12_ms4"] = (near_dependent_equalities(48, 12, 40, 4, 10, 3e-5, 125), {}, False,
+                                 "same with simple bounds")
+    c["rare_eqpairs_n50"] = (near_dependent_equalities(16, 50, 150, 0, 40, 3e-5, 127), {}, False, "same at the C3 shape")
+    c["rare_eqpairs_n70"] = (near_dependent_equalities(12, 70, 160, 6, 50, 3e-5, 129), {}, False,
+                             "same at n > 64 (team mode of the solve kernel)")
+    c["rare_parallel_1e-3"] = (generate_g1(48, 20, 60, 0, 16, seed=99, near_parallel=(2, 1e-3)), {}, False,
+                               "nearly parallel active inequalities: pivot_last + refine without equalities")
+    c["rare_cycle_guard"] = (generate_g1(48, 20, 60, 0, 16, seed=124), {"progress_tol": 1.0, "cycle_tol": 5}, False,
+                             "cycle guard forced by settings (progress_tol = 1, cycle_tol = 5): repair, then EXIT_CYCLE or optimal")
+    c["rare_cycle_exit"] = (generate_g1(32, 10, 30, 3, 8, seed=126), {"progress_tol": 1e30, "cycle_tol": 3}, False,
+                            "every add counts as no progress: repair after cycle_tol + 2 adds, EXIT_CYCLE after the next")
+    # non-convex / singular Hessians (utils.c:246-377): eps_prox = 0 turns the proximal hand-over into exit flag -5
+    b = generate_g1(12, 8, 20, 0, 6, seed=130)
+    b.H[0::3] -= 3.0 * np.eye(8)                      # indefinite dense H
+    for p in range(1, 12, 3):
+        b.H[p] = np.diag(np.linspace(1, 2, 8)); b.H[p, 2, 2] = -1.0  # indefinite diagonal H
+    c["rare_nonconvex"] = (b, {"eps_prox": 0.0}, False,
+                           "indefinite H (dense and diagonal) with eps_prox = 0 => -5 (example_test.py:444-456); the rest solve")
+    # zero rows of A (utils.c:595-606): harmless when 0 lies inside the bounds, infeasible otherwise
+    b = generate_g1(12, 8, 20, 2, 6, seed=131)
+    for p in range(12):
+        b.A[p, 5] = 0.0
+        if p % 2 == 0: b.blower[p, 7], b.bupper[p, 7] = -1.0, 1.0
+        else: b.blower[p, 7], b.bupper[p, 7] = 0.5, 1.0
+    c["rare_zero_rows"] = (b, {}, False, "zero row of A: IMMUTABLE when 0 is inside its bounds, exit flag -1 otherwise")
+    return c
+
+
+def main():
+    harness.build(ref=True)
+    ref = harness.RefLib("libdaqp_ref_strict.so")
+    orc = harness.OracleLib()
+    for name, (b, over, use_sense, note) in cases().items():
+        st = harness.default_settings(**over) if over else None
+        r = ref.solve(b, settings=st, use_sense=use_sense, want_ws=True)
+        o = orc.solve(b, settings=st, use_sense=use_sense)
+        ok = r.exitflag > 0
+        same = (np.array_equal(r.x, o.x) and np.array_equal(r.fval, o.fval) and np.array_equal(r.iter, o.iter)
+                and np.array_equal(r.exitflag, o.exitflag) and np.array_equal(r.lam[ok], o.lam[ok])
+                and all(list(a) == list(c) for a, c, f in zip(r.ws, o.ws, r.exitflag) if f >= -4))
+        assert same, f"{name}: the oracle differs from the strict reference build -- counters not trustworthy"
+        wsmax = b.n + 1
+        ws = -np.ones((b.N, wsmax), np.int32)
+        for p, w in enumerate(r.ws):
+            ws[p, :len(w)] = w
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), n=b.n, m=b.m, ms=b.ms, H=b.H, f=b.f, A=b.A,
+                            bupper=b.bupper, blower=b.blower, sense=b.sense, use_sense=use_sense,
+                            x=r.x, lam=r.lam, fval=r.fval, exitflag=r.exitflag, iter=r.iter, ws=ws,
+                            n_active=np.array([len(w) for w in r.ws], np.int32), counts=o.counts,
+                            settings_keys=np.array(list(over.keys()), dtype="U32"),
+                            settings_vals=np.array(list(over.values()), dtype=np.float64),
+                            xref=b.xref if b.xref is not None else np.zeros((0,)), note=note,
+                            build="libdaqp_ref_strict.so")
+        tot = o.counts.sum(axis=0)
+        print(f"{name:24s} N={b.N} flags={dict(zip(*[v.tolist() for v in np.unique(r.exitflag, return_counts=True)]))} "
+              + " ".join(f"{k}={v}" for k, v in zip(NAMES[4:], tot[4:])))
+
+
+if __name__ == "__main__":
+    main()

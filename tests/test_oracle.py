@@ -3,7 +3,8 @@
 import numpy as np
 import pytest
 
-from common import assert_parity, golden_names, kkt_residuals, load_golden, ws_sets
+from common import (RARE_MUST_HIT, assert_parity, golden_names, kkt_residuals, load_golden, rare_golden_names,
+                    rare_settings, ws_sets)
 from daqp_b200.problems import generate_g0, generate_g1
 
 
@@ -17,6 +18,64 @@ def test_oracle_matches_golden(oracle_libs, name):
     want = ws_sets(d["ws"], d["n_active"])
     for p in np.nonzero(started)[0]:
         assert got[p] == want[p], f"{name}[{p}]: working sets differ"
+
+
+@pytest.mark.parametrize("name", rare_golden_names())
+def test_rare_paths_oracle_matches_reference_bit_for_bit(oracle_libs, name):
+    """The rare control paths of daqp_ldp -- pivot_last, refactor-on-exit, refinement, the cycle guard with its repair
+    and EXIT_CYCLE (daqp.c:28-85, auxiliary.c:379-396,498-593), NONCONVEX (utils.c:246-377), zero rows
+    (utils.c:595-606) -- against outputs of the reference built without reassociation: x, fval, iterations, exit flags,
+    working sets and (for solved problems) lam EQUAL; and the counters prove the paths were taken. lam of a problem that
+    ends in EXIT_CYCLE is not compared: the reference reports the entering row's entry from a multiplier buffer it has
+    not written yet (api.c:463-466 after the pointer swap of auxiliary.c:159-160)."""
+    from oracle import harness
+    b, d = load_golden(name)
+    over = rare_settings(d)
+    st = harness.default_settings(**over) if over else None
+    o = oracle_libs.OracleLib().solve(b, settings=st, use_sense=bool(d["use_sense"]))
+    for key in ("x", "fval", "iter", "exitflag"):
+        np.testing.assert_array_equal(getattr(o, key), d[key], err_msg=f"{name}: {key}")
+    ok = d["exitflag"] > 0
+    np.testing.assert_array_equal(o.lam[ok], d["lam"][ok])
+    want = [list(w[:k]) for w, k in zip(d["ws"], d["n_active"])]
+    for p in np.nonzero(d["exitflag"] >= -4)[0]:
+        assert list(o.ws[p]) == want[p], f"{name}[{p}]: working set (factor order)"
+    np.testing.assert_array_equal(o.counts, d["counts"])
+    for c in RARE_MUST_HIT.get(name, ()):
+        assert o.counts[:, c].sum() > 0, f"{name}: path counter {c} never fired"
+    if name == "rare_nonconvex":
+        assert (d["exitflag"] == -5).sum() == 8 and (d["exitflag"] == 1).sum() == 4
+    if name == "rare_zero_rows":
+        assert (d["exitflag"][0::2] == 1).all() and (d["exitflag"][1::2] == -1).all()
+    if name.startswith("rare_eqpairs") and name != "rare_eqpairs_n70" or name.startswith("rare_cycle"):
+        assert (d["exitflag"] == -2).any(), "EXIT_CYCLE not reached"
+
+
+def test_rare_paths_live_reference(oracle_libs):
+    """The same families on fresh seeds against the live strict build (this container only)."""
+    if not oracle_libs.have_ref("libdaqp_ref_strict.so"):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("mgr", os.path.join(os.path.dirname(__file__), "golden", "make_golden_rare.py"))
+    mgr = importlib.util.module_from_spec(spec); spec.loader.exec_module(mgr)
+    from oracle import harness
+    ref = oracle_libs.RefLib("libdaqp_ref_strict.so")
+    orc = oracle_libs.OracleLib()
+    hits = np.zeros(8, np.int64)
+    for seed, eps in [(501, 3e-5), (502, 2e-5), (503, 1e-4)]:
+        b = mgr.near_dependent_equalities(40, 16, 50, 2, 12, eps, seed)
+        r = ref.solve(b, want_ws=True); o = orc.solve(b)
+        for a, c in ((r.x, o.x), (r.fval, o.fval), (r.iter, o.iter), (r.exitflag, o.exitflag)):
+            np.testing.assert_array_equal(a, c)
+        assert all(list(a) == list(c) for a, c, f in zip(r.ws, o.ws, r.exitflag) if f >= -4)
+        hits += o.counts.sum(axis=0)
+    st = harness.default_settings(progress_tol=1.0, cycle_tol=4)
+    b = generate_g1(40, 16, 50, 2, 12, seed=504)
+    r = ref.solve(b, settings=st, want_ws=True); o = orc.solve(b, settings=st)
+    for a, c in ((r.x, o.x), (r.fval, o.fval), (r.iter, o.iter), (r.exitflag, o.exitflag)):
+        np.testing.assert_array_equal(a, c)
+    hits += o.counts.sum(axis=0)
+    assert (hits[4:] > 0).all(), f"rare path counters {hits[4:]}"
 
 
 def test_known_answers():
