@@ -195,7 +195,7 @@ class Engine:
             ldm = (max(m, 1) + 3) // 4 * 4
             ns = 0 if sense is None else int(((sense & SOFT) != 0).sum(axis=1).max(initial=0))
             r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + ns + 1), np.intc)
-            r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
+            r.counts = np.zeros((N, 8), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
             r.soft_slack = np.zeros(N)
             d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
                              r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)), _p(r.soft_slack))
@@ -228,7 +228,7 @@ class Engine:
         if diag:
             ldm = (max(m, 1) + 3) // 4 * 4
             r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + 1), np.intc)
-            r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
+            r.counts = np.zeros((N, 8), np.intc); r.sense = np.zeros((N, ldm), np.uint8)
             d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
                              r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)), None)
         st = default_settings(**settings)
@@ -400,7 +400,7 @@ class Engine:
         return {"n_active": torch.zeros(N, dtype=torch.int32, device=device),
                 "soft_slack": torch.zeros(N, dtype=torch.float64, device=device),
                 "ws": torch.zeros((N, n + ns + 1), dtype=torch.int32, device=device),
-                "counts": torch.zeros((N, 4), dtype=torch.int32, device=device),
+                "counts": torch.zeros((N, 8), dtype=torch.int32, device=device),
                 "sense": torch.zeros((N, ldm), dtype=torch.uint8, device=device)}
 
 
@@ -482,7 +482,7 @@ class BatchModel:
         if diag:
             ldm = (max(m, 1) + 3) // 4 * 4
             r.n_active = np.zeros(N, np.intc); r.ws = np.zeros((N, n + ns + 1), np.intc)
-            r.counts = np.zeros((N, 4), np.intc); r.sense = np.zeros((N, ldm), np.uint8); r.soft_slack = np.zeros(N)
+            r.counts = np.zeros((N, 8), np.intc); r.sense = np.zeros((N, ldm), np.uint8); r.soft_slack = np.zeros(N)
             d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), _p(r.counts, _ip),
                              r.sense.ctypes.data_as(C.POINTER(C.c_ubyte)), _p(r.soft_slack))
         _check(lib().daqp_b200_workspace_solve(self._w, int(warm), _p(r.x), _p(r.lam), _p(r.fval),

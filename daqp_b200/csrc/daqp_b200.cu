@@ -361,7 +361,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.x = sa.x; la.lam = sa.lam; la.fval = sa.fval; la.exitflag = sa.exitflag; la.iter = sa.iter;
         la.ws_out = (diag && diag->ws) ? diag->ws + (size_t)p0 * cap : nullptr;
         la.nact_out = (diag && diag->n_active) ? diag->n_active + p0 : nullptr;
-        la.counts_out = (diag && diag->counts) ? diag->counts + 4 * (size_t)p0 : nullptr;
+        la.counts_out = (diag && diag->counts) ? diag->counts + 8 * (size_t)p0 : nullptr;
         la.sense_out = (diag && diag->sense) ? diag->sense + (size_t)p0 * ldm : nullptr;
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
         la.soft_slack = sa.soft_slack; la.ns_max = ns_max;
@@ -441,7 +441,7 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     chunk = std::min(chunk, N);
     first_chunk = std::min(first_chunk, chunk);
     const size_t in_b = ((size_t)n * n + n + (size_t)mA * n + 2 * (size_t)m) * sizeof(T) + (size_t)m * sizeof(int);
-    const size_t out_b = ((size_t)n + m + 2) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 4) * sizeof(int) + ldm;
+    const size_t out_b = ((size_t)n + m + 2) * sizeof(T) + 2 * sizeof(int) + (size_t)(cap + 1 + 8) * sizeof(int) + ldm;
     const size_t per_buf = ((size_t)chunk * (in_b + out_b) + 17 * 256 + 255) / 256 * 256; // buffer bases stay 256-byte aligned
     // three staging buffers: the copy-in of chunk c+2 does not have to wait for the solve of chunk c
     constexpr int NB = 3;
@@ -458,7 +458,7 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         b[i].x = cv.take<T>((size_t)chunk * n); b[i].lam = cv.take<T>((size_t)chunk * m);
         b[i].fval = cv.take<T>(chunk); b[i].slack = cv.take<T>(chunk); b[i].flag = cv.take<int>(chunk); b[i].iter = cv.take<int>(chunk);
         b[i].nact = cv.take<int>(chunk); b[i].ws = cv.take<int>((size_t)chunk * cap);
-        b[i].counts = cv.take<int>((size_t)chunk * 4); b[i].so = cv.take<unsigned char>((size_t)chunk * ldm);
+        b[i].counts = cv.take<int>((size_t)chunk * 8); b[i].so = cv.take<unsigned char>((size_t)chunk * ldm);
     }
     cudaEvent_t ev_in[NB], ev_done[NB], ev_out[NB];
     for (int i = 0; i < NB; i++) {
@@ -510,7 +510,7 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         if (diag) {
             if (diag->n_active) CK(cudaMemcpyAsync(diag->n_active + p0, B.nact, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
             if (diag->ws) CK(cudaMemcpyAsync(diag->ws + (size_t)p0 * cap, B.ws, (size_t)P * cap * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
-            if (diag->counts) CK(cudaMemcpyAsync(diag->counts + (size_t)p0 * 4, B.counts, (size_t)P * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
+            if (diag->counts) CK(cudaMemcpyAsync(diag->counts + (size_t)p0 * 8, B.counts, (size_t)P * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->copy_out));
             if (diag->sense) CK(cudaMemcpyAsync(diag->sense + (size_t)p0 * ldm, B.so, (size_t)P * ldm, cudaMemcpyDeviceToHost, h->copy_out));
             if constexpr (sizeof(T) == sizeof(c_float))
                 if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack + p0, B.slack, (size_t)P * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
@@ -914,7 +914,7 @@ static int workspace_setup_impl(DAQPB200Handle* h, int N, int K, int n, int m, i
     WS_TRY(ws_alloc(w, &w->d_fval, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_slack, (size_t)N));
     WS_TRY(ws_alloc(w, &w->d_flag, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_iter, (size_t)N));
     WS_TRY(ws_alloc(w, &w->d_nact, (size_t)N)); WS_TRY(ws_alloc(w, &w->d_ws, (size_t)N * w->cap));
-    WS_TRY(ws_alloc(w, &w->d_counts, (size_t)N * 4)); WS_TRY(ws_alloc(w, &w->d_so, (size_t)N * ldm));
+    WS_TRY(ws_alloc(w, &w->d_counts, (size_t)N * 8)); WS_TRY(ws_alloc(w, &w->d_so, (size_t)N * ldm));
     if (sense) WS_TRY(ws_alloc(w, &w->d_sense, (size_t)G * m));
     WS_TRY(ws_alloc(w, &dH, (size_t)G * n * n)); WS_TRY(ws_alloc(w, &dA, (size_t)G * std::max(mA, 1) * n));
     cudaStream_t st = h->compute;
@@ -1070,7 +1070,7 @@ extern "C" int daqp_b200_workspace_solve(DAQPB200Workspace* w, int warm, c_float
     if (diag) {
         if (diag->n_active) CK(cudaMemcpyAsync(diag->n_active, w->d_nact, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (diag->ws) CK(cudaMemcpyAsync(diag->ws, w->d_ws, (size_t)N * w->cap * sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (diag->counts) CK(cudaMemcpyAsync(diag->counts, w->d_counts, (size_t)N * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (diag->counts) CK(cudaMemcpyAsync(diag->counts, w->d_counts, (size_t)N * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (diag->sense) CK(cudaMemcpyAsync(diag->sense, w->d_so, (size_t)N * w->ldm, cudaMemcpyDeviceToHost, st));
         if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack, w->d_slack, (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, st));
     }

@@ -95,7 +95,7 @@ struct LdpArgs {
     int* iter;                // [P]
     int* ws_out;              // [P][cap] or nullptr : final working set (factor order)
     int* nact_out;            // [P] or nullptr
-    int* counts_out;          // [P][4] or nullptr  : scans, adds, removes, csp solves
+    int* counts_out;          // [P][8] or nullptr  : scans, adds, removes, csp solves, pivot swaps, refinements, refactors, cycle repairs
     unsigned char* sense_out; // [P][ldm] or nullptr: final sense bits
     int* work_counter;        // dynamic problem queue
     int tune;                 // experiment knob (see daqp_b200.cu)
@@ -130,7 +130,7 @@ inline size_t ldp_layout(LdpArgs<T>& a, int team = 0) {
     size_t bytes = (size_t)o * sizeof(T);
     bytes = (bytes + 15) / 16 * 16; // WS is read four indices at a time; padded so that a whole chunk is addressable
     a.oWS = (int)(bytes / sizeof(int)); bytes += (size_t)round_up(cap, RB) * sizeof(int);
-    a.ocnt = (int)(bytes / sizeof(int)); bytes += 4 * sizeof(int);
+    a.ocnt = (int)(bytes / sizeof(int)); bytes += 8 * sizeof(int);
     a.osense = (int)bytes; bytes += (size_t)round_up(a.m, 4);
     bytes = (bytes + 15) / 16 * 16; // the screening scan reads u32 with 128-bit loads
     a.ou32 = (int)(bytes / sizeof(float)); bytes += (size_t)(round_up(a.n, 4) + U_PAD) * sizeof(float);
@@ -536,6 +536,7 @@ struct Warp {
                 const int r = kq - 2;
                 const T Dr = D()[r], Dl = D()[kq - 1];
                 if (uni(Dr < a.st.pivot_tol && Dr < Dl)) {
+                    count(4);
                     if (lane == 0) { pst_id[depth] = WS()[r]; pst_lam[depth] = lam()[r]; }
                     __syncwarp();
                     depth++;
@@ -1177,6 +1178,18 @@ struct Warp {
         }
         iter = uni(iter + 1);
         if (iter >= a.st.iter_limit) return EXIT_ITERLIMIT; // for(iter=1; iter < iter_limit; ++iter)
+        if constexpr (TW > 1) { // experiment knobs: pull this iteration's streams into L2 while the sweeps run
+            if ((a.tune & 16) && a.Mt32) {
+                const char* q = reinterpret_cast<const char*>(a.Mt32) + (size_t)p * a.sMt32;
+                for (unsigned off = 32768u * lane; off < a.sMt32; off += 32u * 32768u)
+                    bulk_prefetch_l2(q + off, min(32768u, a.sMt32 - off) & ~15u);
+            }
+            if (a.tune & 32) {
+                const unsigned rb = a.ldn * (unsigned)sizeof(T);
+                const int kq = uni(k);
+                LANE_LOOP(i, 0, kq) bulk_prefetch_l2(Mr() + (size_t)(unsigned)WS()[i] * rb, rb);
+            }
+        }
         const bool was_singular = uni(sing != EMPTY_IND);
         if (!was_singular) compute_csp(); else singular_direction();
         int op = OP_REMOVE, arg = find_blocking();
@@ -1208,6 +1221,7 @@ struct Warp {
                     min_D = uni(min_D);
                     if (kq > 2 && uni(tried_repair != 1) && min_D < a.st.refactor_tol) {
                         tried_repair = 1;
+                        count(6);
                         LANE_LOOP(i, 0, kq) {
                             const int id = WS()[i];
                             if (lam()[i] >= 0) sense()[id] &= ~B_LOWER; else sense()[id] |= B_LOWER;
@@ -1217,6 +1231,7 @@ struct Warp {
                         return RUNNING;
                     }
                     if (!refined && kq > 0 && min_D < a.st.pivot_tol) {
+                        count(5);
                         refine_active();
                         refined = true;
                         again = true;
@@ -1230,6 +1245,7 @@ struct Warp {
                 if (uni(cycle_counter++ > a.st.cycle_tol)) {
                     if (uni(tried_repair == 1)) return EXIT_CYCLE;
                     tried_repair = 1;
+                    count(7);
                     do_activate = true;
                     cycle_counter = 0;
                     best_fval = -1;
@@ -1291,7 +1307,7 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
         const int sflag = uni(a.setup_flag[pq]); // loaded values are divergent in ptxas' eyes until proven otherwise
         if (sflag != SETUP_SOLVE && sflag != SETUP_SOLVE_ACTIVATE) {
             if (a.nact_out && lane == 0) a.nact_out[pq] = 0;
-            if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)pq + lane] = 0;
+            if (a.counts_out && lane < 8) a.counts_out[8 * (size_t)pq + lane] = 0;
             if (a.sense_out)
                 LANE_LOOP(i, 0, a.m) a.sense_out[(size_t)pq * a.ldm + i] = a.sense[(size_t)pq * a.ldm + i];
             __syncwarp(); // reconverge before the back edge: a lane-divergent tail would leave the loop header diverged
@@ -1305,7 +1321,7 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
             LANE_LOOP(i, 0, a.m) se[i] = sin[i];
             T* up = w.u();
             LANE_LOOP(i, 0, round_up(a.n, VecOf<T>::N) + U_PAD) up[i] = 0;
-            if (lane < 4) w.cnt()[lane] = 0;
+            if (lane < 8) w.cnt()[lane] = 0;
             float* u32p = w.u32();
             LANE_LOOP(i, 0, round_up(a.n, 4) + U_PAD) u32p[i] = 0.f;
             __syncwarp();
@@ -1342,7 +1358,7 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
                         }
                         LANE_LOOP(i, 0, round_up(a.n, VecOf<T>::N) + U_PAD) up[i] = 0;
                         LANE_LOOP(i, 0, round_up(a.n, 4) + U_PAD) u32p[i] = 0.f;
-                        if (lane < 4) w.cnt()[lane] = 0;
+                        if (lane < 8) w.cnt()[lane] = 0;
                         __syncwarp();
                     }
                 }
@@ -1397,7 +1413,7 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS
         if (a.nact_out && lane == 0) a.nact_out[p] = w.k;
         if (a.ws_out) LANE_LOOP(i, 0, kfin) a.ws_out[(size_t)p * a.cap + i] = w.WS()[i];
         if (a.sense_out) LANE_LOOP(i, 0, a.m) a.sense_out[(size_t)p * a.ldm + i] = w.sense()[i];
-        if (a.counts_out && lane < 4) a.counts_out[4 * (size_t)p + lane] = w.cnt()[lane];
+        if (a.counts_out && lane < 8) a.counts_out[8 * (size_t)p + lane] = w.cnt()[lane];
         if (EXT && a.state && a.state_save) { // keep factor, multipliers, working set and sense for the next warm solve
             char* blob = a.state + (size_t)p * a.state_stride;
             int4* dst4 = reinterpret_cast<int4*>(blob);

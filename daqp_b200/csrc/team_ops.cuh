@@ -58,9 +58,10 @@ __device__ __forceinline__ float ldg_ordered(const float* p) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void ldg128_ordered_last(const void* p, float (&o)[4]) { // L2 evict_last: the screening copy is re-read every scan
+template <bool LAST> // L2 evict_last (the screening copy is re-read every scan) or evict_first (pure stream)
+__device__ __forceinline__ void ldg128_ordered(const void* p, float (&o)[4]) {
     asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p), "l"(0x14F0000000000000ull));
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p), "l"(LAST ? 0x14F0000000000000ull : 0x12F0000000000000ull));
 }
 
 // tmp <- L^-1 tmp on rows [rlo, len) (rows < rlo hold the solution already). Blocked by 32: the warp that owns the rows
@@ -284,10 +285,9 @@ __device__ __noinline__ void team_primal(int lane, int wid, int kk, int lsw) {
 // a8 for a team, fp32 screening (see Warp::scan_screen for the error bound and the decision rule): the 32-row groups
 // are dealt round-robin to the warps (group g = wid + TW r, row = 32 g + lane); quads of columns stream through PF
 // register buffers per lane. Per-warp result -> box: rv = best, rk = key (INT_MAX: none), rv2 = runner-up, rs = sure.
-template <int TW, int NR>
+template <int TW, int NR, int PF = 3, bool LAST = true>
 __device__ __forceinline__ void team_scan32_n(int lane, int wid) {
     TEAM_SMEM;
-    constexpr int PF = 3;
     const int m = box->m, n = box->n;
     int rowi[NR];
     bool own[NR];
@@ -311,7 +311,7 @@ __device__ __forceinline__ void team_scan32_n(int lane, int wid) {
 #pragma unroll
     for (int i = 0; i < PF; i++)
 #pragma unroll
-        for (int r = 0; r < NR; r++) ldg128_ordered_last(src + (size_t)min(i, nq - 1) * slab + 16u * rowi[r], buf[i][r]);
+        for (int r = 0; r < NR; r++) ldg128_ordered<LAST>(src + (size_t)min(i, nq - 1) * slab + 16u * rowi[r], buf[i][r]);
     const float* u32 = reinterpret_cast<const float*>(smem_raw + box->ou32);
     for (int q0 = 0; q0 < nq; q0 += PF) {
 #pragma unroll
@@ -324,7 +324,7 @@ __device__ __forceinline__ void team_scan32_n(int lane, int wid) {
                 for (int r = 0; r < NR; r++) {
                     acc[r] += buf[i][r][0] * uq.x; acc[r] += buf[i][r][1] * uq.y;
                     acc[r] += buf[i][r][2] * uq.z; acc[r] += buf[i][r][3] * uq.w;
-                    ldg128_ordered_last(nx + 16u * rowi[r], buf[i][r]);
+                    ldg128_ordered<LAST>(nx + 16u * rowi[r], buf[i][r]);
                 }
             }
         }
@@ -368,7 +368,11 @@ __device__ __noinline__ void team_scan32(int lane, int wid) {
         case 1: team_scan32_n<TW, 1>(lane, wid); break;
         case 2: team_scan32_n<TW, 2>(lane, wid); break;
         case 3: team_scan32_n<TW, 3>(lane, wid); break;
-        case 4: team_scan32_n<TW, 4>(lane, wid); break;
+        case 4: // (the C4 shape; experiment knobs: tune & 8 = stream policy for the screening copy, tune & 64 = deeper pipeline)
+            if (box->tune & 8) team_scan32_n<TW, 4, 3, false>(lane, wid);
+            else if (box->tune & 64) team_scan32_n<TW, 4, 5, true>(lane, wid);
+            else team_scan32_n<TW, 4>(lane, wid);
+            break;
         case 5: team_scan32_n<TW, 5>(lane, wid); break;
         default: team_scan32_n<TW, 6>(lane, wid); break; // m <= 768 with four warps (the host enables the screening up to there)
     }

@@ -127,7 +127,9 @@ typedef struct {
     int* n_active;  /* [N]          final size of the working set                         */
     int* ws;        /* [N][n+ns+1]  final working set in factor order; ns = the largest number of soft
                                     constraints (sense & DAQP_SOFT) any problem of the batch carries, 0 without sense */
-    int* counts;    /* [N][4]       feasibility scans, LDL adds, LDL removes, CSP solves  */
+    int* counts;    /* [N][8]       feasibility scans, LDL adds, LDL removes, CSP solves, then the rare paths of
+                                    daqp_ldp: pivot swaps (auxiliary.c:379-396), refinements (daqp.c:52-56),
+                                    refactor-on-exit repairs (daqp.c:33-46), cycle-guard repairs (daqp.c:67-81) */
     unsigned char* sense; /* [N][ldm], ldm = m rounded up to 4: final sense bits          */
     c_float* soft_slack;  /* [N]    DAQPResult.soft_slack (reference src/api.c:469)       */
 } DAQPB200Diag;

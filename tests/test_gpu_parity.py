@@ -6,7 +6,8 @@ final working sets and per-problem operation counts must be EQUAL.
 import numpy as np
 import pytest
 
-from common import assert_parity, golden_names, kkt_residuals, load_golden, ws_sets
+from common import (RARE_MUST_HIT, assert_parity, golden_names, kkt_residuals, load_golden, rare_golden_names,
+                    rare_settings, ws_sets)
 from daqp_b200.problems import generate_config, generate_g0, generate_g1, soften
 
 pytestmark = pytest.mark.gpu
@@ -59,6 +60,28 @@ def test_cuda_matches_golden(engine, name):
     got = [sorted(w) for w in r.working_sets()]
     for p in np.nonzero(d["exitflag"] >= -4)[0]:
         assert got[p] == want[p], f"{name}[{p}]: final active set differs from the reference"
+
+
+@pytest.mark.parametrize("name", rare_golden_names())
+def test_rare_paths_cuda_matches_reference(engine, name):
+    """The rare control paths of daqp_ldp in the PLAIN instantiation of the solve kernel (and its team mode, n = 70):
+    pivot_last, refactor-on-exit, refinement, cycle guard + repair + EXIT_CYCLE, NONCONVEX, zero rows. Reference =
+    the build without reassociation (tests/golden/make_golden_rare.py). Exit flags, iteration counts, working sets in
+    factor order and all eight path counters EQUAL; the counters prove the paths ran on the GPU. Values: these inputs are
+    ill-conditioned on purpose (pivots ~1e-10), so x / lam are held to 1e-5 relative."""
+    b, d = load_golden(name)
+    over = rare_settings(d)
+    r = run_gpu(engine, b, use_sense=bool(d["use_sense"]), **over)
+    assert_parity(d["x"], d["lam"], d["fval"], d["exitflag"], d["iter"], r.x, r.lam, r.fval, r.exitflag, r.iter, name,
+                  x_tol=1e-5, f_tol=1e-6)
+    want = [list(w[:k]) for w, k in zip(d["ws"], d["n_active"])]
+    got = r.working_sets()
+    started = d["exitflag"] >= -4
+    for p in np.nonzero(started)[0]:
+        assert got[p] == want[p], f"{name}[{p}]: working set (factor order) differs"
+    np.testing.assert_array_equal(r.counts[started], d["counts"][started], err_msg=f"{name}: path counters")
+    for c in RARE_MUST_HIT.get(name, ()):
+        assert r.counts[:, c].sum() > 0, f"{name}: path counter {c} never fired on the GPU"
 
 
 @pytest.mark.parametrize("cfg", ["C1", "C2", "C3"])
