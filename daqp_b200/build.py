@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdaqp_b200.so")
-SOURCES = ["daqp_b200.cu", "team_launch.cu", "dropin.cu"]
+SOURCES = ["daqp_b200.cu", "team_launch.cu", "setup2_launch.cu", "dropin.cu"]
 HEADERS = ["common.cuh", "ldp_kernel.cuh", "setup_kernel.cuh", "update_kernel.cuh", "minrep_kernel.cuh",
-           "warmstart_kernel.cuh", "engine.h", os.path.join("..", "..", "include", "daqp_b200.h")]
+           "warmstart_kernel.cuh", "team_ops.cuh", "setup2_kernel.cuh", "engine.h", os.path.join("..", "..", "include", "daqp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -186,7 +186,8 @@ struct Carver {
 template <typename T>
 static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
     size_t e = (size_t)n * ldm + (size_t)m * ldn + 3 * (size_t)ldm + (size_t)n * (n + 1) / 2 + n;
-    return e * sizeof(T) + (size_t)((n + 3) / 4) * m * 16 + ldm + sizeof(int) + 64; // + fp32 quad copy + sense + flag + slack
+    return e * sizeof(T) + (size_t)((n + 3) / 4) * m * 16 + ldm + sizeof(int) + 64 // + fp32 quad copy + sense + flag + slack
+           + (size_t)(n + 1) * sizeof(T) + 4 * sizeof(int);                           // + hand-over of the split setup
 }
 
 template <typename T, int NV, bool EXT>
@@ -210,6 +211,9 @@ static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t
 }
 // team mode (n > 64, plain fp64 path): instantiated in team_launch.cu (separate translation unit: compiled in parallel)
 cudaError_t daqp_b200_launch_solve_team(const LdpArgs<double>& a, int nv, int grid, size_t smem, cudaStream_t s);
+
+// split QP -> LDP transform (fp64, n <= 127): factor kernel + tensor-core product kernel, instantiated in setup2_launch.cu
+cudaError_t daqp_b200_launch_setup_split(const SetupArgs<double>& a, int num_sms, size_t smem_optin, cudaStream_t s);
 
 template <typename T, int NGS>
 static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
@@ -313,6 +317,9 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         T* vv = ps ? ps->vv : cv.take<T>((size_t)P * n);
         unsigned char* sense8 = ps ? ps->sense8 : cv.take<unsigned char>((size_t)P * ldm);
         int* sflag = ps ? ps->sflag : cv.take<int>(P);
+        T* xu_s = cv.take<T>((size_t)P * n);
+        T* vnorm_s = cv.take<T>(P);
+        int* info_s = cv.take<int>((size_t)P * 4);
         int* pst_id = cv.take<int>((size_t)grid_max * 16 * cap);
         T* pst_lam = cv.take<T>((size_t)grid_max * 16 * cap);
 
@@ -335,7 +342,15 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         sa.soft_slack = nullptr; sa.ns_max = ns_max;
         if constexpr (sizeof(T) == sizeof(c_float)) sa.soft_slack = (diag && diag->soft_slack) ? diag->soft_slack + p0 : nullptr;
         sa.no_shortcut = ps ? 1 : 0; sa.sense_static = ps ? ps->sense_static : nullptr;
-        if (!ps || ps->phase == 1) {
+        sa.xu = xu_s; sa.vnorm = vnorm_s; sa.info = info_s;
+        bool split = sizeof(T) == 8 && n <= 127; // factor kernel + tensor-core product kernel
+        if (const char* senv = getenv("DAQP_B200_SETUP")) { if (!strcmp(senv, "fused")) split = false; }
+        if ((!ps || ps->phase == 1) && split) {
+            cudaError_t e = cudaErrorNotSupported;
+            if constexpr (sizeof(T) == 8) e = daqp_b200_launch_setup_split(sa, h->num_sms, h->smem_optin, stream);
+            if (e != cudaSuccess) return fail("split setup launch", e, __LINE__);
+            h->stats.setup_launches += 2;
+        } else if (!ps || ps->phase == 1) {
             const int grid = std::min(grid_max, (P + w_setup - 1) / w_setup);
             const size_t smem = smem_setup_w * w_setup;
             cudaError_t e = cudaErrorInvalidValue;

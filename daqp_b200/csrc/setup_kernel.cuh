@@ -31,6 +31,10 @@ struct SetupArgs {
     unsigned char* sense_static;          // [P][ldm] or nullptr: user sense bits with zero rows marked IMMUTABLE, WITHOUT
                                           // the equality marks check_bounds derives from the current bounds
     int ns_max;                           // upper bound on soft constraints per problem (sizes the solve kernel's factor)
+    // hand-over between the two kernels of the split transform (setup2_kernel.cuh); unused by the fused kernel
+    T* xu;                                // [P][n]  unconstrained optimum
+    int* info;                            // [P][4]  {flag, SI_* bits, -, -}
+    T* vnorm;                             // [P]     |v|^2
     DevSettings<T> st;
 };
 
