@@ -1012,6 +1012,15 @@ extern "C" int daqp_b200_workspace_setup_shared(DAQPB200Handle* h, int G, int K,
     return workspace_setup_impl(h, G, K, n, m, ms, H, nullptr, A, nullptr, nullptr, sense, settings, out);
 }
 
+extern "C" int daqp_b200_workspace_flags(DAQPB200Workspace* w, int* exitflag) {
+    if (!w) { g_last_error = "daqp_b200: null workspace"; return -2; }
+    std::lock_guard<std::mutex> lk(w->h->mu);
+    CK(cudaSetDevice(w->h->device));
+    CK(cudaMemcpyAsync(exitflag, w->d_flag, (size_t)w->N * sizeof(int), cudaMemcpyDeviceToHost, w->h->compute));
+    CK(cudaStreamSynchronize(w->h->compute));
+    return 0;
+}
+
 // kind: host arrays are staged with cudaMemcpyHostToDevice, device arrays with DeviceToDevice (the workspace keeps its
 // own copy of the current f / bounds either way: a later update may replace only some of them)
 static int workspace_update_impl(DAQPB200Workspace* w, const c_float* f, const c_float* bupper, const c_float* blower,

@@ -99,6 +99,49 @@ typedef struct {
     c_float setup_time;
 } DAQPResult;
 
+/* update masks of daqp_update_ldp -- reference include/constants.h:54-61 */
+#define DAQP_UPDATE_Rinv 1
+#define DAQP_UPDATE_M 2
+#define DAQP_UPDATE_v 4
+#define DAQP_UPDATE_d 8
+#define DAQP_UPDATE_sense 16
+#define DAQP_UPDATE_hierarchy 32
+#define DAQP_UPDATE_unconstrained 64
+#define DAQP_UPDATE_eliminate 128
+
+/* reference include/types.h:187-264 (SOFT_WEIGHTS off, the default build): same field order, sizes and offsets, because
+ * the reference's interfaces allocate this struct themselves (Cython daqp.pyx:264, Eigen daqp.cpp:148) and read fields
+ * by name or by offset (Julia api.jl:444-457). The LDP and the LDL' factor of a workspace live on the GPU; of the
+ * pointer members this library fills the ones interfaces read back -- x, lam, lam_star, WS, sense, scaling (host
+ * copies refreshed by daqp_solve) -- and leaves the rest NULL. The bnb / avi / eq slots hold this library's own
+ * bookkeeping (those drivers are out of scope here). */
+typedef struct {
+    DAQPProblem* qp;
+    int n, m, ms;
+    c_float *M, *dupper, *dlower, *Rinv, *v;
+    int* sense;
+    c_float *scaling, *RinvD;
+    c_float *x, *xold, *lam, *lam_star, *u;
+    c_float fval;
+    c_float *L, *D, *xldl, *zldl;
+    int reuse_ind;
+    int* WS;
+    int n_active;
+    int iterations;
+    int sing_ind;
+    int* prox_mask;
+    int n_prox;
+    c_float soft_slack;
+    DAQPSettings* settings;
+    void* bnb;          /* reference: DAQPBnB*            */
+    int nh;
+    int* break_points;
+    void* avi;          /* reference: DAQPAVI*;    here: host-side bookkeeping of the workspace          */
+    void* eq;           /* reference: DAQPEqElim*; here: the device-resident batch-of-one workspace     */
+    void* timer;
+    c_float* Mu;
+} DAQPWorkspace;
+
 /* ---- drop-in entry points ------------------------------------------------------------------------------- */
 
 /* reference include/api.h:30 (src/api.c:62-79). settings == NULL selects the defaults. */
@@ -106,6 +149,26 @@ void daqp_quadprog(DAQPResult* res, DAQPProblem* qp, DAQPSettings* settings);
 
 /* reference include/api.h:52 (src/api.c:505-527) */
 void daqp_default_settings(DAQPSettings* settings);
+
+/* ---- drop-in workspace flow: what daqp.Model / the Eigen class DAQP / Julia's Model call ----------------------
+ * reference include/api.h:33-49, src/api.c:8-59,84-160,244-275,399-431, include/utils.h:11, src/utils.c:58-221.
+ * A workspace is a batch of one on the GPU: setup_daqp runs the QP -> LDP transform and keeps the LDP on the device,
+ * daqp_update_ldp(DAQP_UPDATE_v / _d) recomputes v and d there, daqp_solve continues from the factor and working set of
+ * the previous solve. Masks that change the matrices or the sense bits (Rinv, M, sense) redo the transform. With
+ * DAQP_UPDATE_unconstrained in init_mask (the mask daqp_quadprog itself uses, src/api.c:67-68) setup_daqp_main + daqp_solve
+ * together ARE one daqp_quadprog call and run as one. Return values and the ownership of `settings` follow the
+ * reference: 1 on success, the negative exit flag on failure (then the workspace is already freed, and a settings
+ * struct the caller installed is left to the caller). */
+int setup_daqp(DAQPProblem* qp, DAQPWorkspace* work, c_float* setup_time);
+int setup_daqp_main(DAQPProblem* qp, DAQPWorkspace* work, c_float* setup_time, int init_mask);
+void daqp_solve(DAQPResult* res, DAQPWorkspace* work);
+int daqp_update_ldp(const int mask, DAQPWorkspace* work, DAQPProblem* qp);
+void allocate_daqp_settings(DAQPWorkspace* work);
+void free_daqp_workspace(DAQPWorkspace* work);
+void free_daqp_ldp(DAQPWorkspace* work);
+void daqp_set_primal_start(DAQPWorkspace* work, c_float* x);
+/* reference include/api.h:55 (src/api.c:562-574): index of the first constraint x violates by more than tol, or m */
+int daqp_first_violating(c_float* x, c_float* A, c_float* bu, c_float* bl, int n, int m, int ms, c_float tol);
 
 /* ---- batch entry points (new) --------------------------------------------------------------------------- */
 
@@ -205,6 +268,9 @@ int daqp_b200_workspace_update_device(DAQPB200Workspace* w, const c_float* df, c
 int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, c_float* dx, c_float* dlam, c_float* dfval,
                                      int* dexitflag, int* diter, void* stream);
 void daqp_b200_workspace_free(DAQPB200Workspace* w);
+/* Exit flags the setup (or the last update) raised per problem, 0 where none: infeasible bounds (-1), non-convex or
+ * singular Hessian (-5), out-of-scope input (-8). HOST array [N]; synchronises the workspace's stream. */
+int daqp_b200_workspace_flags(DAQPB200Workspace* w, int* exitflag);
 
 /* ---- warm-start initialisers (the callers on the input side of the path) -----------------------------------------
  * reference include/api.h:57-58 (src/api.c:577-631): set the ACTIVE / LOWER bits of qp->sense from a primal iterate

@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 from dataclasses import dataclass
 
 import numpy as np
@@ -63,8 +64,12 @@ _F32 = _structs(C.c_float)
 
 def build(ref: bool = True) -> None:
     """Compile the oracle restatement, and the reference into oracle/_ref when /root/reference is present."""
-    targets = ["oracle"] + (["ref"] if ref and os.path.isdir("/root/reference/src") else [])
-    subprocess.run(["make", "-C", HERE, "CC=gcc"] + targets, check=True, capture_output=True)
+    have_src = ref and os.path.isdir("/root/reference/src")
+    targets = ["oracle"] + (["ref"] if have_src else [])
+    # the reference's own Cython interface linked against the product library (tests/test_reference_binding.py)
+    if have_src and os.path.exists(os.path.join(os.path.dirname(HERE), "daqp_b200", "libdaqp_b200.so")):
+        targets.append("pybind")
+    subprocess.run(["make", "-C", HERE, "CC=gcc", f"PY={sys.executable}"] + targets, check=True, capture_output=True)
 
 
 def have_ref(name: str = "libdaqp_ref.so") -> bool:

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "daqp_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(daqp_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:daqp_|setup_daqp|allocate_daqp|free_daqp)[a-z0-9_]*)\s*\(", src)))
 
 
 def test_header_symbols_exported(cuda_lib):
@@ -50,6 +50,32 @@ def test_layout_against_live_reference(oracle_libs):
     ref.daqp_quadprog(C.byref(res), C.byref(qp), C.byref(st))
     assert res.exitflag == 1
     np.testing.assert_allclose(x, [-1, -1], atol=1e-9)
+
+
+WS_FIELDS = ["qp", "n", "m", "ms", "M", "dupper", "dlower", "Rinv", "v", "sense", "scaling", "RinvD", "x", "xold", "lam",
+             "lam_star", "u", "fval", "L", "D", "xldl", "zldl", "reuse_ind", "WS", "n_active", "iterations", "sing_ind",
+             "prox_mask", "n_prox", "soft_slack", "settings", "bnb", "nh", "break_points", "avi", "eq", "timer", "Mu"]
+
+
+def _offsets(header_dir, header, tmp_path, tag):
+    import subprocess
+    src = tmp_path / f"off_{tag}.c"
+    exe = tmp_path / f"off_{tag}"
+    body = "".join(f'printf("%zu ", offsetof(DAQPWorkspace, {f}));' for f in WS_FIELDS)
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{header}"\n'
+                   f'int main(void) {{ printf("%zu ", sizeof(DAQPWorkspace)); {body} return 0; }}\n')
+    subprocess.run(["gcc", "-I", header_dir, "-o", str(exe), str(src)], check=True)
+    return subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+
+
+def test_workspace_layout_matches_reference_header(tmp_path):
+    """DAQPWorkspace is ABI: the reference's interfaces allocate it and read its fields (daqp.pyx:264, api.jl:444-457).
+    Size and every field offset of include/daqp_b200.h against the reference's include/types.h:187-264."""
+    ours = _offsets(os.path.join(ROOT, "include"), "daqp_b200.h", tmp_path, "ours")
+    assert int(ours[0]) == 288 and len(ours) == len(WS_FIELDS) + 1  # LP64, SOFT_WEIGHTS off
+    if os.path.isdir("/root/reference/include"):
+        ref = _offsets("/root/reference/include", "types.h", tmp_path, "ref")
+        assert ours == ref
 
 
 def test_default_settings_match_reference_constants(cuda_lib):

@@ -233,7 +233,7 @@ def test_team_mode_rare_paths(engine, oracle):
     check_vs_oracle(engine, oracle, b, "team: vertex (nact = n)", x_tol=1e-8)
     rng = np.random.default_rng(7)
     b.sense[:] = np.where(rng.random(b.sense.shape) < 0.5, rng.choice([1, 3], b.sense.shape), 0)
-    check_vs_oracle(engine, oracle, b, "team: over-determined warm start", use_sense=True)
+    check_vs_oracle(engine, oracle, b, "team: over-determined warm start", use_sense=True, x_tol=1e-8)
     b = generate_g1(80, 90, 220, 0, 60, seed=7104)
     for p in range(b.N):
         b.sense[p, np.nonzero(b.active_ref[p])[0][:5]] = 5
