@@ -154,8 +154,14 @@ static void ldl_delete(Ldp *w, int r) {
         real p = q[t];
         real dbar = w->D[io] + alpha * p * p;
         w->D[io - 1] = dbar;
+#ifdef ORC_GPU_ARITH /* the CUDA kernels' form: one correctly rounded reciprocal for both quotients (fixture triage only) */
+        const real rdb = (real)1 / dbar;
+        real beta = p * alpha * rdb;
+        alpha = w->D[io] * alpha * rdb;
+#else
         real beta = p * alpha / dbar;
         alpha = w->D[io] * alpha / dbar;
+#endif
         for (int s = t + 1; s < nu; s++) {
             q[s] -= p * Lij(w, r + s, c);
             Lij(w, r + s, c) += beta * q[s];

@@ -248,12 +248,15 @@ class RefDriver:
 class OracleLib:
     """This repo's scalar restatement (oracle/daqp_oracle.c)."""
 
-    def __init__(self, single: bool = False):
+    def __init__(self, single: bool = False, variant: str | None = None):
+        """variant="gpuarith": the restatement compiled with FMA contraction and the kernels' reciprocal form of the C1
+        quotients -- a voter in the path-stability filters of the fixture generators, nothing else."""
         self.single = single
         self.real = C.c_float if single else C.c_double
         self.dtype = np.float32 if single else np.float64
         self.Problem, self.Settings, self.Result, _, self.Trace = _F32 if single else _F64
-        self.lib = C.CDLL(os.path.join(HERE, "libdaqp_oracle_f32.so" if single else "libdaqp_oracle.so"))
+        name = "libdaqp_oracle_f32.so" if single else ("libdaqp_oracle_" + variant + ".so" if variant else "libdaqp_oracle.so")
+        self.lib = C.CDLL(os.path.join(HERE, name))
         self.lib.orc_quadprog.restype = None
         self.lib.orc_solve_packed.restype = C.c_double
 
