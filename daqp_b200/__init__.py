@@ -45,6 +45,19 @@ class DAQPResult(C.Structure):  # reference include/api.h:15-27
                 ("iter", C.c_int), ("nodes", C.c_int), ("solve_time", C.c_double), ("setup_time", C.c_double)]
 
 
+_fp = C.POINTER(C.c_float)
+
+
+class DAQPProblemF32(C.Structure):  # the reference's DAQPProblem with c_float = float (include/types.h:8-12,32-49)
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("ms", C.c_int), ("H", _fp), ("f", _fp), ("A", _fp), ("bupper", _fp),
+                ("blower", _fp), ("sense", _ip), ("break_points", _ip), ("nh", C.c_int), ("problem_type", C.c_int)]
+
+
+class DAQPResultF32(C.Structure):  # include/api.h:15-27 with c_float = float
+    _fields_ = [("x", _fp), ("lam", _fp), ("fval", C.c_float), ("soft_slack", C.c_float), ("exitflag", C.c_int),
+                ("iter", C.c_int), ("nodes", C.c_int), ("solve_time", C.c_float), ("setup_time", C.c_float)]
+
+
 class DAQPB200Diag(C.Structure):
     _fields_ = [("n_active", _ip), ("ws", _ip), ("counts", _ip), ("sense", C.POINTER(C.c_ubyte)), ("soft_slack", _dp)]
 
@@ -550,6 +563,34 @@ def solve_batch(H, f, A, bupper, blower, sense=None, **kw) -> BatchResult:
     return _default_engine.solve_batch(H, f, A, bupper, blower, sense, **kw)
 
 
+def solve_batch_multi(H, f, A, bupper, blower, sense=None, ms: int | None = None, devices=None, out: BatchResult | None = None,
+                      **settings):
+    """One process, several GPUs (``daqp_b200_solve_packed_multi``): the batch is cut into contiguous blocks, one host
+    thread + engine per device, no exchange between devices. ``devices``: list of CUDA device indices (default: all
+    visible). Returns ``(BatchResult, seconds_per_device)``."""
+    L = lib()
+    L.daqp_b200_solve_packed_multi.restype = C.c_int
+    H = _f64(H); f = _f64(f); A = _f64(A); bupper = _f64(bupper); blower = _f64(blower)
+    N, n = H.shape[0], H.shape[1]
+    m = bupper.shape[1]
+    mA = A.shape[1] if A is not None and A.size else 0
+    ms = m - mA if ms is None else ms
+    if sense is not None:
+        sense = np.ascontiguousarray(sense, dtype=np.intc)
+    if devices is None:
+        import torch
+        devices = list(range(torch.cuda.device_count()))
+    dv = np.asarray(devices, dtype=np.intc)
+    r = out or BatchResult(x=np.empty((N, n)), lam=np.empty((N, m)), fval=np.zeros(N), exitflag=np.empty(N, np.intc),
+                           iter=np.empty(N, np.intc))
+    secs = np.zeros(len(dv))
+    st = default_settings(**settings)
+    _check(L.daqp_b200_solve_packed_multi(C.c_int(len(dv)), _p(dv, _ip), N, n, m, ms, _p(H), _p(f), _p(A), _p(bupper),
+                                          _p(blower), _p(sense, _ip), C.byref(st), _p(r.x), _p(r.lam), _p(r.fval),
+                                          _p(r.exitflag, _ip), _p(r.iter, _ip), _p(secs)))
+    return r, secs
+
+
 def minrep(A, b):
     """Drop-in for the reference's ``daqp.minrep(A, b)`` (interfaces/daqp-python/daqp.pyx:636-652): which constraints
     of {x : A x <= b} are redundant. ``b`` longer than A's row count means the leading entries are simple bounds.
@@ -597,4 +638,33 @@ def quadprog_batch(problems: list[dict], **settings):
     return [(keep[i][6], res[i].fval, res[i].exitflag,
              {"iterations": res[i].iter, "lam": keep[i][7], "solve_time": res[i].solve_time,
               "setup_time": res[i].setup_time, "nodes": res[i].nodes, "soft_slack": res[i].soft_slack})
+            for i in range(N)]
+
+
+def quadprog_batch_f32(problems: list[dict], **settings):
+    """The same array-of-struct batch in fp32 arithmetic (``daqp_quadprog_batch_f32``: the structs of the reference's
+    -DDAQP_SINGLE_PRECISION build). Mixed shapes in one call; x / lam come back as float32 arrays."""
+    L = lib()
+    L.daqp_quadprog_batch_f32.restype = C.c_int
+    N = len(problems)
+    qps = (DAQPProblemF32 * N)(); res = (DAQPResultF32 * N)()
+    keep = []
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    pf = lambda a: None if a is None else a.ctypes.data_as(_fp)
+    for i, pr in enumerate(problems):
+        H = f32(pr["H"]); f = f32(pr.get("f")); A = f32(pr.get("A")); bu = f32(pr["bupper"])
+        m = bu.shape[0]
+        n = H.shape[0]
+        mA = A.shape[0] if A is not None and A.size else 0
+        bl = np.full(m, -DAQP_INF, np.float32) if pr.get("blower") is None else f32(pr["blower"])
+        se = None if pr.get("sense") is None else np.ascontiguousarray(pr["sense"], dtype=np.intc)
+        x = np.empty(n, np.float32); lam = np.empty(m, np.float32)
+        keep.append((H, f, A, bu, bl, se, x, lam))
+        qps[i] = DAQPProblemF32(n, m, m - mA, pf(H), pf(f), pf(A) if mA else None, pf(bu), pf(bl), _p(se, _ip), None, 0, 0)
+        res[i] = DAQPResultF32(pf(x), pf(lam) if m else None, 0, 0, 0, 0, 0, 0, 0)
+    st = default_settings(**settings)
+    _check(L.daqp_quadprog_batch_f32(N, qps, res, C.byref(st)))
+    return [(keep[i][6], res[i].fval, res[i].exitflag,
+             {"iterations": res[i].iter, "lam": keep[i][7], "solve_time": res[i].solve_time,
+              "setup_time": res[i].setup_time, "nodes": res[i].nodes})
             for i in range(N)]

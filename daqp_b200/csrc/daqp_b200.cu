@@ -12,6 +12,9 @@
 #include "warmstart_kernel.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,7 +55,30 @@ struct DAQPB200Handle {
     std::vector<EventTriple> pending, free_events;
     DAQPB200Stats stats{};
     std::mutex mu;
+    // The scratch arena is reused from offset 0 by every call. Calls may arrive on different streams: the last user records
+    // `arena_ev`, the next one's stream waits on it before it touches the arena.
+    cudaEvent_t arena_ev = nullptr;
+    cudaStream_t arena_stream = nullptr;
+    bool arena_used = false;
+    char* pin = nullptr;          // pinned host mirror of `stage` for small batches (one copy in, one copy out)
+    size_t pin_bytes = 0;
+    int live_workspaces = 0;      // persistent workspaces that still point at this handle
 };
+
+// order this call after the previous user of the arena (no-op on the same stream)
+static int arena_acquire(DAQPB200Handle* h, cudaStream_t s) {
+    if (h->arena_used && h->arena_stream != s) {
+        cudaError_t e = cudaStreamWaitEvent(s, h->arena_ev, 0);
+        if (e != cudaSuccess) { g_last_error = "daqp_b200: cudaStreamWaitEvent on the arena event failed"; return -100 - (int)e; }
+    }
+    return 0;
+}
+static int arena_release(DAQPB200Handle* h, cudaStream_t s) {
+    cudaError_t e = cudaEventRecord(h->arena_ev, s);
+    if (e != cudaSuccess) { g_last_error = "daqp_b200: cudaEventRecord on the arena event failed"; return -100 - (int)e; }
+    h->arena_used = true; h->arena_stream = s;
+    return 0;
+}
 
 extern "C" void daqp_default_settings(DAQPSettings* s) { // reference src/api.c:505-527, include/constants.h:15-29
     s->primal_tol = 1e-6; s->dual_tol = 1e-12; s->zero_tol = 1e-11; s->pivot_tol = 1e-6;
@@ -91,6 +117,7 @@ extern "C" int daqp_b200_create(DAQPB200Handle** out, int device) {
     CK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->arena_ev, cudaEventDisableTiming));
     const char* lim = getenv("DAQP_B200_SCRATCH_GB");
     if (lim) h->scratch_limit = (long long)(atof(lim) * (double)(1ll << 30));
     *out = h;
@@ -99,8 +126,17 @@ extern "C" int daqp_b200_create(DAQPB200Handle** out, int device) {
 
 extern "C" void daqp_b200_destroy(DAQPB200Handle* h) {
     if (!h) return;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (h->live_workspaces > 0) { // workspaces dereference the handle: free them first
+            g_last_error = "daqp_b200: destroy refused, persistent workspaces of this engine are still alive";
+            return;
+        }
+    }
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->arena_ev) cudaEventDestroy(h->arena_ev);
+    if (h->pin) cudaFreeHost(h->pin);
     for (auto& t : h->pending) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto& t : h->free_events) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     if (h->arena) cudaFree(h->arena);
@@ -264,6 +300,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         int* dcount = nullptr;
         int rc0 = ensure(&h->arena, &h->arena_bytes, 1 << 20);
         if (rc0) return rc0;
+        rc0 = arena_acquire(h, stream);
+        if (rc0) return rc0;
         dcount = reinterpret_cast<int*>(h->arena);
         CK(cudaMemsetAsync(dcount, 0, sizeof(int), stream));
         max_soft_kernel<<<std::min(1024, (N + 127) / 128), 128, 0, stream>>>(dsense, N, m, dcount);
@@ -299,6 +337,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     int rc = ensure(&h->arena, &h->arena_bytes, (ps ? 0 : (size_t)chunk * per) + pst + (1 << 20));
     if (rc) return rc;
 
+    rc = arena_acquire(h, stream);
+    if (rc) return rc;
     const DevSettings<T> st = to_dev_settings<T>(settings);
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
@@ -412,7 +452,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         CK(cudaEventRecord(ev.e2, stream));
         h->pending.push_back(ev);
     }
-    return 0;
+    return arena_release(h, stream);
 }
 
 extern "C" int daqp_b200_solve_device(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* dH,
@@ -463,6 +503,68 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     int rc = ensure(&h->stage, &h->stage_bytes, NB * per_buf);
     if (rc) return rc;
 
+    // ---- small batches (a single daqp_quadprog call, a handful of problems): latency, not bandwidth. Everything goes
+    // through ONE pinned mirror of the staging buffer: one copy in, the two kernels, one copy out, one synchronisation on
+    // one stream (the chunk pipeline below costs nine event creations and three stream synchronisations per call).
+    if ((size_t)N * (in_b + out_b) <= ((size_t)1 << 20)) {
+        if (h->pin_bytes < per_buf) {
+            if (h->pin) { CK(cudaFreeHost(h->pin)); h->pin = nullptr; h->pin_bytes = 0; }
+            CK(cudaHostAlloc((void**)&h->pin, per_buf, cudaHostAllocDefault));
+            h->pin_bytes = per_buf;
+        }
+        struct View { T *H, *f, *A, *bu, *bl; int* sense; T *x, *lam, *fval, *slack; int *flag, *iter, *nact, *ws, *counts; unsigned char* so; char* out0; };
+        auto carve = [&](char* base) {
+            View v; Carver cv(base);
+            v.H = cv.take<T>((size_t)chunk * n * n); v.f = cv.take<T>((size_t)chunk * n);
+            v.A = cv.take<T>((size_t)chunk * mA * n); v.bu = cv.take<T>((size_t)chunk * m);
+            v.bl = cv.take<T>((size_t)chunk * m); v.sense = cv.take<int>((size_t)chunk * m);
+            v.x = cv.take<T>((size_t)chunk * n); v.out0 = reinterpret_cast<char*>(v.x);
+            v.lam = cv.take<T>((size_t)chunk * m);
+            v.fval = cv.take<T>(chunk); v.slack = cv.take<T>(chunk); v.flag = cv.take<int>(chunk); v.iter = cv.take<int>(chunk);
+            v.nact = cv.take<int>(chunk); v.ws = cv.take<int>((size_t)chunk * cap);
+            v.counts = cv.take<int>((size_t)chunk * 8); v.so = cv.take<unsigned char>((size_t)chunk * ldm);
+            return std::make_pair(v, cv.off);
+        };
+        auto hv = carve(h->pin).first;
+        auto dvp = carve(h->stage);
+        auto dv = dvp.first;
+        const size_t in_bytes = (size_t)(hv.out0 - h->pin), all_bytes = dvp.second;
+        memcpy(hv.H, H, (size_t)N * n * n * sizeof(T));
+        if (f) memcpy(hv.f, f, (size_t)N * n * sizeof(T));
+        if (mA > 0) memcpy(hv.A, A, (size_t)N * mA * n * sizeof(T));
+        if (m > 0) {
+            memcpy(hv.bu, bupper, (size_t)N * m * sizeof(T)); memcpy(hv.bl, blower, (size_t)N * m * sizeof(T));
+            if (sense) memcpy(hv.sense, sense, (size_t)N * m * sizeof(int));
+        }
+        if (fval) memcpy(hv.fval, fval, (size_t)N * sizeof(T)); // untouched entries (no linear term) keep the caller's value
+        cudaStream_t s1 = h->compute;
+        CK(cudaMemcpyAsync(h->stage, h->pin, in_bytes, cudaMemcpyHostToDevice, s1));
+        if (fval) CK(cudaMemcpyAsync(dv.fval, hv.fval, (size_t)N * sizeof(T), cudaMemcpyHostToDevice, s1));
+        DAQPB200Diag dd{};
+        if (diag) { dd.n_active = diag->n_active ? dv.nact : nullptr; dd.ws = diag->ws ? dv.ws : nullptr;
+                    dd.counts = diag->counts ? dv.counts : nullptr; dd.sense = diag->sense ? dv.so : nullptr;
+                    if constexpr (sizeof(T) == sizeof(c_float)) dd.soft_slack = diag->soft_slack ? dv.slack : nullptr; }
+        rc = solve_device_impl<T>(h, N, n, m, ms, dv.H, f ? dv.f : nullptr, dv.A, dv.bu, dv.bl, sense ? dv.sense : nullptr, settings,
+                                  dv.x, lam ? dv.lam : nullptr, dv.fval, dv.flag, dv.iter, diag ? &dd : nullptr, s1, ns_max);
+        if (rc) { cudaStreamSynchronize(s1); return rc; }
+        CK(cudaMemcpyAsync(hv.out0, dv.out0, all_bytes - in_bytes, cudaMemcpyDeviceToHost, s1));
+        CK(cudaStreamSynchronize(s1));
+        memcpy(x, hv.x, (size_t)N * n * sizeof(T));
+        if (lam && m > 0) memcpy(lam, hv.lam, (size_t)N * m * sizeof(T));
+        if (fval) memcpy(fval, hv.fval, (size_t)N * sizeof(T));
+        memcpy(exitflag, hv.flag, (size_t)N * sizeof(int));
+        if (iter) memcpy(iter, hv.iter, (size_t)N * sizeof(int));
+        if (diag) {
+            if (diag->n_active) memcpy(diag->n_active, hv.nact, (size_t)N * sizeof(int));
+            if (diag->ws) memcpy(diag->ws, hv.ws, (size_t)N * cap * sizeof(int));
+            if (diag->counts) memcpy(diag->counts, hv.counts, (size_t)N * 8 * sizeof(int));
+            if (diag->sense) memcpy(diag->sense, hv.so, (size_t)N * ldm);
+            if constexpr (sizeof(T) == sizeof(c_float))
+                if (diag->soft_slack) memcpy(diag->soft_slack, hv.slack, (size_t)N * sizeof(T));
+        }
+        return 0;
+    }
+
     struct Buf { T *H, *f, *A, *bu, *bl; int* sense; T *x, *lam, *fval, *slack; int *flag, *iter, *nact, *ws, *counts; unsigned char* so; };
     Buf b[NB];
     for (int i = 0; i < NB; i++) {
@@ -491,8 +593,11 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         left -= P;
     }
     int p0 = 0;
-    for (size_t ci = 0; ci < sched.size() && result == 0; p0 += sched[ci], ci++, c++) {
-        const int P = sched[ci], s = c % NB;
+    // one chunk: enqueue copy-in, solve, copy-out. A failing call returns from the lambda only -- the streams are always
+    // synchronised and the events destroyed below, so no copy into the caller's arrays is in flight when this function
+    // returns with an error.
+    auto enqueue_chunk = [&](int P, int p0, int c) -> int {
+        const int s = c % NB;
         Buf& B = b[s];
         // input buffers are free once the solve that read them (two chunks ago) has finished
         if (c >= NB) CK(cudaStreamWaitEvent(h->copy_in, ev_done[s], 0));
@@ -511,10 +616,10 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         if (diag) { dd.n_active = diag->n_active ? B.nact : nullptr; dd.ws = diag->ws ? B.ws : nullptr;
                     dd.counts = diag->counts ? B.counts : nullptr; dd.sense = diag->sense ? B.so : nullptr;
                     if constexpr (sizeof(T) == sizeof(c_float)) dd.soft_slack = diag->soft_slack ? B.slack : nullptr; }
-        result = solve_device_impl<T>(h, P, n, m, ms, B.H, f ? B.f : nullptr, B.A, B.bu, B.bl, sense ? B.sense : nullptr,
-                                      settings, B.x, lam ? B.lam : nullptr, B.fval, B.flag, B.iter, diag ? &dd : nullptr,
-                                      h->compute, ns_max);
-        if (result) break;
+        const int r2 = solve_device_impl<T>(h, P, n, m, ms, B.H, f ? B.f : nullptr, B.A, B.bu, B.bl, sense ? B.sense : nullptr,
+                                            settings, B.x, lam ? B.lam : nullptr, B.fval, B.flag, B.iter, diag ? &dd : nullptr,
+                                            h->compute, ns_max);
+        if (r2) return r2;
         CK(cudaEventRecord(ev_done[s], h->compute));
         CK(cudaStreamWaitEvent(h->copy_out, ev_done[s], 0));
         CK(cudaMemcpyAsync(x + (size_t)p0 * n, B.x, (size_t)P * n * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
@@ -531,7 +636,9 @@ static int solve_packed_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
                 if (diag->soft_slack) CK(cudaMemcpyAsync(diag->soft_slack + p0, B.slack, (size_t)P * sizeof(T), cudaMemcpyDeviceToHost, h->copy_out));
         }
         CK(cudaEventRecord(ev_out[s], h->copy_out));
-    }
+        return 0;
+    };
+    for (size_t ci = 0; ci < sched.size() && result == 0; p0 += sched[ci], ci++, c++) result = enqueue_chunk(sched[ci], p0, c);
     cudaError_t e1 = cudaStreamSynchronize(h->copy_in), e2 = cudaStreamSynchronize(h->compute), e3 = cudaStreamSynchronize(h->copy_out);
     for (int i = 0; i < NB; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
     if (result) return result;
@@ -600,6 +707,8 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
     const size_t pst = (size_t)grid_max * 16 * cap * (sizeof(int) + sizeof(T)) + 4096;
     int rc = ensure(&h->arena, &h->arena_bytes, (size_t)chunk * per + pst + (1 << 20));
     if (rc) return rc;
+    rc = arena_acquire(h, stream);
+    if (rc) return rc;
     const DevSettings<T> st = to_dev_settings<T>(settings);
     for (int q0 = 0; q0 < P; q0 += chunk) {
         const int Q = std::min(chunk, P - q0);
@@ -662,7 +771,7 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
         h->pending.push_back(ev);
         if (q0 + chunk < P) CK(cudaStreamSynchronize(stream)); // the next chunk reuses the scratch
     }
-    return 0;
+    return arena_release(h, stream);
 }
 
 extern "C" int daqp_b200_minrep_device(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA,
@@ -857,6 +966,7 @@ struct DAQPB200Workspace {
     DAQPSettings settings{};
     Persist<c_float> ps;
     std::vector<void*> owned; // every device allocation of the workspace
+    bool counted = false;     // registered in the handle's live_workspaces
     c_float *d_f = nullptr, *d_bu = nullptr, *d_bl = nullptr;                           // inputs of update
     c_float *d_x = nullptr, *d_lam = nullptr, *d_fval = nullptr, *d_slack = nullptr;    // outputs of solve
     int *d_flag = nullptr, *d_iter = nullptr, *d_nact = nullptr, *d_ws = nullptr, *d_counts = nullptr;
@@ -875,6 +985,7 @@ extern "C" void daqp_b200_workspace_free(DAQPB200Workspace* w) {
     cudaSetDevice(w->h->device);
     cudaDeviceSynchronize();
     for (void* p : w->owned) cudaFree(p);
+    if (w->counted) { std::lock_guard<std::mutex> lk(w->h->mu); w->h->live_workspaces--; } // (a failed setup frees with mu held: not counted yet)
     delete w;
 }
 
@@ -994,6 +1105,8 @@ static int workspace_setup_impl(DAQPB200Handle* h, int N, int K, int n, int m, i
     w->owned.erase(std::remove(w->owned.begin(), w->owned.end(), (void*)dA), w->owned.end());
 #undef WS_TRY
 #undef WS_CK
+    w->counted = true;
+    h->live_workspaces++; // (h->mu is held)
     *out = w;
     return 0;
 }
@@ -1126,63 +1239,216 @@ extern "C" int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, 
     return 0;
 }
 
-// Array-of-struct batch: group by shape, pack, solve, scatter (identical in effect to N daqp_quadprog calls).
-extern "C" int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQPSettings* settings) {
+// ---- one process, several GPUs: the batch is cut into contiguous blocks, one host thread + engine per device ---------
+extern "C" int daqp_b200_solve_packed_multi(int ndev, const int* devices, int N, int n, int m, int ms, const c_float* H,
+                                            const c_float* f, const c_float* A, const c_float* bupper, const c_float* blower,
+                                            const int* sense, const DAQPSettings* settings, c_float* x, c_float* lam,
+                                            c_float* fval, int* exitflag, int* iter, double* seconds_per_device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        g_last_error = "daqp_b200: no CUDA device available (this library has no CPU path)";
+        return -1;
+    }
+    if (ndev <= 0) ndev = count;
     if (N <= 0) return 0;
-    std::map<std::tuple<int, int, int, bool, bool>, std::vector<int>> groups;
+    const int mA = m - ms;
+    std::vector<int> rcs((size_t)ndev, 0);
+    std::vector<std::string> errs((size_t)ndev);
+    std::vector<std::thread> th;
+    const int base = N / ndev, extra = N % ndev;
+    int lo = 0;
+    for (int r = 0; r < ndev; r++) {
+        const int cnt = base + (r < extra ? 1 : 0), p0 = lo, dev = devices ? devices[r] : r % count;
+        lo += cnt;
+        th.emplace_back([=, &rcs, &errs]() {
+            const auto t0 = std::chrono::steady_clock::now();
+            int rc = 0;
+            if (cnt > 0) {
+                if (cudaSetDevice(dev) != cudaSuccess) rc = -1;
+                DAQPB200Handle* h = nullptr;
+                if (!rc) rc = default_handle(&h);
+                if (!rc)
+                    rc = daqp_b200_solve_packed(h, cnt, n, m, ms, H + (size_t)p0 * n * n, f ? f + (size_t)p0 * n : nullptr,
+                                                A + (size_t)p0 * mA * n, bupper + (size_t)p0 * m, blower + (size_t)p0 * m,
+                                                sense ? sense + (size_t)p0 * m : nullptr, settings, x + (size_t)p0 * n,
+                                                lam ? lam + (size_t)p0 * m : nullptr, fval ? fval + p0 : nullptr, exitflag + p0,
+                                                iter ? iter + p0 : nullptr, nullptr);
+                if (rc) errs[r] = g_last_error; // (thread-local: carry it to the caller's thread)
+            }
+            rcs[r] = rc;
+            if (seconds_per_device) seconds_per_device[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ndev; r++)
+        if (rcs[r]) { g_last_error = errs[r]; return rcs[r]; }
+    return 0;
+}
+
+// cudaHostRegister / cudaHostUnregister for callers without a CUDA toolchain: pinned arrays make the chunked copies of
+// daqp_b200_solve_packed asynchronous (pageable memory is staged by the driver, at about half the rate)
+extern "C" int daqp_b200_pin(void* ptr, size_t bytes) { CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0; }
+extern "C" int daqp_b200_unpin(void* ptr) { CK(cudaHostUnregister(ptr)); return 0; }
+
+// ---- array-of-struct batch (identical in effect to N daqp_quadprog calls) -----------------------------------------------
+// Problems are grouped by shape; the groups are dealt, largest estimated cost first, to a few LANES (sub-engines with
+// their own streams, scratch and pinned staging) that run side by side: while one lane's group is being solved, another
+// lane packs its next group into pinned memory or copies results out. A group is packed by several host threads.
+namespace {
+struct Lane {
+    DAQPB200Handle* h = nullptr;
+    char* pin = nullptr;
+    size_t pin_bytes = 0;
+};
+std::mutex g_lane_mu;
+std::map<int, std::vector<Lane>> g_lanes;
+constexpr int N_LANES = 3;
+
+int get_lanes(std::vector<Lane>** out) {
+    std::lock_guard<std::mutex> lk(g_lane_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { g_last_error = "daqp_b200: no CUDA device available (this library has no CPU path)"; return -1; }
+    auto& v = g_lanes[dev];
+    if (v.empty()) {
+        v.resize(N_LANES);
+        int rc = default_handle(&v[0].h); // lane 0 is the process-wide default engine (single calls reuse its buffers)
+        if (rc) { v.clear(); return rc; }
+        for (int i = 1; i < N_LANES; i++) {
+            rc = daqp_b200_create(&v[i].h, dev);
+            if (rc) { v.clear(); return rc; }
+        }
+    }
+    *out = &v;
+    return 0;
+}
+
+template <typename F> void parallel_for(size_t count, size_t min_per_thread, F fn) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(hw, 8), count / std::max<size_t>(1, min_per_thread)));
+    if (nt <= 1) { fn(0, count); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back([=]() { fn(count * t / nt, count * (t + 1) / nt); });
+    for (auto& t : th) t.join();
+}
+
+struct ShapeKey { int n, m, ms; bool has_f, has_s; };
+
+template <typename T> struct Aos;
+template <> struct Aos<double> { typedef DAQPProblem Problem; typedef DAQPResult Result; };
+template <> struct Aos<float> { typedef DAQPProblemF32 Problem; typedef DAQPResultF32 Result; };
+
+// one shape group on one lane: pack into the lane's pinned buffer, solve, scatter the results to the caller's structs
+template <typename T>
+int run_group(Lane& L, const ShapeKey& k, const std::vector<int>& ids, typename Aos<T>::Problem* qps, typename Aos<T>::Result* res,
+              DAQPSettings* settings) {
+    const int n = k.n, m = k.m, ms = k.ms, mA = m - ms;
+    const size_t G = ids.size();
+    const size_t nH = G * n * n, nf = k.has_f ? G * n : 0, nA = G * (size_t)mA * n, nb = G * m, nx = G * n;
+    const size_t bytes = (nH + nf + nA + 2 * nb + nx + nb + 2 * G) * sizeof(T) + (k.has_s ? nb : 0) * sizeof(int) + 2 * G * sizeof(int) + 16 * 64;
+    cudaSetDevice(L.h->device);
+    if (L.pin_bytes < bytes) {
+        if (L.pin) { cudaFreeHost(L.pin); L.pin = nullptr; L.pin_bytes = 0; }
+        if (cudaHostAlloc((void**)&L.pin, bytes, cudaHostAllocDefault) != cudaSuccess) { g_last_error = "daqp_b200: cudaHostAlloc failed"; return -3; }
+        L.pin_bytes = bytes;
+    }
+    char* q = L.pin;
+    auto take = [&](size_t count, size_t size) { char* r = q; q += (count * size + 63) / 64 * 64; return r; };
+    T* H = (T*)take(nH, sizeof(T)); T* f = (T*)take(nf, sizeof(T));
+    T* A = (T*)take(nA, sizeof(T)); T* bu = (T*)take(nb, sizeof(T));
+    T* bl = (T*)take(nb, sizeof(T)); int* se = (int*)take(k.has_s ? nb : 0, sizeof(int));
+    T* x = (T*)take(nx, sizeof(T)); T* lam = (T*)take(nb, sizeof(T));
+    T* fv = (T*)take(G, sizeof(T)); T* slack = (T*)take(G, sizeof(T));
+    int* flag = (int*)take(G, sizeof(int)); int* it = (int*)take(G, sizeof(int));
+    parallel_for(G, 256, [&](size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; g++) {
+            const auto& p = qps[ids[g]];
+            memcpy(H + g * n * n, p.H, sizeof(T) * n * n);
+            if (k.has_f) memcpy(f + g * n, p.f, sizeof(T) * n);
+            if (mA > 0) memcpy(A + g * (size_t)mA * n, p.A, sizeof(T) * mA * n);
+            if (m > 0) { memcpy(bu + g * m, p.bupper, sizeof(T) * m); memcpy(bl + g * m, p.blower, sizeof(T) * m); }
+            if (k.has_s) memcpy(se + g * m, p.sense, sizeof(int) * m);
+            fv[g] = res[ids[g]].fval; // the reference leaves fval untouched when there is no linear term
+            slack[g] = 0;
+        }
+    });
+    DAQPB200Diag dg{};
+    if constexpr (sizeof(T) == sizeof(c_float)) dg.soft_slack = slack;
+    DAQPB200Stats before{}, after{};
+    daqp_b200_get_stats(L.h, &before, 0);
+    int rc = solve_packed_impl<T>(L.h, (int)G, n, m, ms, H, k.has_f ? f : nullptr, A, bu, bl, k.has_s ? se : nullptr, settings, x, lam,
+                                  fv, flag, it, sizeof(T) == sizeof(c_float) ? &dg : nullptr);
+    if (rc) return rc;
+    daqp_b200_get_stats(L.h, &after, 0);
+    const T t_setup = (T)(1e-3 * (after.setup_ms - before.setup_ms)), t_solve = (T)(1e-3 * (after.solve_ms - before.solve_ms));
+    parallel_for(G, 1024, [&](size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; g++) {
+            auto& r = res[ids[g]];
+            r.exitflag = flag[g];
+            r.setup_time = t_setup; r.solve_time = t_solve;
+            r.iter = it[g];
+            if (it[g] <= 0) continue; // setup failures leave x untouched (api.c:69-72): exit flags raised before the solve
+            memcpy(r.x, x + g * n, sizeof(T) * n);
+            if (r.lam && m > 0) memcpy(r.lam, lam + g * m, sizeof(T) * m);
+            if (k.has_f) r.fval = fv[g];
+            r.soft_slack = slack[g];
+        }
+    });
+    return 0;
+}
+
+template <typename T>
+int quadprog_batch_impl(int N, typename Aos<T>::Problem* qps, typename Aos<T>::Result* res, DAQPSettings* settings) {
+    if (N <= 0) return 0;
+    typedef std::tuple<int, int, int, bool, bool> Key;
+    std::map<Key, std::vector<int>> groups;
     for (int i = 0; i < N; i++) {
-        const DAQPProblem& q = qps[i];
+        const auto& q = qps[i];
         res[i].nodes = 1; res[i].soft_slack = 0; res[i].solve_time = 0; res[i].setup_time = 0;
         const bool bad = q.H == nullptr || q.nh > 1 || q.problem_type != 0 || q.n < 1 || q.m < q.ms || q.ms > q.n ||
                          (q.m > q.ms && q.A == nullptr) || (q.m > 0 && (q.bupper == nullptr || q.blower == nullptr));
         if (bad) { res[i].exitflag = DAQP_EXIT_UNSUPPORTED; res[i].iter = 0; continue; }
         groups[std::make_tuple(q.n, q.m, q.ms, q.f != nullptr, q.sense != nullptr)].push_back(i);
     }
-    DAQPB200Handle* h = nullptr;
-    int rc = default_handle(&h);
+    if (groups.empty()) return 0;
+    std::vector<Lane>* lanes = nullptr;
+    int rc = get_lanes(&lanes);
     if (rc) return rc;
+    // largest estimated cost first (n^2 m per problem); a lane takes the next group as soon as it is free
+    std::vector<std::pair<double, const std::pair<const Key, std::vector<int>>*>> order;
     for (auto& kv : groups) {
-        const int n = std::get<0>(kv.first), m = std::get<1>(kv.first), ms = std::get<2>(kv.first), mA = m - ms;
-        const bool has_f = std::get<3>(kv.first), has_s = std::get<4>(kv.first);
-        const std::vector<int>& ids = kv.second;
-        const size_t G = ids.size();
-        std::vector<c_float> H(G * n * n), f(has_f ? G * n : 0), A(G * mA * n), bu(G * m), bl(G * m), x(G * n), lam(G * m), fv(G);
-        std::vector<int> se(has_s ? G * m : 0), flag(G), it(G);
-        std::vector<c_float> slack(G, 0);
-        DAQPB200Diag dg{};
-        dg.soft_slack = slack.data();
-        for (size_t g = 0; g < G; g++) {
-            const DAQPProblem& q = qps[ids[g]];
-            memcpy(&H[g * n * n], q.H, sizeof(c_float) * n * n);
-            if (has_f) memcpy(&f[g * n], q.f, sizeof(c_float) * n);
-            if (mA > 0) memcpy(&A[g * mA * n], q.A, sizeof(c_float) * mA * n);
-            if (m > 0) { memcpy(&bu[g * m], q.bupper, sizeof(c_float) * m); memcpy(&bl[g * m], q.blower, sizeof(c_float) * m); }
-            if (has_s) memcpy(&se[g * m], q.sense, sizeof(int) * m);
-            fv[g] = res[ids[g]].fval; // reference leaves fval untouched when there is no linear term
-        }
-        DAQPB200Stats before{}, after{};
-        daqp_b200_get_stats(h, &before, 0);
-        rc = daqp_b200_solve_packed(h, (int)G, n, m, ms, H.data(), has_f ? f.data() : nullptr, A.data(), bu.data(),
-                                    bl.data(), has_s ? se.data() : nullptr, settings, x.data(), lam.data(), fv.data(),
-                                    flag.data(), it.data(), &dg);
-        if (rc) return rc;
-        daqp_b200_get_stats(h, &after, 0);
-        for (size_t g = 0; g < G; g++) {
-            DAQPResult& r = res[ids[g]];
-            r.exitflag = flag[g];
-            r.setup_time = 1e-3 * (after.setup_ms - before.setup_ms);
-            r.solve_time = 1e-3 * (after.solve_ms - before.solve_ms);
-            // setup failures leave x untouched (api.c:69-72): exit flags -1/-5/-6/-8 raised before the solve
-            const bool solved = it[g] > 0;
-            r.iter = it[g];
-            if (!solved) continue;
-            memcpy(r.x, &x[g * n], sizeof(c_float) * n);
-            if (r.lam && m > 0) memcpy(r.lam, &lam[g * m], sizeof(c_float) * m);
-            if (has_f) r.fval = fv[g];
-            r.soft_slack = slack[g];
-        }
+        const double n = std::get<0>(kv.first), m = std::get<1>(kv.first);
+        order.push_back({n * n * std::max(m, 1.0) * (double)kv.second.size(), &kv});
     }
+    std::sort(order.begin(), order.end(), [](auto& a, auto& b) { return a.first > b.first; });
+    auto key_of = [](const Key& t) { return ShapeKey{std::get<0>(t), std::get<1>(t), std::get<2>(t), std::get<3>(t), std::get<4>(t)}; };
+    if (order.size() == 1) return run_group<T>((*lanes)[0], key_of(order[0].second->first), order[0].second->second, qps, res, settings);
+    const int nl = (int)std::min<size_t>(lanes->size(), order.size());
+    std::vector<int> rcs((size_t)nl, 0);
+    std::vector<std::string> errs((size_t)nl);
+    std::vector<std::thread> th;
+    std::atomic<size_t> next{0};
+    for (int l = 0; l < nl; l++)
+        th.emplace_back([&, l]() {
+            for (;;) {
+                const size_t gi = next.fetch_add(1);
+                if (gi >= order.size() || rcs[l]) break;
+                rcs[l] = run_group<T>((*lanes)[l], key_of(order[gi].second->first), order[gi].second->second, qps, res, settings);
+                if (rcs[l]) errs[l] = g_last_error;
+            }
+        });
+    for (auto& t : th) t.join();
+    for (int l = 0; l < nl; l++)
+        if (rcs[l]) { g_last_error = errs[l]; return rcs[l]; }
     return 0;
+}
+} // namespace
+
+extern "C" int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQPSettings* settings) {
+    return quadprog_batch_impl<double>(N, qps, res, settings);
+}
+// the same for the single-precision ABI (the reference built with -DDAQP_SINGLE_PRECISION, include/types.h:8-12)
+extern "C" int daqp_quadprog_batch_f32(int N, DAQPProblemF32* qps, DAQPResultF32* res, DAQPSettings* settings) {
+    return quadprog_batch_impl<float>(N, qps, res, settings);
 }
 
 extern "C" void daqp_quadprog(DAQPResult* res, DAQPProblem* qp, DAQPSettings* settings) {

@@ -39,50 +39,12 @@ def partition_by_cost(costs: Sequence[float], world: int) -> list[np.ndarray]:
 
 def scatter_solve_gather(arrays: dict | None, n: int, m: int, ms: int, solve_local: Callable[[dict], dict], src: int = 0,
                          device=None) -> dict | None:
-    """Rank ``src`` holds the whole batch (dict of torch tensors H, f, A, bupper, blower with leading dim N); every
-    rank receives its block, runs ``solve_local`` on it and the results (x, lam, fval, exitflag, iter) are gathered
-    back on ``src``. Other ranks pass ``arrays=None`` and get ``None`` back."""
-    import torch
-    import torch.distributed as dist
-    rank, world = dist.get_rank(), dist.get_world_size()
-    meta = [None]
-    if rank == src:
-        meta = [(int(arrays["H"].shape[0]), str(arrays["H"].dtype))]
-    dist.broadcast_object_list(meta, src=src)
-    N = meta[0][0]
-    blocks = partition(N, world)
-    lo, hi = blocks[rank]
-    dev = device if device is not None else (arrays["H"].device if rank == src else torch.device("cpu"))
-    mA = m - ms
-    shapes = {"H": (n, n), "f": (n,), "A": (mA, n), "bupper": (m,), "blower": (m,)}
-    local = {}
-    for key, shp in shapes.items():
-        recv = torch.empty((hi - lo,) + shp, dtype=torch.float64, device=dev)
-        if rank == src:
-            chunks = [arrays[key][a:b].contiguous().to(dev) for a, b in blocks]
-            # scatter needs equally sized chunks: pad the short ones, receivers trim
-            width = max(b - a for a, b in blocks)
-            padded = [torch.cat([c, c.new_zeros((width - c.shape[0],) + shp)]) if c.shape[0] < width else c for c in chunks]
-            buf = torch.empty((width,) + shp, dtype=torch.float64, device=dev)
-            dist.scatter(buf, padded, src=src)
-        else:
-            width = max(b - a for a, b in blocks)
-            buf = torch.empty((width,) + shp, dtype=torch.float64, device=dev)
-            dist.scatter(buf, None, src=src)
-        recv.copy_(buf[: hi - lo])
-        local[key] = recv
-    res = solve_local(local)
-    out = {} if rank == src else None
-    width = max(b - a for a, b in blocks)
-    for key in ("x", "lam", "fval", "exitflag", "iter"):
-        t = res[key]
-        pad = t.new_zeros((width,) + tuple(t.shape[1:]))
-        pad[: t.shape[0]] = t
-        gathered = [torch.empty_like(pad) for _ in range(world)] if rank == src else None
-        dist.gather(pad, gathered, dst=src)
-        if rank == src:
-            out[key] = torch.cat([g[: b - a] for g, (a, b) in zip(gathered, blocks)])
-    return out
+    """Rank ``src`` holds the whole batch (dict of torch tensors H, A, bupper, blower and optionally f and sense -- int32
+    warm-start / equality / soft bits -- with leading dim N); every rank receives its block of EVERY array present, runs
+    ``solve_local`` on it and the results (x, lam, fval, exitflag, iter, in their own dtypes) are gathered back on
+    ``src``. Other ranks pass ``arrays=None`` and get ``None`` back. (n, m, ms are kept for the callers' convenience:
+    the shapes travel with the tensors.)"""
+    return scatter_apply_gather(arrays, solve_local, src=src, device=device)
 
 
 def scatter_apply_gather(arrays: dict | None, apply_local: Callable[[dict], dict], src: int = 0, device=None) -> dict | None:

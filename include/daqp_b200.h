@@ -23,6 +23,8 @@
 #ifndef DAQP_B200_H
 #define DAQP_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -173,9 +175,29 @@ int daqp_first_violating(c_float* x, c_float* A, c_float* bu, c_float* bl, int n
 /* ---- batch entry points (new) --------------------------------------------------------------------------- */
 
 /* N independent problems, identical in effect to N calls of daqp_quadprog(&res[i], &qps[i], settings).
- * Problems may differ in (n, m, ms); they are grouped by shape internally. Returns 0, or a negative CUDA-side
- * error code (then no result field is valid). */
+ * Problems may differ in (n, m, ms): they are grouped by shape and the groups run side by side on a few lanes
+ * (sub-engines with their own streams and pinned staging), largest estimated cost first. Returns 0, or a negative
+ * CUDA-side error code (then no result field is valid). */
 int daqp_quadprog_batch(int N, DAQPProblem* qps, DAQPResult* res, DAQPSettings* settings);
+
+/* The same for callers of the reference's SINGLE-PRECISION build (-DDAQP_SINGLE_PRECISION, include/types.h:8-12): the
+ * two structs with c_float = float (settings stay the double struct and are rounded to float like the reference's
+ * constants). Arithmetic is fp32 end to end; plain inequality / equality / warm-start path (no soft constraints). */
+typedef struct {
+    int n, m, ms;
+    float *H, *f, *A, *bupper, *blower;
+    int* sense;
+    int* break_points;
+    int nh;
+    int problem_type;
+} DAQPProblemF32;
+typedef struct {
+    float *x, *lam;
+    float fval, soft_slack;
+    int exitflag, iter, nodes;
+    float solve_time, setup_time;
+} DAQPResultF32;
+int daqp_quadprog_batch_f32(int N, DAQPProblemF32* qps, DAQPResultF32* res, DAQPSettings* settings);
 
 typedef struct DAQPB200Handle DAQPB200Handle;
 
@@ -207,6 +229,20 @@ int daqp_b200_solve_packed(DAQPB200Handle* h, int N, int n, int m, int ms,
                            const DAQPSettings* settings,
                            c_float* x, c_float* lam, c_float* fval, int* exitflag, int* iter,
                            const DAQPB200Diag* diag);
+
+/* The same batch on SEVERAL GPUs of this process: the batch is cut into ndev contiguous blocks, one host thread and one
+ * engine per device, no data exchanged between devices (problems are independent). devices == NULL selects
+ * 0 .. ndev-1; ndev <= 0 selects every visible device. seconds_per_device ([ndev], may be NULL) receives the wall time
+ * each device's block took, copies included. Pinned host arrays (daqp_b200_pin) keep the copies of the devices apart. */
+int daqp_b200_solve_packed_multi(int ndev, const int* devices, int N, int n, int m, int ms,
+                                 const c_float* H, const c_float* f, const c_float* A,
+                                 const c_float* bupper, const c_float* blower, const int* sense,
+                                 const DAQPSettings* settings,
+                                 c_float* x, c_float* lam, c_float* fval, int* exitflag, int* iter,
+                                 double* seconds_per_device);
+/* Page-lock / release a caller array (cudaHostRegister / cudaHostUnregister) for callers without a CUDA toolchain. */
+int daqp_b200_pin(void* ptr, size_t bytes);
+int daqp_b200_unpin(void* ptr);
 
 /* Same with DEVICE arrays; enqueues on `stream` (a cudaStream_t; NULL = the engine's own stream) and returns
  * without synchronising. */

@@ -263,8 +263,9 @@ def test_odd_batch_sizes_keep_staging_aligned(engine, oracle):
 
 def test_c5_mixed_sizes_one_call(cuda_lib, oracle):
     """BASELINE.json config 5 size mix through daqp_quadprog_batch: n in {8,16,...,128}, m = 4 n, the number of active
-    constraints at the optimum drawn from U{0..n} (divergent iteration counts), one call for all shapes. fp64 (the
-    fp32 instantiation has no entry point yet)."""
+    constraints at the optimum drawn from U{0..n} (divergent iteration counts), one call for all shapes -- the shape
+    groups run side by side on the library's lanes, largest estimated cost first. This test is the fp64 pass (exact path
+    parity with the oracle); test_c5_mixed_sizes_fp32_one_call is the fp32 pass BASELINE.json names."""
     import daqp_b200
     rng = np.random.default_rng(55)
     probs, refs = [], []
@@ -281,6 +282,44 @@ def test_c5_mixed_sizes_one_call(cuda_lib, oracle):
         np.testing.assert_allclose(info["lam"], o.lam[0], rtol=0, atol=1e-7 * (1 + np.abs(o.lam[0]).max()))
         its.append(info["iterations"])
     assert max(its) > 10 * max(1, min(its))  # the iteration counts really diverge
+
+
+def test_c5_mixed_sizes_fp32_one_call(cuda_lib, oracle_libs, capsys):
+    """BASELINE.json config 5 as stated: fp32, mixed sizes n in {8..128}, m = 4 n, random active-set sizes, ONE call
+    (daqp_quadprog_batch_f32, the single-precision ABI of the reference). Against the oracle compiled with c_float = float
+    (pinned on the reference's -DDAQP_SINGLE_PRECISION build): every problem solved to the constructed optimum within the
+    reference's own gate (1e-4, core_tests.jl:26-30, relative to |x|), exit flags equal, and the path-mismatch RATE
+    (iteration counts that differ from the fp32 oracle) reported and bounded. The reference's tolerances sit far below
+    fp32 epsilon (dual_tol 1e-12, sing_tol 3.7e-11), so two correct fp32 implementations part on near-ties."""
+    import daqp_b200
+    orc = oracle_libs.OracleLib(single=True)
+    rng = np.random.default_rng(56)
+    probs, batches = [], []
+    for k, n in enumerate([8, 16, 24, 32, 40, 48, 56, 64, 72, 80, 88, 96, 104, 112, 120, 128] * 3):
+        na = int(rng.integers(0, n + 1))
+        b = generate_g1(1, n, 4 * n, 0, na, seed=5600 + k)
+        batches.append(b)
+        probs.append(dict(H=b.H[0], f=b.f[0], A=b.A[0], bupper=b.bupper[0], blower=b.blower[0]))
+    out = daqp_b200.quadprog_batch_f32(probs)
+    mism, worst, by_n, solved, flag_mism = 0, 0.0, {}, 0, 0
+    for (x, fval, flag, info), b in zip(out, batches):
+        o = orc.solve(b)
+        assert x.dtype == np.float32
+        flag_mism += int(flag != o.exitflag[0])
+        if flag != 1 or o.exitflag[0] != 1:
+            continue
+        solved += 1
+        err = np.abs(x - b.xref[0]).max() / (1 + np.abs(b.xref[0]).max())
+        worst = max(worst, err)
+        assert err < 1e-3, f"n={b.n}: fp32 solution {err:.2e} away from the constructed optimum"
+        d = int(info["iterations"] != o.iter[0])
+        mism += d
+        by_n[b.n] = by_n.get(b.n, 0) + d
+    rate = mism / max(1, solved)
+    with capsys.disabled():
+        print(f"\nC5 fp32, {len(out)} problems, n = 8..128: {solved} optimal in both, exit flags differ on {flag_mism}; "
+              f"path-mismatch rate vs the fp32 oracle {rate:.3f} (by n: {by_n}), worst relative |x - xref| {worst:.2e}")
+    assert solved >= 0.95 * len(out) and flag_mism <= 0.05 * len(out) and rate <= 0.25
 
 
 def test_fp32_path_vs_fp32_oracle(engine, oracle_libs):
@@ -514,6 +553,23 @@ def test_full_size_properties(engine):
     np.testing.assert_array_equal(sub.x, r.x[perm])
 
 
+def test_solve_packed_multi_matches_single(engine, oracle):
+    """daqp_b200_solve_packed_multi: the batch cut into per-device blocks (one host thread + engine each). With one GPU
+    both blocks land on device 0; the answers must equal the single-engine call bit for bit either way."""
+    import torch
+    import daqp_b200
+    b = generate_g1(4001, 20, 60, 4, 16, seed=93)
+    b.sense[::3, 7] = 1  # some warm-start bits: sense must travel with its block
+    one = engine.solve_batch(b.H, b.f, b.A, b.bupper, b.blower, b.sense, ms=b.ms)
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    r, secs = daqp_b200.solve_batch_multi(b.H, b.f, b.A, b.bupper, b.blower, b.sense, ms=b.ms, devices=devs)
+    for k in ("x", "lam", "fval", "exitflag", "iter"):
+        np.testing.assert_array_equal(getattr(r, k), getattr(one, k))
+    assert (secs > 0).all()
+    o = oracle.solve(b.slice(0, 300), use_sense=True)
+    np.testing.assert_array_equal(r.iter[:300], o.iter)
+
+
 def _nccl_worker(rank, world, port, tmp):
     import os, sys
     import torch
@@ -537,11 +593,25 @@ def _nccl_worker(rank, world, port, tmp):
         return eng.solve_batch_device(loc["H"], loc["f"], loc["A"], loc["bupper"], loc["blower"], None, ms=ms)
 
     out = scatter_solve_gather(arrays, n, m, ms, solve_local, src=0, device=dev)
+    ok = True
     if rank == 0:
         whole = eng.solve_batch_device(*(arrays[k] for k in ("H", "f", "A", "bupper", "blower")), None, ms=ms)
         torch.cuda.synchronize()
         ok = all(torch.equal(out[k], whole[k]) for k in ("x", "lam", "iter", "exitflag"))
         ok = ok and float((out["x"].cpu() - torch.from_numpy(b.xref)).abs().max()) < 1e-8
+        # second pass: warm-start bits (int32 sense) travel with their block -> one iteration per problem
+        sense = torch.zeros((1001, m), dtype=torch.int32, device=dev)
+        sense[whole["lam"] > 1e-12] = 1
+        sense[whole["lam"] < -1e-12] = 3
+        arrays = dict(arrays, sense=sense)
+
+    def solve_local_warm(loc):
+        return eng.solve_batch_device(loc["H"], loc["f"], loc["A"], loc["bupper"], loc["blower"], loc["sense"], ms=ms)
+
+    out2 = scatter_solve_gather(arrays, n, m, ms, solve_local_warm, src=0, device=dev)
+    if rank == 0:
+        ok = ok and bool((out2["iter"] == 1).all()) and bool((out2["exitflag"] == 1).all())
+        ok = ok and float((out2["x"] - whole["x"]).abs().max()) < 1e-9
         open(tmp, "w").write("ok" if ok else "mismatch")
     dist.barrier()
     dist.destroy_process_group()

@@ -74,6 +74,47 @@ def test_scatter_solve_gather_world2_gloo(oracle_libs, tmp_path):
     assert open(marker).read() == "ok"
 
 
+def _worker_sense(rank, world, port, tmp):
+    """sense (int32 warm-start / equality bits) is scattered with its block; f may be absent."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from daqp_b200.problems import QPBatch, generate_g1
+    from daqp_b200.sharding import scatter_solve_gather
+    from oracle import harness
+    n, m, ms = 8, 20, 2
+    arrays = None
+    if rank == 0:
+        b = generate_g1(23, n, m, ms, 6, seed=78)
+        cold = harness.OracleLib().solve_packed(b)
+        b.sense[cold.lam > 1e-12] = 1
+        b.sense[cold.lam < -1e-12] = 3
+        arrays = {k: torch.from_numpy(getattr(b, k)) for k in ("H", "f", "A", "bupper", "blower", "sense")}
+
+    def solve_local(loc):
+        assert loc["sense"].dtype == torch.int32
+        lb = QPBatch(n, m, ms, *(loc[k].numpy() for k in ("H", "f", "A", "bupper", "blower")), loc["sense"].numpy())
+        s = harness.OracleLib().solve_packed(lb, use_sense=True)
+        return {"x": torch.from_numpy(s.x), "iter": torch.from_numpy(s.iter), "exitflag": torch.from_numpy(s.exitflag)}
+
+    out = scatter_solve_gather(arrays, n, m, ms, solve_local, src=0)
+    if rank == 0:
+        ok = bool((out["iter"] == 1).all()) and out["iter"].dtype == torch.int32 and np.abs(out["x"].numpy() - cold.x).max() < 1e-9
+        open(tmp, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_solve_gather_carries_sense_world2_gloo(oracle_libs, tmp_path):
+    import torch.multiprocessing as mp
+    marker = str(tmp_path / "result_sense.txt")
+    mp.spawn(_worker_sense, args=(2, 29519, marker), nprocs=2, join=True)
+    assert open(marker).read() == "ok"
+
+
 def _worker_minrep(rank, world, port, tmp):
     import torch
     import torch.distributed as dist
