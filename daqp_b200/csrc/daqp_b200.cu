@@ -319,12 +319,16 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     // n > 64: a warp per problem leaves the SM nearly empty (three problems fit at n = 120) -- a team of four warps per
     // problem instead (plain fp64 path; soft constraints / workspaces / shared matrices stay on the warp kernel)
     int team = 0;
-    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 32 * TEAM_WARPS) team = TEAM_WARPS;
-    if (const char* tenv = getenv("DAQP_B200_TEAM")) { if (atoi(tenv) == 0) team = 0; }
+    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 128) team = 4;
+    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv == 2) team = 2;
+    if (const char* tenv = getenv("DAQP_B200_TEAM")) { // experiment knob: 0 = a warp per problem everywhere, 4 = teams only for n > 64
+        const int tv = atoi(tenv);
+        if (tv == 0 || (tv == 4 && team == 2)) team = 0;
+    }
     const size_t smem_solve_w = ldp_layout<T>(la, team), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
     int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
-    if (team) w_solve = (int)std::min<size_t>(TEAM_MAX_CTAS, (budget + 1024) / (smem_solve_w + 1024)); // CTAs (= problems) per SM
+    if (team) w_solve = (int)std::min<size_t>(team_max_ctas(team), (budget + 1024) / (smem_solve_w + 1024)); // CTAs (= problems) per SM
     if (w_solve < 1 || w_setup < 1) { g_last_error = "daqp_b200: problem too large for shared memory"; return -2; }
     if (const char* wenv = getenv("DAQP_B200_WARPS")) w_solve = std::max(1, std::min(w_solve, atoi(wenv))); // tuning knob
     h->stats.warps_per_sm = w_solve;
@@ -342,7 +346,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     const DevSettings<T> st = to_dev_settings<T>(settings);
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
-    const bool screening = sizeof(T) == 8 && !(tune & 2) && (team ? (m + 31) / 32 <= TEAM_SCREEN_MAX_GROUPS * TEAM_WARPS : m <= 256);
+    const bool screening = sizeof(T) == 8 && !(tune & 2) && (team ? (m + 31) / 32 <= TEAM_SCREEN_MAX_GROUPS * team : m <= 256);
     for (int p0 = 0; p0 < N; p0 += chunk) {
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);

@@ -1270,7 +1270,7 @@ struct Warp {
 // TW > 1 (team mode, n > 64): one CTA of TW warps per problem -- at n = 120 the packed factor is 58 KB, so only three
 // problems fit an SM and a warp each would leave the SM at three warps. Warp 0 runs the loop below, warps 1.. serve it.
 template <typename T, int NV, bool EXT, int TW = 1>
-__global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? TEAM_MAX_CTAS : 1) ldp_solve_kernel(const __grid_constant__ LdpArgs<T> a) {
+__global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? team_max_ctas(TW) : 1) ldp_solve_kernel(const __grid_constant__ LdpArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = uni((int)(threadIdx.x >> 5)); // uniform: so are all shared-memory bases
     const int gw = TW > 1 ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + wib);

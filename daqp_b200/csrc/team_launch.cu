@@ -4,18 +4,18 @@
 
 using namespace dq;
 
-template <int NV>
+template <int NV, int TW>
 static cudaError_t launch_team(const LdpArgs<double>& a, int grid, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<double, NV, false, TEAM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<double, NV, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ldp_solve_kernel<double, NV, false, TEAM_WARPS><<<grid, 32 * TEAM_WARPS, smem, s>>>(a);
+    ldp_solve_kernel<double, NV, false, TW><<<grid, 32 * TW, smem, s>>>(a);
     return cudaGetLastError();
 }
 
+// a.team = warps per problem (2: factor rows <= 64, 4: <= 128)
 cudaError_t daqp_b200_launch_solve_team(const LdpArgs<double>& a, int nv, int grid, size_t smem, cudaStream_t s) {
-    switch (nv) {
-        case 3: return launch_team<3>(a, grid, smem, s);
-        case 4: return launch_team<4>(a, grid, smem, s);
-        default: return cudaErrorNotSupported;
-    }
+    if (a.team == 2 && nv == 2) return launch_team<2, 2>(a, grid, smem, s);
+    if (a.team == 4 && nv == 3) return launch_team<3, 4>(a, grid, smem, s);
+    if (a.team == 4 && nv == 4) return launch_team<4, 4>(a, grid, smem, s);
+    return cudaErrorNotSupported;
 }

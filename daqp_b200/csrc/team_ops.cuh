@@ -37,8 +37,12 @@ struct TeamBox {
 };
 constexpr int TEAM_BOX_BYTES = 384;
 static_assert(sizeof(TeamBox) <= TEAM_BOX_BYTES, "TeamBox grew past its slot");
-constexpr int TEAM_WARPS = 4;    // warps per problem in team mode (factor rows <= 128)
-constexpr int TEAM_MAX_CTAS = 3; // resident teams per SM the kernel is compiled for (__launch_bounds__)
+// Team widths: four warps per problem for 64 < n + 1 <= 128 (three problems fit an SM: twelve warps), two warps per
+// problem for 32 < n + 1 <= 64 (the per-problem block without a staging arena is 14 KB at n = 50: twelve to fourteen
+// problems fit, 24 - 28 warps instead of the 12 a warp per problem gives -- the single-warp kernel is bound by dependent
+// latency at three warps per scheduler, not by issue slots).
+constexpr int TEAM_WARPS = 4;
+__host__ __device__ constexpr int team_max_ctas(int tw) { return tw == 2 ? 12 : 3; } // resident teams per SM (__launch_bounds__)
 enum { TC_EXIT = 0, TC_FWD, TC_BWD, TC_REMOVE, TC_DOTS, TC_PRIMAL, TC_SCAN32, TC_SCAN64 };
 
 #define TEAM_SMEM                                                   \
