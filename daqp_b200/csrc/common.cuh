@@ -198,6 +198,16 @@ template <> __device__ __forceinline__ float rsqrt_exact<float>(float x) { retur
 
 __host__ __device__ __forceinline__ int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
+// Largest dynamic shared memory a kernel of the current device may opt in to. Every launcher raises its kernel's limit to
+// THIS value, never to the launch's own size: the attribute is per kernel function, and two host threads (lanes of the
+// array-of-struct batch) launching the same instantiation with different sizes would otherwise lower it under each other.
+inline int max_optin_smem() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return v;
+}
+
 // packed strict-lower storage of the unit-lower factor: row i holds L[i][0..i-1] at offset i(i-1)/2
 __host__ __device__ __forceinline__ int loff(int i) { return (i * (i - 1)) >> 1; }
 // packed upper-triangular (by rows) offset such that (R + roff(i,n))[j] is element (i,j), j >= i

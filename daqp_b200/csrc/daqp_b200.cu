@@ -228,7 +228,7 @@ static size_t scratch_per_problem(int n, int m, int ldm, int ldn) {
 
 template <typename T, int NV, bool EXT>
 static cudaError_t launch_solve_x(const LdpArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NV, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<T, NV, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     ldp_solve_kernel<T, NV, EXT><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
@@ -253,7 +253,7 @@ cudaError_t daqp_b200_launch_setup_split(const SetupArgs<double>& a, int num_sms
 
 template <typename T, int NGS>
 static cudaError_t launch_setup(const SetupArgs<T>& a, int grid, int block, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(qp_setup_kernel<T, NGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qp_setup_kernel<T, NGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     qp_setup_kernel<T, NGS><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
@@ -900,7 +900,7 @@ static int init_active_launch(DAQPB200Handle* h, int N, int n, int m, int ms, co
     ia.sense = dsense;
     const size_t smem = ia_smem_per_warp(n) * IA_WARPS;
     if (smem > h->smem_optin) { g_last_error = "daqp_b200: n too large for the init_active tile"; return -2; }
-    CK(cudaFuncSetAttribute(init_active_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(init_active_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem()));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, h->smem_optin / (smem + 1024)));
     init_active_kernel<<<std::min(h->num_sms * per_sm, (N + IA_WARPS - 1) / IA_WARPS), 32 * IA_WARPS, smem, s>>>(ia);
     CK(cudaGetLastError());

@@ -19,7 +19,7 @@ static cudaError_t launch_factor(const SetupArgs<double>& a, int num_sms, size_t
         if (ctas < 1) return cudaErrorInvalidConfiguration;
         block = 32 * TW; smem = per; grid = std::min(num_sms * ctas, a.P);
     }
-    cudaError_t e = cudaFuncSetAttribute(qp_factor_kernel<double, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qp_factor_kernel<double, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     qp_factor_kernel<double, TW><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
@@ -30,7 +30,7 @@ static cudaError_t launch_product(const SetupArgs<double>& a, int num_sms, size_
     const size_t smem = product_smem(a.n);
     const int ctas = (int)std::min<size_t>(NCT <= 9 ? 4 : 3, (smem_optin + 1024) / (smem + 1024));
     if (ctas < 1) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(qp_product_kernel<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qp_product_kernel<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     qp_product_kernel<NCT><<<std::min(num_sms * ctas, a.P), 128, smem, s>>>(a);
     return cudaGetLastError();

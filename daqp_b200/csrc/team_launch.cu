@@ -6,7 +6,7 @@ using namespace dq;
 
 template <int NV, int TW>
 static cudaError_t launch_team(const LdpArgs<double>& a, int grid, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<double, NV, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ldp_solve_kernel<double, NV, false, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     ldp_solve_kernel<double, NV, false, TW><<<grid, 32 * TW, smem, s>>>(a);
     return cudaGetLastError();
