@@ -247,6 +247,7 @@ static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t
 }
 // team mode (n > 64, plain fp64 path): instantiated in team_launch.cu (separate translation unit: compiled in parallel)
 cudaError_t daqp_b200_launch_solve_team(const LdpArgs<double>& a, int nv, int grid, size_t smem, cudaStream_t s);
+cudaError_t daqp_b200_launch_solve_regs(const LdpArgs<double>& a, int nv, int grid, int block, size_t smem, cudaStream_t s);
 
 // split QP -> LDP transform (fp64, n <= 127): factor kernel + tensor-core product kernel, instantiated in setup2_launch.cu
 cudaError_t daqp_b200_launch_setup_split(const SetupArgs<double>& a, int num_sms, size_t smem_optin, cudaStream_t s);
@@ -320,12 +321,16 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     // problem instead (plain fp64 path; soft constraints / workspaces / shared matrices stay on the warp kernel)
     int team = 0;
     if (sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 128) team = 4;
-    if (sizeof(T) == 8 && ns_max == 0 && !ps && nv == 2) team = 2;
-    if (const char* tenv = getenv("DAQP_B200_TEAM")) { // experiment knob: 0 = a warp per problem everywhere, 4 = teams only for n > 64
-        const int tv = atoi(tenv);
-        if (tv == 0 || (tv == 4 && team == 2)) team = 0;
+    if (const char* tenv = getenv("DAQP_B200_TEAM")) { // experiment knob: 0 = a warp per problem everywhere; 2 = two-warp teams for
+        const int tv = atoi(tenv);                        // 32 < n + 1 <= 64 as well (measured on C3: 220 ms against 105 ms for a
+        if (tv == 0) team = 0;                            // warp per problem -- the iteration is bound by L2 round trips either way,
+        if (tv == 2 && sizeof(T) == 8 && ns_max == 0 && !ps && nv == 2) team = 2; // and the fork-join adds barriers to each)
     }
-    const size_t smem_solve_w = ldp_layout<T>(la, team), smem_setup_w = setup_smem_per_warp<T>(n);
+    // n <= 63, plain fp64 path: the register-staged warp kernel (no staging arena in shared memory: 16 problems per SM at
+    // n = 50 instead of 12). DAQP_B200_REGSTAGE=0 selects the cp.async-staged kernel (the round-1 headline kernel).
+    bool regstage = sizeof(T) == 8 && ns_max == 0 && !ps && team == 0 && nv <= 2;
+    if (const char* renv = getenv("DAQP_B200_REGSTAGE")) regstage = regstage && atoi(renv) != 0;
+    const size_t smem_solve_w = ldp_layout<T>(la, regstage ? -1 : team), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
     int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
     if (team) w_solve = (int)std::min<size_t>(team_max_ctas(team), (budget + 1024) / (smem_solve_w + 1024)); // CTAs (= problems) per SM
@@ -431,6 +436,12 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
             if constexpr (sizeof(T) == 8)
                 e = daqp_b200_launch_solve_team(la, nv, std::min(grid_max * w_solve, P), smem_solve_w, stream);
             if (e != cudaSuccess) return fail("ldp_solve_kernel (team) launch", e, __LINE__);
+            h->stats.solve_launches++;
+        } else if (regstage) {
+            cudaError_t e = cudaErrorNotSupported;
+            if constexpr (sizeof(T) == 8)
+                e = daqp_b200_launch_solve_regs(la, nv, std::min(grid_max, (P + w_solve - 1) / w_solve), 32 * w_solve, smem_solve_w * w_solve, stream);
+            if (e != cudaSuccess) return fail("ldp_solve_kernel (register-staged) launch", e, __LINE__);
             h->stats.solve_launches++;
         } else if (!ps || ps->phase == 2) {
             const int grid = std::min(grid_max, (P + w_solve - 1) / w_solve);

@@ -42,6 +42,7 @@ constexpr int RB = 6;     // active rows per cp.async chunk of the row passes (t
 constexpr int QRING = 2;  // depth of the screening scan's ring (quads of columns in flight); 3 buys nothing (the scan
                           // is not latency-bound) and costs the twelfth resident problem, 4 -> 125 ms, 1 -> 119 ms
 constexpr int SCR_PITCH = 34; // doubles per parked row of partial dot products (16-byte aligned rows)
+constexpr int TW_REGS = 0;    // Warp<..., TW = TW_REGS>: one warp per problem, streaming phases staged through registers (no arena)
 
 // Warp-uniform values are made PROVABLY uniform for the compiler by reading them from lane 0: loops and branches on
 // them then compile to plain uniform control flow (no BSSY/BSYNC reconvergence bookkeeping, no BRA.DIV in front of
@@ -112,7 +113,7 @@ struct LdpArgs {
 template <typename T>
 inline size_t ldp_layout(LdpArgs<T>& a, int team = 0) {
     const int V = VecOf<T>::N, cap = a.cap;
-    a.team = team;
+    a.team = team; // (-1: one warp per problem without the staging arena, the register-staged kernel)
     a.team_prefix = 0;
     if (team > 1) { // box | tmp[32 team] | pv[32 team] | bv[32 team] | side[team-1][32]
         const unsigned nt = 32u * team, w = (unsigned)sizeof(T);
@@ -140,7 +141,7 @@ inline size_t ldp_layout(LdpArgs<T>& a, int team = 0) {
     a.oarena = (int)bytes;
     const size_t slab = (size_t)a.m * 16, rowb = (size_t)a.ldn * sizeof(T);
     a.rowbuf = (unsigned)std::max<size_t>(RB * rowb, (size_t)RB * SCR_PITCH * sizeof(T));
-    if (team <= 1) bytes += (a.m <= 256) ? std::max<size_t>(QRING * slab, 2 * (size_t)a.rowbuf) : 2 * (size_t)a.rowbuf;
+    if (team == 0 || team == 1) bytes += (a.m <= 256) ? std::max<size_t>(QRING * slab, 2 * (size_t)a.rowbuf) : 2 * (size_t)a.rowbuf;
     bytes = (bytes + 15) / 16 * 16; // (a team stages through registers: no arena)
     a.per_warp_bytes = (unsigned)bytes;
     a.sMt = (unsigned)((size_t)a.n * a.ldm * sizeof(T));
@@ -195,7 +196,7 @@ __device__ __noinline__ void issue_rows_fn(const int* ids, int nrows, unsigned b
 template <typename T, int NV, bool EXT, int TW = 1>
 struct Warp {
     static_assert(!(EXT && TW > 1), "team mode covers the plain path");
-    static_assert(32 * TW >= 32 * NV || TW == 1, "a team holds one factor row per thread");
+    static_assert(32 * TW >= 32 * NV || TW <= 1, "a team holds one factor row per thread");
     static constexpr int V = VecOf<T>::N;
     static constexpr int NG = (NV + 1) / 2;                         // 128-bit column groups of a row: n <= 32 NV - 1
     static constexpr int ROWB = (NG == 1) ? 8 : (NG == 2 ? 4 : 2);  // active rows fetched per batch
@@ -367,6 +368,7 @@ struct Warp {
         }
         if (kk > 0) {
             if constexpr (TW > 1) team_run(TC_DOTS, add, kk);
+            if constexpr (TW == TW_REGS) dots_regs(kk, mi, okg);
             // l_j = M_{WS[j]} . m_add: per-lane partial products of a chunk's rows are parked in the consumed buffer and
             // summed with a transposed read (lane = (row, quarter)) instead of RB full shuffle reductions.
             if constexpr (TW == 1) {
@@ -673,6 +675,7 @@ struct Warp {
             __syncwarp();
             return;
         }
+        if constexpr (TW == TW_REGS) { primal_regs(); return; }
         const char* M = Mr() + (size_t)(V * lane) * sizeof(T);
         const unsigned rstride = a.ldn * (unsigned)sizeof(T);
         const T* ls = lams();
@@ -922,6 +925,22 @@ struct Warp {
     __device__ __forceinline__ int scan_infeasible() {
         count(0);
         if constexpr (TW > 1) return team_scan_leader();
+        if constexpr (sizeof(T) == 8 && TW == TW_REGS) {
+            if (a.Mt32 != nullptr) {
+                int r;
+                switch ((a.m + 31) >> 5) {
+                    case 1: r = scan_screen_regs<1>(); break;
+                    case 2: r = scan_screen_regs<2>(); break;
+                    case 3: r = scan_screen_regs<3>(); break;
+                    case 4: r = scan_screen_regs<4>(); break;
+                    case 5: r = scan_screen_regs<5>(); break;
+                    case 6: r = scan_screen_regs<6>(); break;
+                    case 7: r = scan_screen_regs<7>(); break;
+                    default: r = scan_screen_regs<8>(); break;
+                }
+                if (r != -2) return r;
+            }
+        } else
         if constexpr (sizeof(T) == 8) {
             if (a.Mt32 != nullptr) { // screening in fp32 (host enables it for m <= 256)
                 int r;
@@ -949,6 +968,193 @@ struct Warp {
         warp_argmin(best, key);
         key = uni(key);
         return key == INT_MAX ? -1 : key;
+    }
+
+    // =====================================================================================================================
+    // Register-staged variants (TW == TW_REGS): the same three streaming phases WITHOUT the cp.async staging arena. At
+    // n = 50 the arena is 4.8 KB of a warp's 18.6 KB: without it sixteen problems fit an SM instead of twelve, and the
+    // kernel is bound by dependent latency at three warps per scheduler, not by any unit's throughput (ncu: issue slots
+    // 42 %, shared-memory pipe 51 %, L2 25 %, DRAM 3 % of peak). Loads go global/L2 -> registers in program order
+    // (asm volatile), a batch in flight while the previous one is consumed.
+    // =====================================================================================================================
+    // l_j = M_{WS[j]} . m_add for j < kk into row kk of the factor: batches of DB rows, one transposed butterfly per batch
+    __device__ __forceinline__ void dots_regs(int kk, const T (&mi)[NG][V], const bool (&okg)[NG]) {
+        constexpr int DB = 8;
+        const T* M = reinterpret_cast<const T*>(Mr()) + V * lane;
+        const unsigned ldn = a.ldn;
+        const int* ws = WS();
+        T* Lk = L() + loff(kk);
+        const uint64_t pol = policy_evict_last();
+#pragma unroll 1
+        for (int j0 = 0; j0 < kk; j0 += DB) {
+            T t[DB][NG][V];
+#pragma unroll
+            for (int rr = 0; rr < DB; rr++) {
+                const T* row = M + (size_t)((unsigned)ws[min(j0 + rr, kk - 1)] * ldn);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+#pragma unroll
+                    for (int e = 0; e < V; e++) t[rr][g][e] = 0;
+                    if (okg[g]) ldg_vec_hint_ordered<T>(row + 32 * V * g, t[rr][g], pol);
+                }
+            }
+            T pj[DB];
+#pragma unroll
+            for (int rr = 0; rr < DB; rr++) {
+                pj[rr] = 0;
+#pragma unroll
+                for (int g = 0; g < NG; g++)
+#pragma unroll
+                    for (int e = 0; e < V; e++) pj[rr] += t[rr][g][e] * mi[g][e];
+            }
+            const T total = warp_sum_multi<DB>(pj, lane);
+            const int jr = j0 + multi_index<DB>(lane);
+            if ((lane & (32 / DB - 1)) == 0 && jr < kk) Lk[jr] = total;
+        }
+        __syncwarp();
+    }
+
+    // u = -Mk' lam*, fval = |u|^2 : FMAs in index order (auxiliary.c:54-68), UNR rows in flight
+    __device__ __forceinline__ void primal_regs() {
+        constexpr int UNR = 8;
+        const T* M = reinterpret_cast<const T*>(Mr()) + V * lane;
+        const unsigned ldn = a.ldn;
+        const T* ls = lams();
+        const int* ws = WS();
+        const int kk = uni(k);
+        const uint64_t pol = policy_evict_last();
+        T acc[NG][V];
+        bool okg[NG];
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            okg[g] = V * (lane + 32 * g) < a.ldn;
+#pragma unroll
+            for (int e = 0; e < V; e++) acc[g][e] = 0;
+        }
+#pragma unroll 1
+        for (int i0 = 0; i0 < kk; i0 += UNR) {
+            T t[UNR][NG][V];
+#pragma unroll
+            for (int rr = 0; rr < UNR; rr++) {
+                const T* row = M + (size_t)((unsigned)ws[min(i0 + rr, kk - 1)] * ldn);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+#pragma unroll
+                    for (int e = 0; e < V; e++) t[rr][g][e] = 0;
+                    if (okg[g]) ldg_vec_hint_ordered<T>(row + 32 * V * g, t[rr][g], pol);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < UNR; rr++) {
+                const T li = (i0 + rr < kk) ? ls[i0 + rr] : (T)0; // rows past the end re-read the last one, times zero
+#pragma unroll
+                for (int g = 0; g < NG; g++)
+#pragma unroll
+                    for (int e = 0; e < V; e++) acc[g][e] -= t[rr][g][e] * li;
+            }
+        }
+        T* up = u();
+        T part = 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const int c = V * (lane + 32 * g);
+            if (c < a.ldn) {
+#pragma unroll
+                for (int e = 0; e < V; e++) { up[c + e] = acc[g][e]; u32()[c + e] = (float)acc[g][e]; part += acc[g][e] * acc[g][e]; }
+            }
+        }
+        fval = uni(warp_sum(part));
+        __syncwarp();
+    }
+
+    // fp32 screening scan (see scan_screen for the error bound and the decision rule), quads of columns through two
+    // register buffers per owned row instead of the shared-memory ring
+    template <int NR>
+    __device__ __forceinline__ int scan_screen_regs() {
+        const bool own_last = lane + 32 * (NR - 1) < a.m;
+        float acc[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) acc[r] = 0.f;
+        const unsigned slab = (unsigned)a.m * 16u;
+        const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)pmat() * a.sMt32 + 16 * lane;
+        const int nq = (a.n + 3) >> 2;
+        const uint64_t pol = policy_evict_last();
+        const unsigned ub = smem_u32(u32());
+        float b0[NR][4], b1[NR][4];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) { b0[r][e] = 0.f; b1[r][e] = 0.f; }
+            ldg_vec_pred<float>(src + 512 * r, b0[r], pol, r < NR - 1 || own_last);
+        }
+#pragma unroll 1
+        for (int q = 0; q < nq; q += 2) { // two quads per trip: static buffer names, the next quad in flight while this one is used
+            const bool more1 = q + 1 < nq, more2 = q + 2 < nq;
+            const char* s1 = src + (size_t)min(q + 1, nq - 1) * slab;
+#pragma unroll
+            for (int r = 0; r < NR; r++) ldg_vec_pred<float>(s1 + 512 * r, b1[r], pol, more1 && (r < NR - 1 || own_last));
+            float uq[4];
+            lds_vec<float>(ub + 16 * q, uq);
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[r] += b0[r][e] * uq[e];
+            const char* s2 = src + (size_t)min(q + 2, nq - 1) * slab;
+#pragma unroll
+            for (int r = 0; r < NR; r++) ldg_vec_pred<float>(s2 + 512 * r, b0[r], pol, more2 && (r < NR - 1 || own_last));
+            if (more1) {
+                lds_vec<float>(ub + 16 * (q + 1), uq);
+#pragma unroll
+                for (int r = 0; r < NR; r++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[r] += b1[r][e] * uq[e];
+            }
+        }
+        double bu[NR], bl[NR], bs[NR]; // (loaded after the products here: registers are the scarce resource)
+        {
+            const double* dup = reinterpret_cast<const double*>(du()) + lane;
+            const double* dlp = reinterpret_cast<const double*>(dl()) + lane;
+            const double* scp = reinterpret_cast<const double*>(sc()) + lane;
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                bu[r] = bl[r] = bs[r] = 0;
+                if (r < NR - 1 || own_last) { bu[r] = __ldg(dup + 32 * r); bl[r] = __ldg(dlp + 32 * r); bs[r] = __ldg(scp + 32 * r); }
+            }
+        }
+        const double unorm = (double)sqrtf((float)fval) * 1.0001 + 1e-22;
+        const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * unorm;
+        const double ep = -(double)a.st.primal_tol;
+        const unsigned char* se = sense();
+        double best = 1e300, second = 1e300;
+        int key = INT_MAX;
+        bool best_sure = false;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const int row = lane + 32 * r;
+            const double mu = (double)acc[r];
+            const double cu = bu[r] - mu, cl = mu - bl[r];
+            const bool lower = cl < cu;
+            const double cand = lower ? cl : cu;
+            const double bound = ep * bs[r];
+            const bool possible = (r < NR - 1 || own_last) && !(se[row] & (B_ACTIVE + B_IMMUTABLE)) && cand - delta < bound;
+            const bool nb = possible && cand < best;
+            second = nb ? best : ((possible && cand < second) ? cand : second);
+            best_sure = nb ? (cand + delta < bound) : best_sure;
+            key = nb ? 2 * row + (int)lower : key;
+            best = nb ? cand : best;
+        }
+        double wbest = best;
+        int wkey = key;
+        warp_argmin(wbest, wkey);
+        wkey = uni(wkey);
+        if (wkey == INT_MAX) return -1;
+        wbest = uni(wbest);
+        double other = (key == wkey) ? second : best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) other = fmin(other, __shfl_xor_sync(FULL, other, o));
+        const bool sure = __any_sync(FULL, key == wkey && best_sure);
+        if (sure && uni(other - wbest > 2.0 * delta)) return wkey;
+        return -2;
     }
 
     // ---- team mode (TW > 1), leader side: the heavy phases live in team_ops.cuh; the leader posts a command, runs its own

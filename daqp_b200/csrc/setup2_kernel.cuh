@@ -20,6 +20,7 @@
 
 namespace dq {
 
+constexpr int FACTOR_MAX_WARPS = 20; // problems per CTA of the factor kernel (one warp each): 20 x 32 threads x 102 registers = the register file
 constexpr int SI_UNC = 1, SI_DIAG = 2, SI_FIXED = 4, SI_BADBOUNDS = 8, SI_HAS_SENSE = 16;
 
 template <typename T>
@@ -36,7 +37,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 
 // ---- kernel 1: Hessian factor --------------------------------------------------------------------------------------
 template <typename T, int TW>
-__global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, 1) qp_factor_kernel(const SetupArgs<T> a) {
+__global__ void __launch_bounds__(TW > 1 ? 32 * TW : 32 * FACTOR_MAX_WARPS, 1) qp_factor_kernel(const SetupArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = 32 * TW;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

@@ -11,7 +11,7 @@ static cudaError_t launch_factor(const SetupArgs<double>& a, int num_sms, size_t
     int grid, block;
     size_t smem;
     if (TW == 1) {
-        const int w = (int)std::min<size_t>(16, smem_optin / per);
+        const int w = (int)std::min<size_t>(FACTOR_MAX_WARPS, smem_optin / per);
         if (w < 1) return cudaErrorInvalidConfiguration;
         block = 32 * w; smem = per * w; grid = std::min(num_sms, (a.P + w - 1) / w);
     } else {
