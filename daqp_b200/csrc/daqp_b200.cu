@@ -326,10 +326,11 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         if (tv == 0) team = 0;                            // warp per problem -- the iteration is bound by L2 round trips either way,
         if (tv == 2 && sizeof(T) == 8 && ns_max == 0 && !ps && nv == 2) team = 2; // and the fork-join adds barriers to each)
     }
-    // n <= 63, plain fp64 path: the register-staged warp kernel (no staging arena in shared memory: 16 problems per SM at
-    // n = 50 instead of 12). DAQP_B200_REGSTAGE=0 selects the cp.async-staged kernel (the round-1 headline kernel).
-    bool regstage = sizeof(T) == 8 && ns_max == 0 && !ps && team == 0 && nv <= 2;
-    if (const char* renv = getenv("DAQP_B200_REGSTAGE")) regstage = regstage && atoi(renv) != 0;
+    // experiment knob DAQP_B200_REGSTAGE=1 (n <= 63, plain fp64 path): the register-staged warp kernel -- no staging arena in
+    // shared memory, 16 problems per SM at n = 50 instead of 12. Measured on C3: 104.9 ms against 104.65 ms for the
+    // cp.async-staged kernel with 12 -- a third more resident warps buys nothing, so it stays opt-in.
+    bool regstage = false;
+    if (const char* renv = getenv("DAQP_B200_REGSTAGE")) regstage = atoi(renv) != 0 && sizeof(T) == 8 && ns_max == 0 && !ps && team == 0 && nv <= 2;
     const size_t smem_solve_w = ldp_layout<T>(la, regstage ? -1 : team), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
     int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
