@@ -961,6 +961,36 @@ extern "C" int daqp_b200_init_active(DAQPB200Handle* h, int N, int n, int m, int
     return 0;
 }
 
+// ---- daqp_first_violating, batched (reference src/api.c:562-574): N points against one polyhedron ------------------------
+extern "C" int daqp_b200_first_violating_batch(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* x, const c_float* A,
+                                               const c_float* bupper, const c_float* blower, c_float tol, int* first) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (N <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid polyhedron dimensions"; return -2; }
+    const size_t mA = (size_t)(m - ms), nx = (size_t)N * n, nA = mA * n;
+    int rc = ensure(&h->stage, &h->stage_bytes, (nx + nA + 2 * (size_t)m) * sizeof(c_float) + (size_t)N * sizeof(int) + 8 * 256);
+    if (rc) return rc;
+    Carver cv(h->stage);
+    c_float* dx = cv.take<c_float>(nx); c_float* dA = cv.take<c_float>(nA);
+    c_float* dbu = cv.take<c_float>(m); c_float* dbl = cv.take<c_float>(m); int* dout = cv.take<int>(N);
+    cudaStream_t s = h->compute;
+    CK(cudaMemcpyAsync(dx, x, nx * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    if (nA) CK(cudaMemcpyAsync(dA, A, nA * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    if (m) {
+        CK(cudaMemcpyAsync(dbu, bupper, (size_t)m * sizeof(c_float), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dbl, blower, (size_t)m * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    }
+    const int warps = 8;
+    first_violating_kernel<<<std::min(h->num_sms * 8, (N + warps - 1) / warps), 32 * warps, (size_t)warps * n * sizeof(c_float), s>>>(
+        N, n, m, ms, dx, dA, dbu, dbl, tol, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(first, dout, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 // Drop-ins (reference include/api.h:57-58): one problem, qp->sense updated in place. Like the reference they return
 // nothing; without a CUDA device qp->sense is left untouched and daqp_b200_last_error() says why.
 extern "C" void daqp_primal_init_active(DAQPProblem* qp, c_float* x) {

@@ -236,16 +236,11 @@ extern "C" void daqp_set_primal_start(DAQPWorkspace* work, c_float* x) { // src/
     if (work->x && x) for (int i = 0; i < work->n; i++) work->x[i] = x[i];
 }
 
-// src/api.c:562-574. One problem, O(mn) on the host like the reference: the batched form of this scan is the primal
-// pass of daqp_b200_init_active (warmstart_kernel.cuh).
+// src/api.c:562-574: a batch of one through the batched kernel (daqp_b200_first_violating_batch, warmstart_kernel.cuh).
+// Like the reference it has no error channel: on a CUDA-side failure it returns m ("nothing violated") and
+// daqp_b200_last_error() says why.
 extern "C" int daqp_first_violating(c_float* x, c_float* A, c_float* bu, c_float* bl, int n, int m, int ms, c_float tol) {
-    int i = 0;
-    for (; i < ms; i++)
-        if (x[i] > bu[i] + tol || x[i] < bl[i] - tol) return i;
-    for (int disp = 0; i < m; i++) {
-        c_float Ax = 0;
-        for (int j = 0; j < n; j++) Ax += A[disp++] * x[j];
-        if (Ax > bu[i] + tol || Ax < bl[i] - tol) return i;
-    }
-    return m;
+    int first = m;
+    if (daqp_b200_first_violating_batch(nullptr, 1, n, m, ms, x, A, bu, bl, tol, &first) != 0) return m;
+    return first;
 }

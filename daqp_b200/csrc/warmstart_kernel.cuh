@@ -125,4 +125,34 @@ __global__ void __launch_bounds__(32 * IA_WARPS) init_active_kernel(const InitAc
     }
 }
 
+// ---- daqp_first_violating for a batch of points (reference src/api.c:562-574): index of the first constraint of
+// {bl <= [I(ms); A] x <= bu} that x violates by more than tol, or m. One warp per point; lane r walks rows r, r + 32, ...
+// left to right with separate multiply and add (the reference's loop order, bit for bit), keeps the smallest violated
+// index it meets, and the warp takes the minimum.
+__global__ void __launch_bounds__(256) first_violating_kernel(int N, int n, int m, int ms, const double* x, const double* A,
+                                                               const double* bu, const double* bl, double tol, int* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* xs = reinterpret_cast<double*>(smem_raw) + (size_t)wib * n;
+    for (int p = blockIdx.x * wpb + wib; p < N; p += gridDim.x * wpb) {
+        const double* xp = x + (size_t)p * n;
+        for (int j = lane; j < n; j += 32) xs[j] = xp[j];
+        __syncwarp();
+        int first = m;
+        for (int i = lane; i < m && first == m; i += 32) {
+            double v;
+            if (i < ms) v = xs[i];
+            else {
+                const double* row = A + (size_t)(i - ms) * n;
+                v = 0;
+                for (int j = 0; j < n; j++) v = __dadd_rn(v, __dmul_rn(__ldg(row + j), xs[j]));
+            }
+            if (v > bu[i] + tol || v < bl[i] - tol) first = i;
+        }
+        first = __reduce_min_sync(FULL, first);
+        if (lane == 0) out[p] = first;
+        __syncwarp();
+    }
+}
+
 } // namespace dq

@@ -325,6 +325,11 @@ int daqp_b200_init_active_device(DAQPB200Handle* h, int N, int n, int m, int ms,
                                  const c_float* dA, const c_float* dbupper, const c_float* dblower, int* dsense,
                                  void* stream);
 
+/* NEW: daqp_first_violating (reference include/api.h:55) for N points x[N][n] against one polyhedron: first[p] = index of
+ * the first constraint point p violates by more than tol, or m. HOST arrays, blocking. */
+int daqp_b200_first_violating_batch(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* x, const c_float* A,
+                                    const c_float* bupper, const c_float* blower, c_float tol, int* first);
+
 /* ---- minimal representation of polyhedra (batched LDP consumer) ---------------------------------------------
  * reference include/api.h:54 (src/api.c:531-556, src/utils.c:808-835): is_redundant[i] = 1 iff constraint i of
  * {x : [I(ms); A] x <= b} is redundant (the LDP with row i turned into an active equality is infeasible), else 0.

@@ -130,3 +130,36 @@ def test_init_active_at_scale(engine):
     ax = np.einsum("bmn,bn->bm", b.A, r.x)
     near = np.minimum(np.abs(ax - b.bupper), np.abs(ax - b.blower))
     assert ((sx & 1) != 0)[near < 5e-10].all() and not ((sx & 1) != 0)[near > 2e-9].any()
+
+
+@pytest.mark.gpu
+def test_first_violating_matches_reference_rule(cuda_lib):
+    """daqp_first_violating (reference src/api.c:562-574) through the drop-in symbol and the batched entry: the first
+    index with x_i or A_i x outside [bl - tol, bu + tol], simple bounds first, else m -- checked against the same loop in
+    numpy (same left-to-right accumulation)."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    n, m, ms, N = 7, 40, 3, 257
+    A = rng.standard_normal((m - ms, n)); bu = rng.random(m) + 0.5; bl = -bu
+    X = rng.standard_normal((N, n)) * np.linspace(0.01, 1.0, N)[:, None]
+    want = np.full(N, m, np.intc)
+    for p in range(N):
+        for i in range(m):
+            if i < ms: v = X[p, i]
+            else:
+                v = 0.0
+                for j in range(n): v += A[i - ms, j] * X[p, j]
+            if v > bu[i] + 1e-9 or v < bl[i] - 1e-9:
+                want[p] = i
+                break
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    got = np.zeros(N, np.intc)
+    cuda_lib.daqp_b200_first_violating_batch.restype = C.c_int
+    assert cuda_lib.daqp_b200_first_violating_batch(None, N, n, m, ms, dp(X), dp(A), dp(bu), dp(bl), C.c_double(1e-9),
+                                                    got.ctypes.data_as(C.POINTER(C.c_int))) == 0
+    np.testing.assert_array_equal(got, want)
+    assert (want < m).any() and (want == m).any()
+    cuda_lib.daqp_first_violating.restype = C.c_int
+    for p in (0, 100, 256):
+        x = np.ascontiguousarray(X[p])
+        assert cuda_lib.daqp_first_violating(dp(x), dp(A), dp(bu), dp(bl), n, m, ms, C.c_double(1e-9)) == want[p]
