@@ -612,6 +612,18 @@ def main():
             e2e_step()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # the host link alone: every rank copies its pinned H block to the device at the same time, nothing else running --
+        # what the box's host-to-device fabric gives N concurrent ranks (the e2e step cannot beat it)
+        dst = torch.empty_like(t["H"])
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(2):
+            dst.copy_(h["H"], non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_gbs = 2 * h["H"].numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dst
         h2d = sum(v.numel() * v.element_size() for v in h.values())
         d2h = res.x.nbytes + res.lam.nbytes + res.fval.nbytes + res.exitflag.nbytes + res.iter.nbytes
         h2d_all = sum(gather_floats(float(h2d)))
@@ -619,6 +631,7 @@ def main():
         e2e = {"value": args.problems * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                "steps": ksteps, "api": "daqp_b200_solve_packed (host C ABI, pinned buffers, chunked copy/solve overlap)",
                "h2d_gbs_per_rank": [round(g, 2) for g in gather_floats(h2d * ksteps / solve_secs[0] / 1e9)],
+               "h2d_copy_only_gbs_per_rank": [round(g, 2) for g in gather_floats(copy_gbs)],
                "numa": numa}
         # ---- persistent workspace: setup once, then update(f, b) + warm solve per "MPC step".
         # Reported next to the headline, not part of it: an extra object in the same line.
