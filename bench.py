@@ -517,6 +517,7 @@ def main():
     e1.record()
     barrier()
     ms_rank = e0.elapsed_time(e1)
+    st = eng.stats(reset=True)  # kernel times and launch counts of the TIMED steps only
     # the timed region can be shorter than nvidia-smi's first sample (16 ms per step at 8 GPUs): keep the same load running,
     # untimed, until the sampler has seen it
     t_probe = time.perf_counter()
@@ -526,7 +527,7 @@ def main():
     clocks = sampler.stop()
     clocks["note"] = "sampled every 100 ms over the timed steps and the identical untimed steps that follow them"
     barrier()
-    st = eng.stats(reset=True)
+    eng.stats(reset=True)
     ms_total = max_over_ranks(ms_rank)
     value = args.problems * args.steps / (ms_total * 1e-3)
     per_rank_ms = gather_floats(ms_rank / args.steps)
