@@ -1467,11 +1467,10 @@ struct Warp {
 
 // One warp per problem, persistent CTAs pulling problem indices from an atomic queue (iteration counts diverge).
 //
-// Phase alignment: all warps of the CTA meet at ONE block barrier per active-set iteration and then run the same
-// sequence (direction solve -> ratio test -> remove | primal -> scan -> add). Without it sixteen warps sit in sixteen
-// different routines and the SM's instruction cache thrashes (measured: 24 % of all stall samples were
-// "no instruction", icc hit rate 75 %); with it the instruction working set at any moment is one routine. The
-// barrier carries no data -- problems stay independent -- it only keeps the instruction streams together.
+// The warps of a CTA never synchronise with each other (TW <= 1): every warp owns its problem for the whole solve and
+// sits in its own phase of the iteration, which is why the hot instruction footprint, not the kernel's size, decides the
+// instruction-cache hit rate (see the header). (An earlier version lined the warps up at one block barrier per iteration
+// to share instruction-cache lines; keeping the hot code small did better.)
 //
 // TW > 1 (team mode, n > 64): one CTA of TW warps per problem -- at n = 120 the packed factor is 58 KB, so only three
 // problems fit an SM and a warp each would leave the SM at three warps. Warp 0 runs the loop below, warps 1.. serve it.
