@@ -1285,6 +1285,178 @@ extern "C" int daqp_b200_workspace_solve_device(DAQPB200Workspace* w, int warm, 
     return 0;
 }
 
+// ---- branch and bound over binary constraints: the node relaxations as a batched LDP consumer --------------------------
+// reference src/bnb.c:23-128 (daqp_bnb, daqp_process_node, daqp_get_branch_id, daqp_spawn_children). The reference walks
+// the tree depth first, one relaxation (= one daqp_ldp on the same workspace) at a time. Here the TREE stays on the host
+// and every WAVE of open nodes is one launch of the solve kernel in shared-matrix mode: the QP -> LDP transform runs once
+// for the problem, all nodes read the same device copy of the matrices, a node is nothing but its own sense bytes -- the
+// binaries fixed on the way down as ACTIVE + IMMUTABLE (+ LOWER) rows, the parent's final working set as warm-start bits.
+// Pruning is the reference's: the incumbent's objective goes into settings.fval_bound, a node whose objective passes it
+// ends INFEASIBLE inside the kernel (daqp.c:19-23). The branching rule (first free binary in index order that is not
+// within primal_tol of an endpoint, nearer endpoint first) is bnb.c:130-158 evaluated on x. What differs from the
+// reference is the ORDER in which nodes are visited (waves of the deepest open nodes instead of strict depth first), so
+// `nodes` and `iter` count a different walk to the same optimum.
+__global__ void bnb_wave_kernel(int N, int ldm, const unsigned char* base, const unsigned char* node, const int* used,
+                                unsigned char* sense, int* sflag) {
+    const int p = blockIdx.x;
+    if (p >= N) return;
+    for (int r = threadIdx.x; r < ldm; r += blockDim.x)
+        sense[(size_t)p * ldm + r] = base[(size_t)p * ldm + r] | node[(size_t)p * ldm + r];
+    if (threadIdx.x == 0) sflag[p] = used[p] ? SETUP_SOLVE_ACTIVATE : EXIT_INFEASIBLE; // unused slots are passed through
+}
+
+extern "C" int daqp_b200_bnb(DAQPB200Handle* h, const DAQPProblem* qp, const DAQPSettings* settings_in, DAQPResult* res,
+                             int wave_width) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    if (!qp || !res || qp->H == nullptr || qp->nh > 1 || qp->problem_type != 0 || qp->n < 1 || qp->m < qp->ms || qp->ms > qp->n ||
+        !qp->sense || (qp->m > qp->ms && qp->A == nullptr) || qp->bupper == nullptr || qp->blower == nullptr) {
+        g_last_error = "daqp_b200: invalid problem for branch and bound"; return -2;
+    }
+    const int n = qp->n, m = qp->m, ms = qp->ms, ldm = round_up(std::max(m, 1), 4);
+    const int W = std::max(1, wave_width > 0 ? wave_width : 256);
+    DAQPSettings st;
+    if (settings_in) st = *settings_in; else daqp_default_settings(&st);
+    std::vector<int> bin_ids, sense_base((size_t)m);
+    for (int i = 0; i < m; i++) {
+        if (qp->sense[i] & DAQP_BINARY) bin_ids.push_back(i);
+        sense_base[i] = qp->sense[i] & ~DAQP_BINARY; // the relaxation sees a binary as a two-sided inequality
+    }
+    res->nodes = 0; res->iter = 0; res->soft_slack = 0; res->setup_time = 0; res->solve_time = 0;
+    if ((int)bin_ids.size() > n) { res->exitflag = DAQP_EXIT_OVERDETERMINED_INITIAL; return 0; } // api.c:226
+    // ---- one transform, W node slots
+    DAQPB200Workspace* w = nullptr;
+    int rc = workspace_setup_impl(h, 1, W, n, m, ms, qp->H, nullptr, qp->A, nullptr, nullptr, sense_base.data(), &st, &w);
+    if (rc) return rc;
+    struct Guard { DAQPB200Workspace* w; ~Guard() { daqp_b200_workspace_free(w); } } guard{w};
+    {
+        std::vector<c_float> fK((size_t)W * n, 0), buK((size_t)W * m), blK((size_t)W * m);
+        for (int k = 0; k < W; k++) {
+            if (qp->f) memcpy(&fK[(size_t)k * n], qp->f, sizeof(c_float) * n);
+            memcpy(&buK[(size_t)k * m], qp->bupper, sizeof(c_float) * m);
+            memcpy(&blK[(size_t)k * m], qp->blower, sizeof(c_float) * m);
+        }
+        rc = daqp_b200_workspace_update(w, fK.data(), buK.data(), blK.data());
+        if (rc) return rc;
+    }
+    std::vector<int> flag0((size_t)W);
+    rc = daqp_b200_workspace_flags(w, flag0.data());
+    if (rc) return rc;
+    if (flag0[0] < 0) { res->exitflag = flag0[0]; return 0; } // the transform failed (non-convex, infeasible bounds, ...)
+    // sense bytes after the update (bound-derived equalities included), |v|^2 for the objective bound, device scratch
+    unsigned char *d_base = nullptr, *d_node = nullptr;
+    int* d_used = nullptr;
+    c_float vnorm = 0;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        CK(cudaSetDevice(h->device));
+        CK(cudaMalloc((void**)&d_base, (size_t)W * ldm)); w->owned.push_back(d_base);
+        CK(cudaMalloc((void**)&d_node, (size_t)W * ldm)); w->owned.push_back(d_node);
+        CK(cudaMalloc((void**)&d_used, (size_t)W * sizeof(int))); w->owned.push_back(d_used);
+        CK(cudaMemcpyAsync(d_base, w->ps.sense8, (size_t)W * ldm, cudaMemcpyDeviceToDevice, h->compute));
+        std::vector<c_float> v((size_t)n);
+        CK(cudaMemcpyAsync(v.data(), w->ps.vv, sizeof(c_float) * n, cudaMemcpyDeviceToHost, h->compute));
+        CK(cudaStreamSynchronize(h->compute));
+        if (qp->f) for (int i = 0; i < n; i++) vnorm += v[i] * v[i];
+    }
+    struct Node { std::vector<int> fixed; std::vector<unsigned char> warm; }; // fixed: id or id | (1 << 16) for "at lower"
+    std::vector<Node> open(1);
+    const c_float eps_r = 1 / (1 + st.rel_subopt);
+    c_float bound = (st.fval_bound - st.abs_subopt) * eps_r; // bnb.c:29-31
+    bool have_inc = false;
+    c_float best_internal = 0, best_slack = 0;
+    std::vector<c_float> best_x((size_t)n), best_lam((size_t)std::max(m, 1));
+    std::vector<c_float> x((size_t)W * n), lam((size_t)W * std::max(m, 1)), fval((size_t)W), slack((size_t)W);
+    std::vector<int> flag((size_t)W), iter((size_t)W), used((size_t)W), nact((size_t)W);
+    std::vector<unsigned char> node8((size_t)W * ldm), so((size_t)W * ldm);
+    int last_fail = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (!open.empty()) {
+        const int cnt = (int)std::min<size_t>(W, open.size());
+        std::vector<Node> wave(std::make_move_iterator(open.end() - cnt), std::make_move_iterator(open.end())); // the deepest nodes
+        open.resize(open.size() - cnt);
+        std::fill(node8.begin(), node8.end(), 0);
+        for (int k = 0; k < W; k++) used[k] = k < cnt;
+        for (int k = 0; k < cnt; k++) {
+            unsigned char* s8 = &node8[(size_t)k * ldm];
+            if (!wave[k].warm.empty()) memcpy(s8, wave[k].warm.data(), (size_t)m);
+            for (int fx : wave[k].fixed) {
+                const int id = fx & 0xffff;
+                s8[id] = (unsigned char)((sense_base[id] & ~(DAQP_ACTIVE | DAQP_LOWER)) | DAQP_ACTIVE | DAQP_IMMUTABLE | ((fx >> 16) ? DAQP_LOWER : 0));
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(h->mu);
+            CK(cudaSetDevice(h->device));
+            CK(cudaMemcpyAsync(d_node, node8.data(), (size_t)W * ldm, cudaMemcpyHostToDevice, h->compute));
+            CK(cudaMemcpyAsync(d_used, used.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, h->compute));
+            bnb_wave_kernel<<<W, 64, 0, h->compute>>>(W, ldm, d_base, d_node, d_used, w->ps.sense8, w->ps.sflag);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(h->compute)); // (node8 / used are reused by the next wave)
+            w->settings.fval_bound = bound;
+        }
+        DAQPB200Diag dg{};
+        dg.n_active = nact.data(); dg.sense = so.data(); dg.soft_slack = slack.data();
+        rc = daqp_b200_workspace_solve(w, 0, x.data(), lam.data(), fval.data(), flag.data(), iter.data(), &dg);
+        if (rc) return rc;
+        for (int k = 0; k < cnt; k++) {
+            res->nodes++;
+            res->iter += iter[k];
+            const int fl = flag[k];
+            if (fl == DAQP_EXIT_OVERDETERMINED_INITIAL && !wave[k].warm.empty()) {
+                // a fixed binary clashed with the warm-start rows, which are only a guess: once more from the fixings alone
+                Node cold; cold.fixed = wave[k].fixed;
+                open.push_back(std::move(cold));
+                continue;
+            }
+            if (fl == DAQP_EXIT_INFEASIBLE || fl == DAQP_EXIT_OVERDETERMINED_INITIAL) continue; // cut (dominated, or the fixings clash)
+            if (fl < 0) { last_fail = fl; open.clear(); break; }                                   // inner solver failed (bnb.c:63)
+            const c_float* xk = &x[(size_t)k * n];
+            const unsigned char* sk = &so[(size_t)k * ldm];
+            const c_float internal = 2 * fval[k] + vnorm; // work->fval of this node (api.c:471-477 inverted)
+            if (have_inc && !(internal <= 2 * bound)) continue; // the bound moved while the wave was in flight
+            // daqp_get_branch_id (bnb.c:130-158) on x: first free binary that is not within primal_tol of an endpoint
+            int branch = -1;
+            for (int id : bin_ids) {
+                if (sk[id] & DAQP_ACTIVE) continue;
+                c_float val = 0;
+                if (id < ms) val = xk[id];
+                else { const c_float* row = qp->A + (size_t)(id - ms) * n; for (int j = 0; j < n; j++) val += row[j] * xk[j]; }
+                const c_float diff = 0.5 * (qp->bupper[id] + qp->blower[id]) - val;
+                const c_float dist = 0.5 * (qp->bupper[id] - qp->blower[id]) - (diff < 0 ? -diff : diff);
+                if (dist <= st.primal_tol) continue;
+                branch = diff < 0 ? id : (id | (1 << 16)); // explore the endpoint nearest to the relaxation first
+                break;
+            }
+            if (branch < 0) { // integer feasible: new incumbent (bnb.c:66-69)
+                if (!have_inc || internal < best_internal) {
+                    have_inc = true; best_internal = internal; best_slack = slack[k];
+                    memcpy(best_x.data(), xk, sizeof(c_float) * n);
+                    if (m > 0) memcpy(best_lam.data(), &lam[(size_t)k * m], sizeof(c_float) * m);
+                    bound = (0.5 * internal - st.abs_subopt) * eps_r;
+                }
+                continue;
+            }
+            Node far, near; // bnb.c:160-176: the far endpoint is pushed first, the near one is processed first
+            far.fixed = wave[k].fixed; far.fixed.push_back(branch ^ (1 << 16));
+            near.fixed = wave[k].fixed; near.fixed.push_back(branch);
+            far.warm.assign((size_t)m, 0);
+            for (int i = 0; i < m; i++) // the parent's working set as warm-start bits (daqp_save_warmstart, bnb.c:209-221)
+                if ((sk[i] & DAQP_ACTIVE) && !(sk[i] & DAQP_IMMUTABLE)) far.warm[i] = (unsigned char)((sense_base[i] & ~DAQP_LOWER) | DAQP_ACTIVE | (sk[i] & DAQP_LOWER));
+            near.warm = far.warm;
+            open.push_back(std::move(far));
+            open.push_back(std::move(near));
+        }
+    }
+    res->solve_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!have_inc) { res->exitflag = last_fail < 0 ? last_fail : DAQP_EXIT_INFEASIBLE; return 0; }
+    memcpy(res->x, best_x.data(), sizeof(c_float) * n);
+    if (res->lam && m > 0) memcpy(res->lam, best_lam.data(), sizeof(c_float) * m);
+    if (qp->f) res->fval = 0.5 * (best_internal - vnorm);
+    res->soft_slack = best_slack;
+    res->exitflag = last_fail < DAQP_EXIT_INFEASIBLE ? last_fail : DAQP_EXIT_OPTIMAL; // bnb.c:84
+    return 0;
+}
+
 // ---- one process, several GPUs: the batch is cut into contiguous blocks, one host thread + engine per device ---------
 extern "C" int daqp_b200_solve_packed_multi(int ndev, const int* devices, int N, int n, int m, int ms, const c_float* H,
                                             const c_float* f, const c_float* A, const c_float* bupper, const c_float* blower,
@@ -1453,6 +1625,15 @@ int quadprog_batch_impl(int N, typename Aos<T>::Problem* qps, typename Aos<T>::R
         const bool bad = q.H == nullptr || q.nh > 1 || q.problem_type != 0 || q.n < 1 || q.m < q.ms || q.ms > q.n ||
                          (q.m > q.ms && q.A == nullptr) || (q.m > 0 && (q.bupper == nullptr || q.blower == nullptr));
         if (bad) { res[i].exitflag = DAQP_EXIT_UNSUPPORTED; res[i].iter = 0; continue; }
+        if constexpr (sizeof(T) == sizeof(c_float)) { // binary constraints: the tree search, its node relaxations batched
+            bool binary = false;
+            if (q.sense) for (int r = 0; r < q.m && !binary; r++) binary = (q.sense[r] & DAQP_BINARY) != 0;
+            if (binary) {
+                int rcb = daqp_b200_bnb(nullptr, &q, settings, &res[i], 0);
+                if (rcb) return rcb;
+                continue;
+            }
+        }
         groups[std::make_tuple(q.n, q.m, q.ms, q.f != nullptr, q.sense != nullptr)].push_back(i);
     }
     if (groups.empty()) return 0;

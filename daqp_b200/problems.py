@@ -123,6 +123,32 @@ def generate_g1(N: int, n: int, m: int, ms: int, n_active: int, kappa: float = 1
                    sgn.astype(np.int8))
 
 
+def generate_miqp(N: int, n: int, m: int, ms: int, nb: int, seed: int = SEED_BASE + 200) -> QPBatch:
+    """Batched port of the reference's ``generate_test_MIQP(n, m, ms, nb)`` (interfaces/daqp-julia/test/utils.jl:145-166):
+    H = M'M + I, the first nb simple bounds are binary constraints on [0, 1] (sense 16) with a linear term that makes it
+    lucrative to leave the origin, and the first general row is the cardinality constraint sum(x[:nb]) <= floor(nb / 2),
+    so the relaxation is fractional and branch and bound has to search."""
+    assert ms >= nb and m - ms >= 1
+    rng = _rng(seed)
+    M = rng.standard_normal((N, n, n))
+    H = np.swapaxes(M, 1, 2) @ M + np.eye(n)
+    A = rng.standard_normal((N, m - ms, n))
+    bupper = 20 * rng.random((N, m))
+    blower = -20 * rng.random((N, m))
+    f = 100 * rng.standard_normal((N, n))
+    f[:, :nb] = -np.abs(f[:, :nb])
+    bupper[:, :nb] = 1.0
+    blower[:, :nb] = 0.0
+    sense = np.zeros((N, m), np.int32)
+    sense[:, :nb] = 16
+    A[:, 0, :] = 0.0
+    A[:, 0, :nb] = 1.0
+    bupper[:, ms] = np.floor(nb / 2)
+    blower[:, ms] = -1e30
+    c = np.ascontiguousarray
+    return QPBatch(n, m, ms, c(H), c(f), c(A), c(bupper), c(blower), sense)
+
+
 def generate_g0(N: int, n: int, m: int, seed: int = SEED_BASE + 100) -> QPBatch:
     """Probe distribution of BASELINE.md §2: H = G'G/n + I, f ~ 3 N(0,1), A ~ N(0,1), b = A x0 +- (0.1 + U)."""
     rng = _rng(seed)

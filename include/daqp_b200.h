@@ -330,6 +330,16 @@ int daqp_b200_init_active_device(DAQPB200Handle* h, int N, int n, int m, int ms,
 int daqp_b200_first_violating_batch(DAQPB200Handle* h, int N, int n, int m, int ms, const c_float* x, const c_float* A,
                                     const c_float* bupper, const c_float* blower, c_float tol, int* first);
 
+/* ---- binary constraints: branch and bound with batched node relaxations (batched LDP consumer) -------------------------
+ * reference src/bnb.c:23-128 (what daqp_quadprog runs when a constraint carries DAQP_BINARY: it must hold with equality
+ * at its lower or at its upper bound). The tree search stays on the host; every wave of open nodes (at most wave_width,
+ * 0 = 256) is ONE launch of the solve kernel in shared-matrix mode -- the QP -> LDP transform runs once, a node is its
+ * sense bytes (fixed binaries ACTIVE + IMMUTABLE, the parent's working set as warm start), the incumbent prunes through
+ * settings.fval_bound exactly as in the reference. Same optimum, exit flag and fval as the reference; res->nodes and
+ * res->iter count this walk (waves of the deepest open nodes, not strict depth first); res->lam holds the incumbent's
+ * multipliers. daqp_quadprog / daqp_quadprog_batch route problems with binary constraints here. */
+int daqp_b200_bnb(DAQPB200Handle* h, const DAQPProblem* qp, const DAQPSettings* settings, DAQPResult* res, int wave_width);
+
 /* ---- minimal representation of polyhedra (batched LDP consumer) ---------------------------------------------
  * reference include/api.h:54 (src/api.c:531-556, src/utils.c:808-835): is_redundant[i] = 1 iff constraint i of
  * {x : [I(ms); A] x <= b} is redundant (the LDP with row i turned into an active equality is infeasible), else 0.

@@ -6,7 +6,7 @@ final working sets and per-problem operation counts must be EQUAL.
 import numpy as np
 import pytest
 
-from common import (RARE_MUST_HIT, assert_parity, golden_names, kkt_residuals, load_golden, rare_golden_names,
+from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, load_golden, rare_golden_names,
                     rare_settings, ws_sets)
 from daqp_b200.problems import generate_config, generate_g0, generate_g1, soften
 
@@ -551,6 +551,56 @@ def test_full_size_properties(engine):
     perm = np.random.default_rng(0).permutation(b.N)[:4000]
     sub = engine.solve_batch(b.H[perm], b.f[perm], b.A[perm], b.bupper[perm], b.blower[perm], None, ms=b.ms)
     np.testing.assert_array_equal(sub.x, r.x[perm])
+
+
+@pytest.mark.parametrize("name", bnb_golden_names())
+def test_bnb_batched_node_relaxations_match_reference(cuda_lib, name):
+    """Binary constraints (sense & 16): branch and bound with the node relaxations solved as batches on the GPU
+    (daqp_b200_bnb behind daqp_quadprog, reference src/bnb.c:23-128) against the reference's own output on the port of its
+    MIQP generator and on the literals of its tests: same exit flag, same optimum (x to 1e-6, fval to 1e-7 relative),
+    every binary on one of its bounds. The walk differs from the reference's depth-first one, so iteration and node
+    counts are not compared -- except where the reference's tests pin them (zero-dual endpoints: one node)."""
+    import daqp_b200
+    b, d = load_golden(name)
+    for p in range(b.N):
+        x, fval, flag, info = daqp_b200.solve(b.H[p], b.f[p], b.A[p] if b.m > b.ms else np.zeros((0, b.n)), b.bupper[p],
+                                              b.blower[p], b.sense[p])
+        assert flag == d["exitflag"][p] == 1, f"{name}[{p}]: exit flag {flag}"
+        np.testing.assert_allclose(x, d["x"][p], atol=1e-6 * (1 + np.abs(d["x"][p]).max()), err_msg=f"{name}[{p}]")
+        assert abs(fval - d["fval"][p]) <= 1e-7 * (1 + abs(d["fval"][p])), f"{name}[{p}]: fval {fval} vs {d['fval'][p]}"
+        for i in np.nonzero(b.sense[p] & 16)[0]:
+            val = x[i] if i < b.ms else b.A[p, i - b.ms] @ x
+            assert min(abs(val - b.bupper[p, i]), abs(val - b.blower[p, i])) < 1e-5
+        assert info["nodes"] >= 1 and info["iterations"] >= 1
+        if name.startswith("bnb_lit_zero_dual"):
+            assert info["nodes"] == 1  # core_tests.jl:160-178
+
+
+def test_bnb_narrow_waves_and_infeasible(cuda_lib):
+    """The same optimum whatever the wave width (1 = one relaxation per launch, the reference's own granularity), and an
+    MIQP whose binaries cannot satisfy an equality ends INFEASIBLE (-1)."""
+    import ctypes as C
+    import daqp_b200 as d
+    from daqp_b200.problems import generate_miqp
+    L = d.lib()
+    L.daqp_b200_bnb.restype = C.c_int
+    b = generate_miqp(3, 10, 20, 8, 6, seed=711)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for p in range(b.N):
+        xs = []
+        for wave in (1, 4, 256):
+            x = np.empty(b.n); lam = np.empty(b.m)
+            se = np.ascontiguousarray(b.sense[p], np.intc)
+            qp = d.DAQPProblem(b.n, b.m, b.ms, dp(b.H[p]), dp(b.f[p]), dp(b.A[p]), dp(b.bupper[p]), dp(b.blower[p]),
+                               se.ctypes.data_as(C.POINTER(C.c_int)), None, 0, 0)
+            res = d.DAQPResult(dp(x), dp(lam), 0, 0, 0, 0, 0, 0, 0)
+            assert L.daqp_b200_bnb(None, C.byref(qp), None, C.byref(res), wave) == 0 and res.exitflag == 1
+            xs.append(x.copy())
+        np.testing.assert_allclose(xs[0], xs[1], atol=1e-9); np.testing.assert_allclose(xs[0], xs[2], atol=1e-9)
+    # x1, x2 binary in {0, 1} and x1 + x2 = 0.5 exactly: no integer point
+    H = np.eye(2); f = np.zeros(2); A = np.ones((1, 2))
+    x, fval, flag, info = d.solve(H, f, A, np.array([1.0, 1.0, 0.5]), np.array([0.0, 0.0, 0.5]), np.array([16, 16, 5], np.intc))
+    assert flag == -1
 
 
 def test_solve_packed_multi_matches_single(engine, oracle):

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from common import (RARE_MUST_HIT, assert_parity, golden_names, kkt_residuals, load_golden, rare_golden_names,
+from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, load_golden, rare_golden_names,
                     rare_settings, ws_sets)
 from daqp_b200.problems import generate_g0, generate_g1
 
@@ -183,3 +183,24 @@ def test_fp32_oracle_vs_live_fp32_reference(oracle_libs):
         np.testing.assert_array_equal(r.exitflag, o.exitflag)
         assert (r.iter == o.iter).mean() >= 0.9  # near-ties resolve differently under fast-math in fp32: a rate, not bit parity
         assert np.abs(r.x - o.x).max() <= 1e-4 * (1 + np.abs(r.x).max())
+
+
+@pytest.mark.parametrize("name", bnb_golden_names())
+def test_bnb_fixtures_are_what_the_reference_gives(oracle_libs, name):
+    """Branch-and-bound fixtures (reference src/bnb.c through daqp_quadprog): every binary constraint sits on one of its
+    bounds at the recorded optimum, the literals of core_tests.jl:150-178 have their known answers, and -- where the
+    reference is compiled here -- the live reference reproduces the file."""
+    b, d = load_golden(name)
+    assert (d["exitflag"] == 1).all()
+    for p in range(b.N):
+        for i in np.nonzero(b.sense[p] & 16)[0]:
+            val = d["x"][p, i] if i < b.ms else b.A[p, i - b.ms] @ d["x"][p]
+            assert min(abs(val - b.bupper[p, i]), abs(val - b.blower[p, i])) < 1e-5
+    if name == "bnb_lit_x011":
+        np.testing.assert_allclose(d["x"][0], [0, 1, 1], atol=1e-6)
+    if name.startswith("bnb_lit_zero_dual"):
+        np.testing.assert_allclose(d["x"][0], 0, atol=1e-9)
+    if oracle_libs.have_ref():
+        r = oracle_libs.RefLib("libdaqp_ref.so").solve(b, use_sense=True)
+        np.testing.assert_array_equal(r.exitflag, d["exitflag"])
+        np.testing.assert_allclose(r.x, d["x"], atol=1e-12)
