@@ -59,7 +59,8 @@ class DAQPResultF32(C.Structure):  # include/api.h:15-27 with c_float = float
 
 
 class DAQPB200Diag(C.Structure):
-    _fields_ = [("n_active", _ip), ("ws", _ip), ("counts", _ip), ("sense", C.POINTER(C.c_ubyte)), ("soft_slack", _dp)]
+    _fields_ = [("n_active", _ip), ("ws", _ip), ("counts", _ip), ("sense", C.POINTER(C.c_ubyte)), ("soft_slack", _dp),
+                ("trace", _ip), ("trace_cap", C.c_int)]
 
 
 class DAQPB200Stats(C.Structure):
@@ -280,7 +281,9 @@ class Engine:
             d = DAQPB200Diag(C.cast(diag["n_active"].data_ptr(), _ip), C.cast(diag["ws"].data_ptr(), _ip),
                              C.cast(diag["counts"].data_ptr(), _ip),
                              C.cast(diag["sense"].data_ptr(), C.POINTER(C.c_ubyte)),
-                             C.cast(diag["soft_slack"].data_ptr(), _dp) if "soft_slack" in diag else None)
+                             C.cast(diag["soft_slack"].data_ptr(), _dp) if "soft_slack" in diag else None,
+                             C.cast(diag["trace"].data_ptr(), _ip) if "trace" in diag else None,
+                             int((diag["trace"].shape[1] - 1) // 2) if "trace" in diag else 0)
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         if stream == 0:

@@ -428,6 +428,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
         la.nact_out = (diag && diag->n_active) ? diag->n_active + p0 : nullptr;
         la.counts_out = (diag && diag->counts) ? diag->counts + 8 * (size_t)p0 : nullptr;
         la.sense_out = (diag && diag->sense) ? diag->sense + (size_t)p0 * ldm : nullptr;
+        la.trace_cap = (diag && diag->trace) ? diag->trace_cap : 0;
+        la.trace_out = (diag && diag->trace && diag->trace_cap > 0) ? diag->trace + (size_t)p0 * (1 + 2 * diag->trace_cap) : nullptr;
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
         la.soft_slack = sa.soft_slack; la.ns_max = ns_max;
         la.tune = tune;

@@ -96,6 +96,8 @@ struct LdpArgs {
     int* iter;                // [P]
     int* ws_out;              // [P][cap] or nullptr : final working set (factor order)
     int* nact_out;            // [P] or nullptr
+    int* trace_out;           // [P][1 + 2 trace_cap] or nullptr: count, then (code, value) per working-set decision -- 1 add
+    int trace_cap;            //   (2 row + lower), 2 remove (row), 3 refactor, 4 refine, 5 cycle repair, 7 exit (flag). Debugging aid.
     int* counts_out;          // [P][8] or nullptr  : scans, adds, removes, csp solves, pivot swaps, refinements, refactors, cycle repairs
     unsigned char* sense_out; // [P][ldm] or nullptr: final sense bits
     int* work_counter;        // dynamic problem queue
@@ -237,6 +239,15 @@ struct Warp {
     __device__ __forceinline__ const T* dl() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.dlower) + (size_t)p * a.sVec); }
     __device__ __forceinline__ const T* sc() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.scaling) + (size_t)pmat() * a.sVec); }
     __device__ __forceinline__ void count(int which) { if (lane == 0) cnt()[which]++; }
+    // decision log (only when the caller asked for it: the cursor lives in the log itself, no register or shared memory)
+    __device__ __forceinline__ void trace(int code, int val) {
+        if (a.trace_out != nullptr && lane == 0) {
+            int* tr = a.trace_out + (size_t)p * (1 + 2 * a.trace_cap);
+            const int c = tr[0];
+            if (c < a.trace_cap) { tr[1 + 2 * c] = code; tr[2 + 2 * c] = val; }
+            tr[0] = c + 1;
+        }
+    }
 
     __device__ __forceinline__ void reset() { sing = EMPTY_IND; k = 0; reuse = 0; } // daqp.c:142-146
 
@@ -1428,6 +1439,7 @@ struct Warp {
                     if (kq > 2 && uni(tried_repair != 1) && min_D < a.st.refactor_tol) {
                         tried_repair = 1;
                         count(6);
+                        trace(3, kq);
                         LANE_LOOP(i, 0, kq) {
                             const int id = WS()[i];
                             if (lam()[i] >= 0) sense()[id] &= ~B_LOWER; else sense()[id] |= B_LOWER;
@@ -1438,6 +1450,7 @@ struct Warp {
                     }
                     if (!refined && kq > 0 && min_D < a.st.pivot_tol) {
                         count(5);
+                        trace(4, kq);
                         refine_active();
                         refined = true;
                         again = true;
@@ -1445,13 +1458,19 @@ struct Warp {
                 }
             }
         }
+        if (a.trace_out != nullptr) trace(op == OP_ADD ? 1 : 2, op == OP_ADD ? 2 * arg + (lamval < 0 ? 1 : 0) : uni(WS()[arg]));
         modify(op, arg, lamval); // the ONE place where the working set changes inside the loop
         if (op == OP_ADD && !refined) { // cycle guard, daqp.c:67-85 (skipped on the refine path, daqp.c:54-55)
+            if (a.trace_out != nullptr) { // the objective the guard compares, bit for bit (8 = high word, 9 = low word)
+                const long long fb = __double_as_longlong((double)fval);
+                trace(8, (int)(fb >> 32)); trace(9, (int)(fb & 0xffffffffll));
+            }
             if (uni(fval - best_fval < a.st.progress_tol)) {
                 if (uni(cycle_counter++ > a.st.cycle_tol)) {
                     if (uni(tried_repair == 1)) return EXIT_CYCLE;
                     tried_repair = 1;
                     count(7);
+                    trace(5, 0);
                     do_activate = true;
                     cycle_counter = 0;
                     best_fval = -1;
@@ -1570,8 +1589,11 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? team_max_ctas
             }
             w.begin(activate);
         }
+        if (a.trace_out != nullptr && lane == 0) a.trace_out[(size_t)pq * (1 + 2 * a.trace_cap)] = 0;
+        __syncwarp();
         int exitflag;
         do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
+        w.trace(7, exitflag);
         {
         const int p = w.p, kfin = uni(w.k);
         if (uni(w.iter == 0)) {

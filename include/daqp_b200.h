@@ -217,6 +217,11 @@ typedef struct {
                                     refactor-on-exit repairs (daqp.c:33-46), cycle-guard repairs (daqp.c:67-81) */
     unsigned char* sense; /* [N][ldm], ldm = m rounded up to 4: final sense bits          */
     c_float* soft_slack;  /* [N]    DAQPResult.soft_slack (reference src/api.c:469)       */
+    int* trace;     /* [N][1 + 2 trace_cap] decision log, a debugging aid (device pointer for solve_device only; the
+                       host entries ignore it): entry 0 = number of decisions, then (code, value) pairs in order --
+                       1 add (2 row + lower), 2 remove (row), 3 refactor, 4 refine, 5 cycle repair, 7 exit (flag), 8 / 9 high and
+                       low word of the objective the cycle guard compares after an add (daqp.c:67)  */
+    int trace_cap;  /* decisions the log has room for (0 without a log)                   */
 } DAQPB200Diag;
 
 /* Homogeneous batch, strided HOST arrays: H[N][n][n], f[N][n] (or NULL), A[N][m-ms][n], bupper/blower[N][m],

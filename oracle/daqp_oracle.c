@@ -56,7 +56,13 @@ typedef struct {
     int *pstack_id; real *pstack_lam;
     int n_scan, n_add, n_remove, n_csp;
     int n_pivot, n_refine, n_refactor, n_cycle; /* rare paths: pivot_last swaps, refinements, refactor-on-exit, cycle repairs */
+    int *oplog; int oplog_cap, n_log;           /* decision log (debugging aid) */
 } Ldp;
+
+static void oplog(Ldp *w, int code, int val) {
+    if (w->oplog && w->n_log < w->oplog_cap) { w->oplog[2 * w->n_log] = code; w->oplog[2 * w->n_log + 1] = val; }
+    w->n_log++;
+}
 
 #define Lij(w, i, j) ((w)->L[(size_t)(i) * (w)->cap + (j)])
 
@@ -273,6 +279,7 @@ static int remove_blocking(Ldp *w) {
     else
         for (int i = 0; i < w->k; i++) w->lam[i] += alpha * w->lam_star[i];
     w->sing = EMPTY_IND;
+    oplog(w, 2, w->WS[rm]);
     remove_constraint(w, rm);
     return 1;
 }
@@ -292,7 +299,24 @@ static void compute_primal(Ldp *w) {
     }
     fv = fv * w->st->rho_soft;
     w->soft_slack = fv;
+#ifdef ORC_GPU_ARITH /* the solve kernel's order: lane L owns columns 2L, 2L+1 (+64 per group), xor-butterfly over the warp */
+    {
+        real part[32];
+        for (int L = 0; L < 32; L++) {
+            part[L] = 0;
+            for (int c = 2 * L; c < n; c += 64)
+                for (int e = 0; e < 2 && c + e < n; e++) part[L] += w->u[c + e] * w->u[c + e];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            real nx[32];
+            for (int L = 0; L < 32; L++) nx[L] = part[L] + part[L ^ o];
+            memcpy(part, nx, sizeof(part));
+        }
+        fv += part[0];
+    }
+#else
     for (int j = 0; j < n; j++) fv += w->u[j] * w->u[j];
+#endif
     w->fval = fv;
 }
 
@@ -319,6 +343,7 @@ static int add_infeasible(Ldp *w) {
     if (add == EMPTY_IND) return 0;
     if (isupper) w->sense[add] &= ~B_LOWER; else w->sense[add] |= B_LOWER;
     real *t = w->lam; w->lam = w->lam_star; w->lam_star = t; /* lam <- lam* (auxiliary.c:159-160) */
+    oplog(w, 1, 2 * add + (isupper ? 0 : 1));
     add_constraint(w, add, isupper ? (real)1 : (real)-1);
     return 1;
 }
@@ -434,6 +459,7 @@ static int ldp_solve(Ldp *w) {
                     if (w->k > 2 && tried_repair != 1 && min_D < w->st->refactor_tol) {
                         tried_repair = 1;
                         w->n_refactor++;
+                        oplog(w, 3, w->k);
                         for (int i = 0; i < w->k; i++) {
                             if (w->lam[i] >= 0) w->sense[w->WS[i]] &= ~B_LOWER;
                             else w->sense[w->WS[i]] |= B_LOWER;
@@ -444,17 +470,24 @@ static int ldp_solve(Ldp *w) {
                     }
                     if (w->k > 0 && min_D < w->st->pivot_tol) {
                         w->n_refine++;
+                        oplog(w, 4, w->k);
                         refine_active(w);
                         if (add_infeasible(w)) continue;
                     }
                     exitflag = (w->soft_slack > w->st->primal_tol) ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL;
                     break;
                 }
+                if (w->oplog) {
+                    double fd = (double)w->fval; long long fb;
+                    memcpy(&fb, &fd, sizeof(fb));
+                    oplog(w, 8, (int)(fb >> 32)); oplog(w, 9, (int)(fb & 0xffffffffll));
+                }
                 if (w->fval - best_fval < w->st->progress_tol) {
                     if (cycle_counter++ > w->st->cycle_tol) {
                         if (tried_repair == 1) { exitflag = EXIT_CYCLE; break; }
                         tried_repair = 1;
                         w->n_cycle++;
+                        oplog(w, 5, 0);
                         reset_ws(w);
                         activate_constraints(w);
                         cycle_counter = 0;
@@ -471,6 +504,7 @@ static int ldp_solve(Ldp *w) {
         }
     }
     w->iterations = iter;
+    oplog(w, 7, exitflag);
     return exitflag;
 }
 
@@ -618,6 +652,8 @@ void orc_quadprog(OrcResult *res, const OrcProblem *qp, const OrcSettings *setti
     if (trace) {
         trace->n_active = 0; trace->n_scan = trace->n_add = trace->n_remove = trace->n_csp = 0;
         trace->n_pivot = trace->n_refine = trace->n_refactor = trace->n_cycle = 0;
+        trace->n_log = 0;
+        w->oplog = trace->oplog; w->oplog_cap = trace->oplog_cap;
     }
 
     if (qp->sense != NULL)
@@ -770,6 +806,7 @@ solve: /* api.c:8-59 */
         if (trace->sense_out) for (int i = 0; i < m; i++) trace->sense_out[i] = w->sense[i];
         trace->n_scan = w->n_scan; trace->n_add = w->n_add; trace->n_remove = w->n_remove; trace->n_csp = w->n_csp;
         trace->n_pivot = w->n_pivot; trace->n_refine = w->n_refine; trace->n_refactor = w->n_refactor; trace->n_cycle = w->n_cycle;
+        trace->n_log = w->n_log;
     }
     ldp_free(w);
     return;

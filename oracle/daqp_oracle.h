@@ -69,6 +69,11 @@ typedef struct {
     int n_refine;     /* daqp_refine_active calls (daqp.c:52-56)                       */
     int n_refactor;   /* refactor-on-exit repairs (daqp.c:33-46)                       */
     int n_cycle;      /* cycle-guard repairs (daqp.c:67-81)                            */
+    /* decision log (debugging aid, same codes as DAQPB200Diag.trace): (code, value) pairs -- 1 add (2 row + lower),
+     * 2 remove (row), 3 refactor, 4 refine, 5 cycle repair, 7 exit (flag) */
+    int *oplog;       /* caller buffer of 2 * oplog_cap ints, or NULL                  */
+    int oplog_cap;
+    int n_log;        /* decisions made (may exceed oplog_cap)                         */
 } OrcTrace;
 
 void orc_default_settings(OrcSettings *s);

@@ -53,7 +53,8 @@ def _structs(real):
     class Trace(C.Structure):
         _fields_ = [("n_active", C.c_int), ("ws", P(C.c_int)), ("sense_out", P(C.c_int)), ("n_scan", C.c_int),
                     ("n_add", C.c_int), ("n_remove", C.c_int), ("n_csp", C.c_int), ("n_pivot", C.c_int),
-                    ("n_refine", C.c_int), ("n_refactor", C.c_int), ("n_cycle", C.c_int)]
+                    ("n_refine", C.c_int), ("n_refactor", C.c_int), ("n_cycle", C.c_int),
+                    ("oplog", P(C.c_int)), ("oplog_cap", C.c_int), ("n_log", C.c_int)]
 
     return Problem, Settings, Result, Workspace, Trace
 
@@ -88,6 +89,7 @@ class Solution:
     counts: np.ndarray | None = None  # [N,8] scan, add, remove, csp, pivot, refine, refactor, cycle repair (oracle only)
     seconds: float = 0.0
     soft_slack: np.ndarray | None = None
+    oplog: list | None = None     # per problem: [k,2] decision log (OracleLib.solve(log_cap=...))
 
 
 def default_settings(dtype=np.float64, **over):
@@ -260,7 +262,9 @@ class OracleLib:
         self.lib.orc_quadprog.restype = None
         self.lib.orc_solve_packed.restype = C.c_double
 
-    def solve(self, b, settings=None, use_sense: bool | None = None) -> Solution:
+    def solve(self, b, settings=None, use_sense: bool | None = None, log_cap: int = 0) -> Solution:
+        """log_cap > 0 also records up to that many (code, value) decisions per problem in Solution.oplog: 1 add
+        (2*constraint + lower), 2 remove (constraint), 3 refactor, 4 refine, 5 cycle repair, 7 exit (flag)."""
         import time
         N, n, m = b.N, b.n, b.m
         b = b.astype(self.dtype)
@@ -271,6 +275,8 @@ class OracleLib:
         slack = np.zeros(N, self.dtype)
         sense_out = np.zeros((N, m), np.int32)
         ws = []
+        logs = []
+        logbuf = np.zeros((max(log_cap, 1), 2), np.int32)
         wsbuf = np.zeros(n + m + 2, np.int32)
         if use_sense is None:
             use_sense = bool(np.any(b.sense))
@@ -285,13 +291,17 @@ class OracleLib:
                               sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)
             res = self.Result(_ptr(x[p], real), _ptr(lam[p], real), 0, 0, 0, 0, 0, 0, 0)
             tr = self.Trace(0, wsbuf.ctypes.data_as(C.POINTER(C.c_int)),
-                            sense_out[p].ctypes.data_as(C.POINTER(C.c_int)), 0, 0, 0, 0, 0, 0, 0, 0)
+                            sense_out[p].ctypes.data_as(C.POINTER(C.c_int)), 0, 0, 0, 0, 0, 0, 0, 0,
+                            logbuf.ctypes.data_as(C.POINTER(C.c_int)) if log_cap else None, log_cap, 0)
             self.lib.orc_quadprog(C.byref(res), C.byref(qp), sp, C.byref(tr))
+            if log_cap:
+                logs.append(logbuf[:min(tr.n_log, log_cap)].copy())
             fval[p], flag[p], it[p] = res.fval, res.exitflag, res.iter
             slack[p] = res.soft_slack
             counts[p] = (tr.n_scan, tr.n_add, tr.n_remove, tr.n_csp, tr.n_pivot, tr.n_refine, tr.n_refactor, tr.n_cycle)
             ws.append(wsbuf[:tr.n_active].tolist())
-        return Solution(x, lam, fval, flag, it, ws, sense_out, counts, time.perf_counter() - t0, slack)
+        return Solution(x, lam, fval, flag, it, ws, sense_out, counts, time.perf_counter() - t0, slack,
+                        logs if log_cap else None)
 
     def solve_packed(self, b, settings=None, nthreads: int = 1, use_sense: bool | None = None) -> Solution:
         """Whole batch inside C (no Python in the timed loop); returns wall seconds measured in C."""
