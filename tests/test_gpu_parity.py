@@ -78,7 +78,7 @@ def test_rare_paths_cuda_matches_reference(engine, name):
     # input perturbations agree on; what is left may still part from a GPU summation order on an isolated problem, which
     # is tolerated up to 1 in 50 and REPORTED -- every other problem, and every problem of every other fixture, must
     # follow the reference's path exactly. The one such problem today (rare_eqpairs_n12_ms4[33]) was traced decision by
-    # decision (scripts/trace_diff.py, profiles/trace_diff_rare_eqpairs_r02.log): both sides make the SAME 38 first
+    # decision (tests/trace_diff.py, profiles/trace_diff_rare_eqpairs_r02.log): both sides make the SAME 38 first
     # decisions and enter the same 4-step cycle; with D ~ 1e-10 the objective is only reproducible to ~1e-11, and the
     # GPU's value drifts by +9e-12 during the first two periods, which the guard's 1e-14 progress test (daqp.c:67) counts
     # as progress -- so the repair fires two periods (8 iterations) later and then proceeds identically to the same exit.

@@ -2,7 +2,7 @@
 (DAQPB200Diag.trace) and in the oracle (OracleLib.solve(log_cap=...)), and print, for every problem whose iteration
 count differs, the first decision the two disagree on together with a few decisions either side.
 
-    python scripts/trace_diff.py rare_eqpairs_n12_ms4 [more fixtures]
+    python tests/trace_diff.py rare_eqpairs_n12_ms4 [more fixtures]
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # test tooling: the oracle is the checker here
 import daqp_b200  # noqa: E402
 from common import load_golden, rare_settings  # noqa: E402
 from oracle import harness  # noqa: E402
