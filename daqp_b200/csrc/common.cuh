@@ -30,7 +30,14 @@ template <typename T>
 struct DevSettings { // the DAQPSettings fields the hot path reads (include/types.h:52-74)
     T primal_tol, dual_tol, zero_tol, pivot_tol, progress_tol, fval_bound, rho_soft, sing_tol, refactor_tol, eps_prox;
     int cycle_tol, iter_limit;
+    long long time_limit_ns; // settings->time_limit in ns of %globaltimer; 0 = no limit (daqp.c:95-103)
 };
+
+__device__ __forceinline__ long long global_timer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <typename T> struct VecOf;
 template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };

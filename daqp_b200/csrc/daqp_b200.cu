@@ -96,6 +96,7 @@ static DevSettings<T> to_dev_settings(const DAQPSettings* s) {
     o.pivot_tol = (T)s->pivot_tol; o.progress_tol = (T)s->progress_tol; o.fval_bound = (T)s->fval_bound;
     o.rho_soft = (T)s->rho_soft; o.sing_tol = (T)s->sing_tol; o.refactor_tol = (T)s->refactor_tol;
     o.eps_prox = (T)s->eps_prox; o.cycle_tol = s->cycle_tol; o.iter_limit = s->iter_limit;
+    o.time_limit_ns = s->time_limit > 0 ? (long long)(s->time_limit * 1e9) + 1 : 0;
     return o;
 }
 
@@ -1373,6 +1374,11 @@ extern "C" int daqp_b200_bnb(DAQPB200Handle* h, const DAQPProblem* qp, const DAQ
     int last_fail = 0;
     const auto t0 = std::chrono::steady_clock::now();
     while (!open.empty()) {
+        if (st.time_limit > 0 && // the limit also holds across the tree (bnb.c:52-60), checked once per wave
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > st.time_limit) {
+            last_fail = DAQP_EXIT_TIMELIMIT;
+            break;
+        }
         const int cnt = (int)std::min<size_t>(W, open.size());
         std::vector<Node> wave(std::make_move_iterator(open.end() - cnt), std::make_move_iterator(open.end())); // the deepest nodes
         open.resize(open.size() - cnt);

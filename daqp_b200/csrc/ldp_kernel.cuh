@@ -1197,7 +1197,7 @@ struct Warp {
             b->oWS = o + a.oWS * 4; b->osense = o + a.osense; b->ou = o + a.ou * w; b->ou32 = o + a.ou32 * 4;
             b->otmp = (int)a.otmp; b->opv = (int)a.opv; b->obv = (int)a.obv; b->oside = (int)a.oside;
             b->cap = a.cap; b->n = a.n; b->m = a.m; b->ldm = a.ldm; b->ldn = a.ldn; b->tune = a.tune;
-            b->primal_tol = (double)a.st.primal_tol;
+            b->primal_tol = (double)a.st.primal_tol; b->sing_tol = (double)a.st.sing_tol; b->pivot_tol = (double)a.st.pivot_tol;
         }
     }
     // once per problem: its global arrays (the helpers see them with the first command of the problem)
@@ -1253,6 +1253,44 @@ struct Warp {
     // ---- a13: warm start / equality activation (auxiliary.c:399-479)
     __device__ __forceinline__ int activate_constraints() {
         unsigned char* se = sense();
+        if constexpr (TW > 1) {
+            // A team activates a whole warm start at once: one pass for every dot product the K row-by-row updates would
+            // compute (team_gram), one right-looking pass for the K forward substitutions (team_ldl) -- the same products
+            // in the same order, without K x (row fetch + dependent sweep). Anything the row-by-row path treats
+            // specially (singular pivot, pivot swap, more rows than dimensions) sends the activation back to it.
+            if (uni(k == 0) && !(EXT && a.ns_max > 0)) {
+                int K = 0;
+                int* wsp = WS();
+                for (int base = 0; base < a.m; base += 32) {
+                    const int i = base + lane;
+                    const bool on = i < a.m && (se[i] & B_ACTIVE);
+                    const unsigned msk = __ballot_sync(FULL, on);
+                    const int pos = K + __popc(msk & ((1u << lane) - 1u));
+                    if (on && pos < a.cap) wsp[pos] = i;
+                    K += __popc(msk);
+                }
+                K = uni(K);
+                __syncwarp();
+                if (K >= TEAM_GRAM_MIN && K <= a.n) {
+                    if (lane == 0) tbox()->rk[0] = K;
+                    team_run(TC_GRAM, K, 0);
+                    team_run(TC_LDL, K, 0);
+                    const int done = uni((int)reinterpret_cast<volatile TeamBox*>(tbox())->rk[0]);
+                    if (done >= K) {
+                        LANE_LOOP(j, 0, K) {
+                            const int id = wsp[j], sb = se[id];
+                            lam()[j] = (sb & B_LOWER) ? (T)-1 : (T)1;
+                            dact()[j] = (sb & B_LOWER) ? dl()[id] : du()[id];
+                        }
+                        if (lane == 0) cnt()[1] += K;
+                        k = K;
+                        sing = EMPTY_IND;
+                        __syncwarp();
+                        return 1;
+                    }
+                }
+            }
+        }
         for (int i = 0; i < a.m; i++) {
             const int sb = uni((int)se[i]);
             if (sb & B_ACTIVE) modify(OP_ADD, i, (sb & B_LOWER) ? (T)-1 : (T)1);
@@ -1592,7 +1630,18 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? team_max_ctas
         if (a.trace_out != nullptr && lane == 0) a.trace_out[(size_t)pq * (1 + 2 * a.trace_cap)] = 0;
         __syncwarp();
         int exitflag;
-        do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
+        if (uni(a.st.time_limit_ns == 0)) {
+            do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
+        } else { // settings->time_limit: the clock starts with the problem's solve (api.c:15) and is read every 32nd
+                 // iteration (daqp.c:95-103); the iteration count reported is the one the check ran in
+            const long long t0 = global_timer_ns();
+            do {
+                exitflag = uni(w.step());
+                if (exitflag == Warp<T, NV, EXT, TW>::RUNNING && (w.iter & 31) == 0 && w.iter > 0 &&
+                    uni((int)(global_timer_ns() - t0 > a.st.time_limit_ns)))
+                    exitflag = EXIT_TIMELIMIT;
+            } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
+        }
         w.trace(7, exitflag);
         {
         const int p = w.p, kfin = uni(w.k);

@@ -31,7 +31,7 @@ struct TeamBox {
     // layout: byte offsets from the start of the CTA's shared memory (written once per launch by the leader)
     int oL, oD, olamA, olamB, oWS, osense, ou, ou32, otmp, opv, obv, oside;
     int cap, n, m, ldm, ldn, tune;
-    double primal_tol;
+    double primal_tol, sing_tol, pivot_tol;
     // global arrays of the current problem (written by the leader when it takes a problem off the queue)
     const void *Mr, *Mt, *Mt32, *du, *dl, *sc;
 };
@@ -43,7 +43,8 @@ static_assert(sizeof(TeamBox) <= TEAM_BOX_BYTES, "TeamBox grew past its slot");
 // latency at three warps per scheduler, not by issue slots).
 constexpr int TEAM_WARPS = 4;
 __host__ __device__ constexpr int team_max_ctas(int tw) { return tw == 2 ? 12 : 3; } // resident teams per SM (__launch_bounds__)
-enum { TC_EXIT = 0, TC_FWD, TC_BWD, TC_REMOVE, TC_DOTS, TC_PRIMAL, TC_SCAN32, TC_SCAN64 };
+enum { TC_EXIT = 0, TC_FWD, TC_BWD, TC_REMOVE, TC_DOTS, TC_PRIMAL, TC_SCAN32, TC_SCAN64, TC_GRAM, TC_LDL };
+constexpr int TEAM_GRAM_MIN = 8; // warm starts with fewer rows than this are activated one by one
 
 #define TEAM_SMEM                                                   \
     extern __shared__ __align__(16) unsigned char smem_raw[];       \
@@ -259,6 +260,115 @@ __device__ __noinline__ void team_dots(int lane, int wid, int add, int kk) {
     }
 }
 
+// a13 for a team, first half: ALL the dot products K successive daqp_update_LDL_add calls would compute
+// (factorization.c:40-84) in one pass -- g_ij = row(WS[i]) . row(WS[j]) into the strict lower triangle of L, g_ii into
+// D. A warp takes four rows i at a time (register-resident) and streams the rows j <= i past them four at a time: every
+// row fetched from L2 serves sixteen products, and no product waits for a factor update. Row blocks are dealt to the
+// warps from the bottom (longest first).
+template <typename T, int TW, int NG>
+__device__ __noinline__ void team_gram(int lane, int wid, int K) {
+    TEAM_SMEM;
+    constexpr int V = VecOf<T>::N, IB = 4, JB = 4;
+    const int ldn = box->ldn;
+    const T* M = reinterpret_cast<const T*>(box->Mr) + V * lane; // this lane's column slice of row 0
+    const int* ws = reinterpret_cast<const int*>(smem_raw + box->oWS);
+    T* Lp = reinterpret_cast<T*>(smem_raw + box->oL);
+    T* Dp = reinterpret_cast<T*>(smem_raw + box->oD);
+    bool okg[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) okg[g] = V * (lane + 32 * g) < ldn;
+    const int nblk = (K + IB - 1) / IB;
+    for (int b = nblk - 1 - wid; b >= 0; b -= TW) {
+        const int i0 = IB * b, jend = min(i0 + IB, K);
+        T mi[IB][NG][V];
+#pragma unroll
+        for (int r = 0; r < IB; r++) {
+            const T* row = M + (size_t)(unsigned)(ws[min(i0 + r, K - 1)] * ldn);
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+#pragma unroll
+                for (int e = 0; e < V; e++) mi[r][g][e] = 0;
+                if (okg[g]) ldg_vec<T>(row + 32 * V * g, mi[r][g]);
+            }
+        }
+        for (int j0 = 0; j0 < jend; j0 += JB) {
+            T t[JB][NG][V];
+#pragma unroll
+            for (int rr = 0; rr < JB; rr++) {
+                const T* row = M + (size_t)(unsigned)(ws[min(j0 + rr, K - 1)] * ldn);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+#pragma unroll
+                    for (int e = 0; e < V; e++) t[rr][g][e] = 0;
+                    if (okg[g]) ldg_vec<T>(row + 32 * V * g, t[rr][g]);
+                }
+            }
+            T pj[IB * JB];
+#pragma unroll
+            for (int r = 0; r < IB; r++)
+#pragma unroll
+                for (int rr = 0; rr < JB; rr++) {
+                    T acc = 0;
+#pragma unroll
+                    for (int g = 0; g < NG; g++)
+#pragma unroll
+                        for (int e = 0; e < V; e++) acc += t[rr][g][e] * mi[r][g][e];
+                    pj[r * JB + rr] = acc;
+                }
+            const T total = warp_sum_multi<IB * JB>(pj, lane);
+            const int idx = multi_index<IB * JB>(lane), i = i0 + idx / JB, j = j0 + idx % JB;
+            if ((lane & (32 / (IB * JB) - 1)) == 0 && i < K && j <= i) {
+                if (j == i) Dp[i] = total; else Lp[loff(i) + j] = total;
+            }
+        }
+    }
+}
+
+// a13 for a team, second half: the LDL' factor of the Gram matrix team_gram left in L / D, in place and right-looking --
+// thread i owns row i. Step j: every row below scales its entry (l_ij = x_ij / d_j, factorization.c:96-99), publishes it,
+// and after the barrier subtracts l_tj x_ij from its entries t = j+1 .. i-1: the products and their (ascending pivot)
+// order are those of the forward substitutions of K successive daqp_update_LDL_add calls (factorization.c:86-92), and
+// d_i = g_ii - sum_j x_ij l_ij (:100-103). The pass stops at the first row the one-by-one path treats specially -- a
+// singular pivot (factorization.c:106-110) or a daqp_pivot_last swap (auxiliary.c:379-396) -- and reports its index in
+// box->rk[0] (K = none); the leader then redoes the activation row by row.
+template <typename T, int TW>
+__device__ __noinline__ void team_ldl(int lane, int wid, int K) {
+    TEAM_SMEM;
+    T* const colA = reinterpret_cast<T*>(smem_raw + box->otmp);
+    T* const colB = reinterpret_cast<T*>(smem_raw + box->opv);
+    T* Dp = reinterpret_cast<T*>(smem_raw + box->oD);
+    volatile int* stop = box->rk;
+    const int i = 32 * wid + lane;
+    T* Li = reinterpret_cast<T*>(smem_raw + box->oL) + loff(min(i, box->cap - 1));
+    const T sing_tol = (T)box->sing_tol, pivot_tol = (T)box->pivot_tol;
+    if (i == 0 && Dp[0] < sing_tol) stop[0] = 0;
+    team_bar<TW>();
+    T acc = 0;
+    for (int j = 0; j + 1 < K; j++) {
+        if (stop[0] <= j) break; // (written before the barrier that ended the previous step: the whole team sees it)
+        T* col = (j & 1) ? colB : colA;
+        const bool below = i > j && i < K;
+        const T dj = Dp[j];
+        const T x = below ? Li[j] : (T)0;
+        const T l = fdiv(x, dj); // unconditional call: no divergence around the division
+        if (below) {
+            acc += x * l;
+            Li[j] = l;
+            col[i] = l;
+            if (i == j + 1) {
+                const T d = Dp[i] - acc;
+                Dp[i] = d;
+                if (d < sing_tol || (dj < pivot_tol && dj < d)) stop[0] = i;
+            }
+        }
+        team_bar<TW>();
+        if (below) {
+#pragma unroll 4
+            for (int t = j + 1; t < i; t++) Li[t] -= col[t] * x;
+        }
+    }
+}
+
 // a7 for a team: u = -sum_i lam*_i row(WS[i]); thread c owns column c and adds the rows in index order (the order of
 // auxiliary.c:54-68), UNR rows in flight per thread. Per-warp partial |u|^2 goes to the box.
 template <typename T, int TW>
@@ -448,6 +558,8 @@ __device__ __forceinline__ void team_dispatch(int cmd, int lane, int wid, int a0
         case TC_REMOVE: team_remove<T, TW>(lane, wid, a0, a1); break;
         case TC_DOTS: team_dots<T, TW, NG>(lane, wid, a0, a1); break;
         case TC_PRIMAL: team_primal<T, TW>(lane, wid, a0, a1); break;
+        case TC_GRAM: team_gram<T, TW, NG>(lane, wid, a0); break;
+        case TC_LDL: team_ldl<T, TW>(lane, wid, a0); break;
         case TC_SCAN32: if constexpr (sizeof(T) == 8) team_scan32<TW>(lane, wid); break;
         default: team_scan64<T, TW>(lane, wid); break;
     }

@@ -488,6 +488,23 @@ def test_settings_and_limits(engine, oracle):
     assert (run_gpu(engine, b).exitflag == -8).all()  # singular H needs the proximal driver: flagged
 
 
+def test_time_limit(engine, oracle):
+    """settings.time_limit (daqp.c:95-103): the clock is read every 32nd iteration, so with a limit no solve can meet a
+    problem either ends before its 32nd iteration, untouched, or leaves there with EXIT_TIMELIMIT (-7) and iter = 32; a
+    generous limit changes nothing. Plain kernel (n = 50) and team mode (n = 70)."""
+    for (n, m, na, seed) in ((50, 150, 40, 55), (70, 200, 50, 56)):
+        b = generate_g1(200, n, m, 0, na, seed=seed)
+        o = oracle.solve(b)
+        r = run_gpu(engine, b, time_limit=1e-9)
+        long = o.iter > 32
+        assert long.any() and (~long).any() or long.all()
+        assert (r.exitflag[long] == -7).all() and (r.iter[long] == 32).all()
+        np.testing.assert_array_equal(r.exitflag[~long], o.exitflag[~long])
+        np.testing.assert_array_equal(r.iter[~long], o.iter[~long])
+        r = run_gpu(engine, b, time_limit=100.0)
+        assert_parity(o.x, o.lam, o.fval, o.exitflag, o.iter, r.x, r.lam, r.fval, r.exitflag, r.iter, "generous time limit")
+
+
 def test_no_linear_term_and_diagonal_hessian(engine, oracle):
     b = generate_g1(100, 12, 36, 4, 9, seed=61)
     b.H[:] = (np.eye(12) * np.linspace(1, 5, 12))[None]
