@@ -242,7 +242,7 @@ static cudaError_t launch_solve(const LdpArgs<T>& a, int grid, int block, size_t
         if constexpr (NV <= 5) return launch_solve_x<T, NV, false>(a, grid, block, smem, s);
         else return cudaErrorNotSupported;
     } else {
-        return (a.ns_max > 0 || a.state || a.grp > 1) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
+        return (a.ns_max > 0 || a.state || a.grp > 1 || a.aux) ? launch_solve_x<T, NV, true>(a, grid, block, smem, s)
                                          : launch_solve_x<T, NV, false>(a, grid, block, smem, s);
     }
 }
@@ -330,8 +330,12 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     // experiment knob DAQP_B200_REGSTAGE=1 (n <= 63, plain fp64 path): the register-staged warp kernel -- no staging arena in
     // shared memory, 16 problems per SM at n = 50 instead of 12. Measured on C3: 104.9 ms against 104.65 ms for the
     // cp.async-staged kernel with 12 -- a third more resident warps buys nothing, so it stays opt-in.
+    // the decision log and settings.time_limit live in the extended and the team instantiations of the solve kernel
+    const DevSettings<T> st = to_dev_settings<T>(settings);
+    const bool aux = sizeof(T) == 8 && ((diag && diag->trace && diag->trace_cap > 0) || st.time_limit_ns != 0);
+    la.aux = aux ? 1 : 0;
     bool regstage = false;
-    if (const char* renv = getenv("DAQP_B200_REGSTAGE")) regstage = atoi(renv) != 0 && sizeof(T) == 8 && ns_max == 0 && !ps && team == 0 && nv <= 2;
+    if (const char* renv = getenv("DAQP_B200_REGSTAGE")) regstage = atoi(renv) != 0 && sizeof(T) == 8 && ns_max == 0 && !ps && team == 0 && nv <= 2 && !aux;
     const size_t smem_solve_w = ldp_layout<T>(la, regstage ? -1 : team), smem_setup_w = setup_smem_per_warp<T>(n);
     const size_t budget = h->smem_optin;
     int w_solve = (int)std::min<size_t>(16, budget / smem_solve_w), w_setup = (int)std::min<size_t>(16, budget / smem_setup_w);
@@ -350,7 +354,6 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
 
     rc = arena_acquire(h, stream);
     if (rc) return rc;
-    const DevSettings<T> st = to_dev_settings<T>(settings);
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
     const bool screening = sizeof(T) == 8 && !(tune & 2) && (team ? (m + 31) / 32 <= TEAM_SCREEN_MAX_GROUPS * team : m <= 256);

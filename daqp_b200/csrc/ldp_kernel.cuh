@@ -96,6 +96,7 @@ struct LdpArgs {
     int* iter;                // [P]
     int* ws_out;              // [P][cap] or nullptr : final working set (factor order)
     int* nact_out;            // [P] or nullptr
+    int aux;                  // the launch needs the decision log or the time limit: instantiations that carry them (AUX below)
     int* trace_out;           // [P][1 + 2 trace_cap] or nullptr: count, then (code, value) per working-set decision -- 1 add
     int trace_cap;            //   (2 row + lower), 2 remove (row), 3 refactor, 4 refine, 5 cycle repair, 7 exit (flag). Debugging aid.
     int* counts_out;          // [P][8] or nullptr  : scans, adds, removes, csp solves, pivot swaps, refinements, refactors, cycle repairs
@@ -240,7 +241,11 @@ struct Warp {
     __device__ __forceinline__ const T* sc() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.scaling) + (size_t)pmat() * a.sVec); }
     __device__ __forceinline__ void count(int which) { if (lane == 0) cnt()[which]++; }
     // decision log (only when the caller asked for it: the cursor lives in the log itself, no register or shared memory)
+    // (the decision log and the time limit are compiled into the extended and the team instantiations only: the plain
+    // warp-per-problem kernel is bound by its instruction-cache footprint, and even dead code between hot blocks costs)
+    static constexpr bool AUX = EXT || TW > 1;
     __device__ __forceinline__ void trace(int code, int val) {
+        if constexpr (!AUX) return;
         if (a.trace_out != nullptr && lane == 0) {
             int* tr = a.trace_out + (size_t)p * (1 + 2 * a.trace_cap);
             const int c = tr[0];
@@ -1496,10 +1501,10 @@ struct Warp {
                 }
             }
         }
-        if (a.trace_out != nullptr) trace(op == OP_ADD ? 1 : 2, op == OP_ADD ? 2 * arg + (lamval < 0 ? 1 : 0) : uni(WS()[arg]));
+        if (AUX && a.trace_out != nullptr) trace(op == OP_ADD ? 1 : 2, op == OP_ADD ? 2 * arg + (lamval < 0 ? 1 : 0) : uni(WS()[arg]));
         modify(op, arg, lamval); // the ONE place where the working set changes inside the loop
         if (op == OP_ADD && !refined) { // cycle guard, daqp.c:67-85 (skipped on the refine path, daqp.c:54-55)
-            if (a.trace_out != nullptr) { // the objective the guard compares, bit for bit (8 = high word, 9 = low word)
+            if (AUX && a.trace_out != nullptr) { // the objective the guard compares, bit for bit (8 = high word, 9 = low word)
                 const long long fb = __double_as_longlong((double)fval);
                 trace(8, (int)(fb >> 32)); trace(9, (int)(fb & 0xffffffffll));
             }
@@ -1627,21 +1632,22 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 512, TW > 1 ? team_max_ctas
             }
             w.begin(activate);
         }
-        if (a.trace_out != nullptr && lane == 0) a.trace_out[(size_t)pq * (1 + 2 * a.trace_cap)] = 0;
+        if (Warp<T, NV, EXT, TW>::AUX && a.trace_out != nullptr && lane == 0) a.trace_out[(size_t)pq * (1 + 2 * a.trace_cap)] = 0;
         __syncwarp();
         int exitflag;
-        if (uni(a.st.time_limit_ns == 0)) {
-            do { exitflag = uni(w.step()); } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
-        } else { // settings->time_limit: the clock starts with the problem's solve (api.c:15) and is read every 32nd
-                 // iteration (daqp.c:95-103); the iteration count reported is the one the check ran in
-            const long long t0 = global_timer_ns();
-            do {
-                exitflag = uni(w.step());
-                if (exitflag == Warp<T, NV, EXT, TW>::RUNNING && (w.iter & 31) == 0 && w.iter > 0 &&
+        // settings->time_limit: the clock starts with the problem's solve (api.c:15) and is read every 32nd iteration
+        // (daqp.c:95-103); the iteration count reported is the one the check ran in. (ONE call site of step(): a second
+        // inlined copy of the state machine costs a third of the kernel's speed in instruction-cache misses.)
+        constexpr bool AUX = Warp<T, NV, EXT, TW>::AUX;
+        const long long t0 = (AUX && a.st.time_limit_ns != 0) ? global_timer_ns() : 0;
+        do {
+            exitflag = uni(w.step());
+            if constexpr (AUX) {
+                if (a.st.time_limit_ns != 0 && exitflag == Warp<T, NV, EXT, TW>::RUNNING && (w.iter & 31) == 0 && w.iter > 0 &&
                     uni((int)(global_timer_ns() - t0 > a.st.time_limit_ns)))
                     exitflag = EXIT_TIMELIMIT;
-            } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
-        }
+            }
+        } while (exitflag == Warp<T, NV, EXT, TW>::RUNNING);
         w.trace(7, exitflag);
         {
         const int p = w.p, kfin = uni(w.k);

@@ -104,14 +104,33 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 32 * FACTOR_MAX_WARPS, 1) q
         T hscale = 0;
         if (flag >= 0) {
             if (st.eps_prox > 0) flag = EXIT_UNSUPPORTED; // forced proximal mode is a different driver
+            // R <- upper triangle of (H + H') / 2 (utils.c:319-323) in two coalesced passes over H: the upper elements
+            // first, then every lower element is averaged into its mirror image (a strided read of H[j][i] per upper
+            // element was a fifth of this kernel's stall samples). h_ij + h_ji either way round: the same sum.
             int nd = 0;
-            for (int idx = tid; idx < n * n; idx += NT) {
-                const int i = idx / n, j = idx - i * n;
-                const T h = H[idx];
-                if (j > i && (h > st.zero_tol || h < -st.zero_tol)) nd = 1;
-                if (j >= i) R[roff(i, n) + j] = (j == i) ? h : (T)0.5 * (h + H[(size_t)j * n + i]);
+            {
+                int i = 0, j = tid;
+                while (j >= n) { j -= n; i++; }
+                for (int idx = tid; idx < n * n; idx += NT) {
+                    const T h = H[idx];
+                    if (j > i && (h > st.zero_tol || h < -st.zero_tol)) nd = 1;
+                    if (j >= i) R[roff(i, n) + j] = h;
+                    j += NT;
+                    while (j >= n) { j -= n; i++; }
+                }
             }
-            is_diag = !any(nd); // (also orders the writes of R before the reads below)
+            is_diag = !any(nd);
+            sync(); // the upper elements are in place before their mirror images are averaged in
+            {
+                int i = 0, j = tid;
+                while (j >= n) { j -= n; i++; }
+                for (int idx = tid; idx < n * n; idx += NT) {
+                    if (j < i) { T* q = R + roff(j, n) + i; *q = (T)0.5 * (*q + H[idx]); }
+                    j += NT;
+                    while (j >= n) { j -= n; i++; }
+                }
+            }
+            sync();
             for (int i = lane; i < n; i += 32) hscale = fmax(hscale, fabs(R[roff(i, n) + i])); // every warp: the whole diagonal
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) hscale = fmax(hscale, __shfl_xor_sync(FULL, hscale, o));
@@ -139,41 +158,104 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 32 * FACTOR_MAX_WARPS, 1) q
             else if (any(prox)) flag = EXIT_UNSUPPORTED; // reference hands over to daqp_prox
             sync();
         } else if (flag >= 0) {
-            // upper Cholesky by rows, 1/r_ii kept on the diagonal (utils.c:337-352)
+            // upper Cholesky by rows, 1/r_ii kept on the diagonal (utils.c:337-352). Rows are taken CB at a time: the part
+            // of their sums that runs over the rows above the block (kk < i0) is accumulated for all CB rows in one
+            // pass -- one load of R[kk][j] serves CB products -- then the rows are finished one after the other with
+            // the terms of the block's own rows. Per element the products and their order (kk ascending) are unchanged.
             T min_piv = (T)1e30, max_piv = 0;
             bool singular = false;
-            for (int i = 0; i < n; i++) {
-                T* Ri = R + roff(i, n);
-                T part = 0; // every warp sums the whole column: no cross-warp reduction
-                for (int kk = lane; kk < i; kk += 32) { const T t = R[roff(kk, n) + i]; part += t * t; }
-                T di = Ri[i] - warp_sum(part);
-                sync(); // every thread has read the pivot before it is replaced below
-                if (di <= st.zero_tol) { singular = true; break; }
-                min_piv = fmin(min_piv, di);
-                max_piv = fmax(max_piv, di);
-                di = rsqrt_exact<T>(di);
-                for (int j = i + 1 + tid; j < n; j += NT) {
-                    T s = Ri[j];
-                    const T* Rk = R; // running row pointer: roff(kk+1) = roff(kk) + (n - kk - 1)
-                    for (int kk = 0; kk < i; kk++) { s -= Rk[i] * Rk[j]; Rk += n - kk - 1; }
-                    Ri[j] = s * di;
+            constexpr int CB = 4, JC = TW > 1 ? 1 : 2; // thread tid owns columns i0 + 1 + tid + NT c (n - 1 <= NT JC)
+            for (int i0 = 0; i0 < n && !singular; i0 += CB) {
+                T s[JC][CB];
+#pragma unroll
+                for (int c = 0; c < JC; c++) {
+                    const int j = i0 + 1 + tid + NT * c;
+#pragma unroll
+                    for (int r = 0; r < CB; r++) s[c][r] = (j < n && j > i0 + r) ? R[roff(i0 + r, n) + j] : (T)0;
                 }
-                if (tid == 0) Ri[i] = di;
-                sync();
+                {
+                    const T* Rk = R; // running row pointer: roff(kk+1) = roff(kk) + (n - kk - 1)
+                    for (int kk = 0; kk < i0; kk++) {
+                        T b[CB];
+#pragma unroll
+                        for (int r = 0; r < CB; r++) b[r] = Rk[min(i0 + r, n - 1)];
+#pragma unroll
+                        for (int c = 0; c < JC; c++) {
+                            if (c == 0 || i0 + 1 + NT * c < n) { // (uniform)
+                                const int j = i0 + 1 + tid + NT * c;
+                                const T x = Rk[min(j, n - 1)];
+#pragma unroll
+                                for (int r = 0; r < CB; r++) s[c][r] -= b[r] * x;
+                            }
+                        }
+                        Rk += n - kk - 1;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < CB; r++) {
+                    const int i = i0 + r;
+                    if (i < n && !singular) { // (uniform)
+                        T* Ri = R + roff(i, n);
+                        T part = 0; // every warp sums the whole column: no cross-warp reduction
+                        for (int kk = lane; kk < i; kk += 32) { const T t = R[roff(kk, n) + i]; part += t * t; }
+                        T di = Ri[i] - warp_sum(part);
+                        sync(); // every thread has read the pivot before it is replaced below
+                        if (di <= st.zero_tol) singular = true;
+                        else {
+                            min_piv = fmin(min_piv, di);
+                            max_piv = fmax(max_piv, di);
+                            di = rsqrt_exact<T>(di);
+#pragma unroll
+                            for (int c = 0; c < JC; c++) {
+                                const int j = i0 + 1 + tid + NT * c;
+                                if (j < n && j > i) {
+                                    T v = s[c][r];
+                                    for (int kk = i0; kk < i; kk++) v -= R[roff(kk, n) + i] * R[roff(kk, n) + j];
+                                    Ri[j] = v * di;
+                                }
+                            }
+                            if (tid == 0) Ri[i] = di;
+                        }
+                        sync();
+                    }
+                }
             }
             if (singular || min_piv <= st.zero_tol * max_piv) { // utils.c:356-377: shift + proximal driver
                 T eps = st.eps_prox < 0 ? -st.eps_prox : st.eps_prox;
                 flag = (eps <= 0) ? EXIT_NONCONVEX : EXIT_UNSUPPORTED;
             } else {
-                // R -> R^-1 in place (utils.c:380-389): all rows advance in lock-step over the pivot i
+                // R -> R^-1 in place (utils.c:380-389): all rows advance in lock-step over the pivot i. The update of pivot
+                // i is the outer product (rows k0 < i) x (columns j > i): tall and narrow late, short and wide early. Early
+                // pivots give a WARP a row and its lanes the columns (row i cached in registers), late ones a THREAD a row
+                // (the round-1 mapping); the switch is per pivot by instruction count. Same products, same order.
+                const int wrp = TW > 1 ? wib : 0;
                 for (int i = 0; i < n; i++) {
                     const T* Ri = R + roff(i, n);
                     const T rii = Ri[i];
-                    for (int k0 = tid; k0 < i; k0 += NT) {
-                        T* Rk = R + roff(k0, n);
-                        const T t = Rk[i] * rii;
-                        Rk[i] = t;
-                        for (int j = i + 1; j < n; j++) Rk[j] -= Ri[j] * t;
+                    const int w = n - i - 1;
+                    const int cost_row = ((i + NT - 1) / NT) * w * 4, cost_col = ((i + TW - 1) / TW) * (((w + 31) >> 5) * 3 + 8);
+                    if (cost_row <= cost_col) {
+                        for (int k0 = tid; k0 < i; k0 += NT) {
+                            T* Rk = R + roff(k0, n);
+                            const T t = Rk[i] * rii;
+                            Rk[i] = t;
+                            for (int j = i + 1; j < n; j++) Rk[j] -= Ri[j] * t;
+                        }
+                    } else {
+                        T rj[4];
+#pragma unroll
+                        for (int c = 0; c < 4; c++) { const int j = i + 1 + lane + 32 * c; rj[c] = j < n ? Ri[j] : (T)0; }
+                        for (int k0 = wrp; k0 < i; k0 += TW) {
+                            T* Rk = R + roff(k0, n);
+                            const T t = Rk[i] * rii;
+                            __syncwarp(); // every lane has read the row's pivot entry before lane 0 replaces it
+                            if (lane == 0) Rk[i] = t;
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const int j = i + 1 + lane + 32 * c;
+                                if (32 * c < w && j < n) Rk[j] -= rj[c] * t;
+                            }
+                        }
                     }
                     sync();
                     for (int j = i + 1 + tid; j < n; j += NT) R[roff(i, n) + j] *= -rii;

@@ -86,7 +86,8 @@ typedef struct {
     c_float sing_tol;
     c_float refactor_tol;
     c_float time_limit; /* seconds per problem, 0 = none: the clock starts when a warp takes the problem and is read every
-                           32nd iteration (daqp.c:95-103) -> DAQP_EXIT_TIMELIMIT; B&B also checks it once per wave */
+                           32nd iteration (daqp.c:95-103) -> DAQP_EXIT_TIMELIMIT; B&B also checks it once per wave.
+                           fp64 entries only (the fp32 entries ignore it) */
 } DAQPSettings;
 
 /* reference include/api.h:15-27 */
