@@ -104,33 +104,16 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 32 * FACTOR_MAX_WARPS, 1) q
         T hscale = 0;
         if (flag >= 0) {
             if (st.eps_prox > 0) flag = EXIT_UNSUPPORTED; // forced proximal mode is a different driver
-            // R <- upper triangle of (H + H') / 2 (utils.c:319-323) in two coalesced passes over H: the upper elements
-            // first, then every lower element is averaged into its mirror image (a strided read of H[j][i] per upper
-            // element was a fifth of this kernel's stall samples). h_ij + h_ji either way round: the same sum.
+            // (a two-pass variant that reads H coalesced both times and averages the lower elements into their mirror
+            // images was slower at both sizes: 7.1 -> 7.4 ms at C3, 60 -> 64 ms at C4 -- the strided read overlaps)
             int nd = 0;
-            {
-                int i = 0, j = tid;
-                while (j >= n) { j -= n; i++; }
-                for (int idx = tid; idx < n * n; idx += NT) {
-                    const T h = H[idx];
-                    if (j > i && (h > st.zero_tol || h < -st.zero_tol)) nd = 1;
-                    if (j >= i) R[roff(i, n) + j] = h;
-                    j += NT;
-                    while (j >= n) { j -= n; i++; }
-                }
+            for (int idx = tid; idx < n * n; idx += NT) {
+                const int i = idx / n, j = idx - i * n;
+                const T h = H[idx];
+                if (j > i && (h > st.zero_tol || h < -st.zero_tol)) nd = 1;
+                if (j >= i) R[roff(i, n) + j] = (j == i) ? h : (T)0.5 * (h + H[(size_t)j * n + i]);
             }
-            is_diag = !any(nd);
-            sync(); // the upper elements are in place before their mirror images are averaged in
-            {
-                int i = 0, j = tid;
-                while (j >= n) { j -= n; i++; }
-                for (int idx = tid; idx < n * n; idx += NT) {
-                    if (j < i) { T* q = R + roff(j, n) + i; *q = (T)0.5 * (*q + H[idx]); }
-                    j += NT;
-                    while (j >= n) { j -= n; i++; }
-                }
-            }
-            sync();
+            is_diag = !any(nd); // (also orders the writes of R before the reads below)
             for (int i = lane; i < n; i += 32) hscale = fmax(hscale, fabs(R[roff(i, n) + i])); // every warp: the whole diagonal
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) hscale = fmax(hscale, __shfl_xor_sync(FULL, hscale, o));
