@@ -123,8 +123,9 @@ def solve(H, f, A, bupper, blower=None, sense=None, primal_start=None, dual_star
     leading entries are simple bounds (reference daqp.pyx:96-104)."""
     A = _f64(A)
     H = _f64(H); f = _f64(f); bupper = _f64(bupper)
-    mA, n = (A.shape if A is not None and A.size else (0, H.shape[0]))
     m = bupper.shape[0]
+    # (H = None with f = None is the LDP min |x|^2 s.t. the constraints; without general rows every bound is a simple one)
+    mA, n = (A.shape if A is not None and A.size else (0, H.shape[0] if H is not None else m))
     blower = np.full(m, -DAQP_INF) if blower is None else _f64(blower)
     sense = np.zeros(m, dtype=np.intc) if sense is None else np.ascontiguousarray(sense, dtype=np.intc)
     x = np.empty(n); lam = np.empty(m)
@@ -626,10 +627,10 @@ def quadprog_batch(problems: list[dict], **settings):
     qps = (DAQPProblem * N)(); res = (DAQPResult * N)()
     keep = []
     for i, pr in enumerate(problems):
-        H = _f64(pr["H"]); f = _f64(pr.get("f")); A = _f64(pr.get("A")); bu = _f64(pr["bupper"])
+        H = _f64(pr.get("H")); f = _f64(pr.get("f")); A = _f64(pr.get("A")); bu = _f64(pr["bupper"])
         m = bu.shape[0]
-        n = H.shape[0]
         mA = A.shape[0] if A is not None and A.size else 0
+        n = H.shape[0] if H is not None else (A.shape[1] if mA else m)  # H = None, f = None: the LDP min |x|^2
         bl = np.full(m, -DAQP_INF) if pr.get("blower") is None else _f64(pr["blower"])
         se = None if pr.get("sense") is None else np.ascontiguousarray(pr["sense"], dtype=np.intc)
         x = np.empty(n); lam = np.empty(m)

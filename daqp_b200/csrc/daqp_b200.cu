@@ -1591,7 +1591,12 @@ int run_group(Lane& L, const ShapeKey& k, const std::vector<int>& ids, typename 
     parallel_for(G, 256, [&](size_t g0, size_t g1) {
         for (size_t g = g0; g < g1; g++) {
             const auto& p = qps[ids[g]];
-            memcpy(H + g * n * n, p.H, sizeof(T) * n * n);
+            if (p.H) memcpy(H + g * n * n, p.H, sizeof(T) * n * n);
+            else { // H == NULL, f == NULL: the LDP min |x|^2 itself -- the identity Hessian gives the reference's iterates bit for bit
+                T* Hg = H + g * n * n;
+                memset(Hg, 0, sizeof(T) * n * n);
+                for (int d = 0; d < n; d++) Hg[(size_t)d * n + d] = (T)1;
+            }
             if (k.has_f) memcpy(f + g * n, p.f, sizeof(T) * n);
             if (mA > 0) memcpy(A + g * (size_t)mA * n, p.A, sizeof(T) * mA * n);
             if (m > 0) { memcpy(bu + g * m, p.bupper, sizeof(T) * m); memcpy(bl + g * m, p.blower, sizeof(T) * m); }
@@ -1633,7 +1638,8 @@ int quadprog_batch_impl(int N, typename Aos<T>::Problem* qps, typename Aos<T>::R
     for (int i = 0; i < N; i++) {
         const auto& q = qps[i];
         res[i].nodes = 1; res[i].soft_slack = 0; res[i].solve_time = 0; res[i].setup_time = 0;
-        const bool bad = q.H == nullptr || q.nh > 1 || q.problem_type != 0 || q.n < 1 || q.m < q.ms || q.ms > q.n ||
+        // (H == NULL with a linear term is an LP: the reference's proximal-point driver, out of scope)
+        const bool bad = (q.H == nullptr && q.f != nullptr) || q.nh > 1 || q.problem_type != 0 || q.n < 1 || q.m < q.ms || q.ms > q.n ||
                          (q.m > q.ms && q.A == nullptr) || (q.m > 0 && (q.bupper == nullptr || q.blower == nullptr));
         if (bad) { res[i].exitflag = DAQP_EXIT_UNSUPPORTED; res[i].iter = 0; continue; }
         if constexpr (sizeof(T) == sizeof(c_float)) { // binary constraints: the tree search, its node relaxations batched

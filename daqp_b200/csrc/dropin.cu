@@ -29,13 +29,25 @@ struct DropinHost {
     std::vector<c_float> x, lam;   // results of the last solve, [n] and [m]
     std::vector<int> ws;           // working set in factor order
     std::vector<unsigned char> sense8;
+    std::vector<c_float> eye;      // H == NULL, f == NULL (the LDP min |x|^2 itself): identity Hessian handed to the engine
 };
 
 DropinHost* host_of(DAQPWorkspace* w) { return static_cast<DropinHost*>(w->avi); }
 DAQPB200Workspace* dev_of(DAQPWorkspace* w) { return static_cast<DAQPB200Workspace*>(w->eq); }
 
+// the Hessian the engine gets: the caller's, or the identity for a pure LDP (same iterates as the reference's Rinv == NULL path)
+const c_float* hessian_of(DropinHost* hs, const DAQPProblem* qp) {
+    if (qp->H) return qp->H;
+    const size_t n = (size_t)qp->n;
+    if (hs->eye.size() != n * n) {
+        hs->eye.assign(n * n, 0);
+        for (size_t d = 0; d < n; d++) hs->eye[d * n + d] = 1;
+    }
+    return hs->eye.data();
+}
+
 bool in_scope(const DAQPProblem* qp) {
-    if (!qp || qp->H == nullptr || qp->nh > 1 || qp->problem_type != 0 || qp->n < 1 || qp->m < qp->ms || qp->ms > qp->n) return false;
+    if (!qp || (qp->H == nullptr && qp->f != nullptr) || qp->nh > 1 || qp->problem_type != 0 || qp->n < 1 || qp->m < qp->ms || qp->ms > qp->n) return false;
     if (qp->m > qp->ms && qp->A == nullptr) return false;
     if (qp->m > 0 && (qp->bupper == nullptr || qp->blower == nullptr)) return false;
     if (qp->sense)
@@ -68,7 +80,7 @@ int run_one_shot(DAQPWorkspace* w, DropinHost* hs) {
     DAQPB200Stats before{}, after{};
     daqp_b200_get_stats(nullptr, &before, 0);
     hs->fval = 0;
-    int rc = daqp_b200_solve_packed(nullptr, 1, n, m, qp->ms, qp->H, qp->f, qp->A, qp->bupper, qp->blower, qp->sense,
+    int rc = daqp_b200_solve_packed(nullptr, 1, n, m, qp->ms, hessian_of(hs, qp), qp->f, qp->A, qp->bupper, qp->blower, qp->sense,
                                     w->settings, hs->x.data(), hs->lam.data(), &hs->fval, &hs->exitflag, &hs->iter, &dg);
     if (rc) return DAQP_EXIT_UNSUPPORTED;
     daqp_b200_get_stats(nullptr, &after, 0);
@@ -152,7 +164,7 @@ extern "C" int setup_daqp_main(DAQPProblem* qp, DAQPWorkspace* work, c_float* se
         if (flag < 0 && hs->iter == 0) return fail_with(flag);
     } else {
         DAQPB200Workspace* dw = nullptr;
-        if (daqp_b200_workspace_setup(nullptr, 1, qp->n, qp->m, qp->ms, qp->H, qp->f, qp->A, qp->bupper, qp->blower, qp->sense,
+        if (daqp_b200_workspace_setup(nullptr, 1, qp->n, qp->m, qp->ms, hessian_of(hs, qp), qp->f, qp->A, qp->bupper, qp->blower, qp->sense,
                                       work->settings, &dw) != 0)
             return fail_with(DAQP_EXIT_UNSUPPORTED);
         work->eq = dw;
@@ -218,7 +230,7 @@ extern "C" int daqp_update_ldp(const int mask, DAQPWorkspace* work, DAQPProblem*
             alloc_iterates(work, qp->n, qp->m, ns);
             hs->ns = ns;
         }
-        if (daqp_b200_workspace_setup(nullptr, 1, qp->n, qp->m, qp->ms, qp->H, qp->f, qp->A, qp->bupper, qp->blower, qp->sense,
+        if (daqp_b200_workspace_setup(nullptr, 1, qp->n, qp->m, qp->ms, hessian_of(hs, qp), qp->f, qp->A, qp->bupper, qp->blower, qp->sense,
                                       work->settings, &dw) != 0)
             return DAQP_EXIT_UNSUPPORTED;
         work->eq = dw;

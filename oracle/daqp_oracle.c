@@ -658,6 +658,18 @@ void orc_quadprog(OrcResult *res, const OrcProblem *qp, const OrcSettings *setti
 
     if (qp->sense != NULL)
         for (int i = 0; i < m; i++) { if (qp->sense[i] & B_SOFT) ns++; if (qp->sense[i] & B_BINARY) nb++; }
+    if (qp->H == NULL && qp->f == NULL && nb == 0 && qp->nh <= 1 && qp->problem_type == 0 && n > 0) {
+        /* the LDP min |x|^2 itself (utils.c:103-110 leaves Rinv == NULL, M = A): the identity Hessian walks the same
+         * iterates bit for bit (unit Cholesky factor, products with 1.0) -- checked against the reference on the
+         * ldp_* fixtures, tests/test_oracle.py */
+        OrcProblem q2 = *qp;
+        orc_real *eye = (orc_real *)calloc((size_t)n * n, sizeof(orc_real));
+        for (int i = 0; i < n; i++) eye[(size_t)i * n + i] = 1;
+        q2.H = eye;
+        orc_quadprog(res, &q2, settings, trace);
+        free(eye);
+        return;
+    }
     if (nb > 0 || qp->nh > 1 || qp->problem_type != 0 || qp->H == NULL) { res->exitflag = EXIT_UNSUPPORTED; return; }
 
     w->n = n; w->m = m; w->ms = ms; w->cap = n + ns + 1; w->st = settings;

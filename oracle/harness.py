@@ -117,16 +117,17 @@ class RefLib:
         self.lib.setup_daqp_main.restype = C.c_int
         self.lib.daqp_solve.restype = None
 
-    def _problem(self, b, p, sense):
+    def _problem(self, b, p, sense, null_H=False):
         real = self.real
         mA = b.m - b.ms
-        return self.Problem(b.n, b.m, b.ms, _ptr(b.H[p], real), _ptr(b.f[p], real) if b.f is not None else None,
+        return self.Problem(b.n, b.m, b.ms, None if null_H else _ptr(b.H[p], real), _ptr(b.f[p], real) if b.f is not None else None,
                             _ptr(b.A[p], real) if mA > 0 else None, _ptr(b.bupper[p], real), _ptr(b.blower[p], real),
                             sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)
 
-    def solve(self, b, settings=None, use_sense: bool | None = None, want_ws: bool = False) -> Solution:
+    def solve(self, b, settings=None, use_sense: bool | None = None, want_ws: bool = False, null_H: bool = False) -> Solution:
         """One daqp_quadprog call per problem (api.c:62-79). want_ws drives the same calls through
-        setup_daqp_main + daqp_solve so that the final working set can be read from the workspace."""
+        setup_daqp_main + daqp_solve so that the final working set can be read from the workspace. null_H passes
+        H = NULL (with b.f = None: the LDP min |x|^2 over the constraints; b.H is then only a placeholder)."""
         import time
         N, n, m = b.N, b.n, b.m
         b = b.astype(self.dtype)
@@ -141,7 +142,7 @@ class RefLib:
         t0 = time.perf_counter()
         for p in range(N):
             sense = b.sense[p].copy() if use_sense else None
-            qp = self._problem(b, p, sense)
+            qp = self._problem(b, p, sense, null_H)
             res = self.Result(_ptr(x[p], self.real), _ptr(lam[p], self.real), 0, 0, 0, 0, 0, 0, 0)
             if not want_ws:
                 self.lib.daqp_quadprog(C.byref(res), C.byref(qp), sp)
@@ -262,7 +263,7 @@ class OracleLib:
         self.lib.orc_quadprog.restype = None
         self.lib.orc_solve_packed.restype = C.c_double
 
-    def solve(self, b, settings=None, use_sense: bool | None = None, log_cap: int = 0) -> Solution:
+    def solve(self, b, settings=None, use_sense: bool | None = None, log_cap: int = 0, null_H: bool = False) -> Solution:
         """log_cap > 0 also records up to that many (code, value) decisions per problem in Solution.oplog: 1 add
         (2*constraint + lower), 2 remove (constraint), 3 refactor, 4 refine, 5 cycle repair, 7 exit (flag)."""
         import time
@@ -285,7 +286,7 @@ class OracleLib:
         t0 = time.perf_counter()
         for p in range(N):
             sense = b.sense[p].copy() if use_sense else None
-            qp = self.Problem(n, m, b.ms, _ptr(b.H[p], real), _ptr(b.f[p], real) if b.f is not None else None,
+            qp = self.Problem(n, m, b.ms, None if null_H else _ptr(b.H[p], real), _ptr(b.f[p], real) if b.f is not None else None,
                               _ptr(b.A[p], real) if mA > 0 else None, _ptr(b.bupper[p], real),
                               _ptr(b.blower[p], real),
                               sense.ctypes.data_as(C.POINTER(C.c_int)) if sense is not None else None, None, 0, 0)

@@ -18,12 +18,26 @@ X_TOL, F_TOL, L_TOL = 1e-9, 1e-9, 1e-7
 def golden_names():
     """Single-solve fixtures (the wsseq_* files hold workspace sequences: see test_workspace_sequence_matches_reference)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_", "rare_", "bnb_"))]
+    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_", "rare_", "bnb_", "ldp_"))]
 
 
 def bnb_golden_names():
     """MIQPs with the reference's own branch-and-bound output (tests/golden/make_golden_bnb.py)."""
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "bnb_*.npz")))
+
+
+def ldp_golden_names():
+    """Pure LDP inputs (H == NULL, f == NULL) with the reference's own output (tests/golden/make_golden_ldp.py)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "ldp_*.npz")))
+
+
+def load_ldp_golden(name):
+    """-> (batch whose H is only an identity placeholder and whose f is None, file)"""
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, N = int(d["n"]), d["bupper"].shape[0]
+    b = QPBatch(n, int(d["m"]), int(d["ms"]), np.broadcast_to(np.eye(n), (N, n, n)).copy(), None, d["A"], d["bupper"],
+                d["blower"], d["sense"].astype(np.int32))
+    return b, d
 
 
 def rare_golden_names():

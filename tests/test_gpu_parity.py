@@ -6,8 +6,8 @@ final working sets and per-problem operation counts must be EQUAL.
 import numpy as np
 import pytest
 
-from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, load_golden, rare_golden_names,
-                    rare_settings, ws_sets)
+from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, ldp_golden_names, load_golden,
+                    load_ldp_golden, rare_golden_names, rare_settings, ws_sets)
 from daqp_b200.problems import generate_config, generate_g0, generate_g1, soften
 
 pytestmark = pytest.mark.gpu
@@ -572,6 +572,30 @@ def test_full_size_properties(engine):
     perm = np.random.default_rng(0).permutation(b.N)[:4000]
     sub = engine.solve_batch(b.H[perm], b.f[perm], b.A[perm], b.bupper[perm], b.blower[perm], None, ms=b.ms)
     np.testing.assert_array_equal(sub.x, r.x[perm])
+
+
+@pytest.mark.parametrize("name", ldp_golden_names())
+def test_pure_ldp_inputs_match_reference(cuda_lib, name):
+    """H == NULL, f == NULL through daqp_quadprog_batch / daqp_quadprog (the LDP min |x|^2 over the constraints, reference
+    utils.c:103-110; the form Julia's polyhedral tools use): exit flags (infeasible polyhedra included) and iteration
+    counts equal to the reference's, x / lam within the fp64 bar, fval untouched (the reference sets none without f)."""
+    import daqp_b200
+    b, d = load_ldp_golden(name)
+    use_sense = bool(d["use_sense"])
+    probs = [{"A": b.A[p], "bupper": b.bupper[p], "blower": b.blower[p], **({"sense": b.sense[p]} if use_sense else {})}
+             for p in range(b.N)]
+    out = daqp_b200.quadprog_batch(probs)
+    flag = np.array([o[2] for o in out]); it = np.array([o[3]["iterations"] for o in out])
+    np.testing.assert_array_equal(flag, d["exitflag"])
+    np.testing.assert_array_equal(it, d["iter"])
+    for p in np.nonzero(d["exitflag"] > 0)[0]:
+        np.testing.assert_allclose(out[p][0], d["x"][p], atol=1e-9 * (1 + np.abs(d["x"][p]).max()), err_msg=f"{name}[{p}] x")
+        np.testing.assert_allclose(out[p][3]["lam"], d["lam"][p], atol=1e-7 * (1 + np.abs(d["lam"][p]).max()), err_msg=f"{name}[{p}]")
+        assert out[p][1] == 0.0  # fval as handed in
+    x, fval, fl, info = daqp_b200.solve(None, None, b.A[0], b.bupper[0], b.blower[0], b.sense[0] if use_sense else None)
+    assert fl == d["exitflag"][0] and info["iterations"] == d["iter"][0]
+    # a linear term without a Hessian is an LP: the reference's proximal driver, flagged out of scope here
+    assert daqp_b200.quadprog_batch([{"f": np.ones(b.n), "A": b.A[0], "bupper": b.bupper[0], "blower": b.blower[0]}])[0][2] == -8
 
 
 @pytest.mark.parametrize("name", bnb_golden_names())

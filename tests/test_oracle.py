@@ -3,7 +3,8 @@
 import numpy as np
 import pytest
 
-from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, load_golden, rare_golden_names,
+from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, ldp_golden_names, load_golden,
+                    load_ldp_golden, rare_golden_names,
                     rare_settings, ws_sets)
 from daqp_b200.problems import generate_g0, generate_g1
 
@@ -183,6 +184,32 @@ def test_fp32_oracle_vs_live_fp32_reference(oracle_libs):
         np.testing.assert_array_equal(r.exitflag, o.exitflag)
         assert (r.iter == o.iter).mean() >= 0.9  # near-ties resolve differently under fast-math in fp32: a rate, not bit parity
         assert np.abs(r.x - o.x).max() <= 1e-4 * (1 + np.abs(r.x).max())
+
+
+@pytest.mark.parametrize("name", ldp_golden_names())
+def test_pure_ldp_oracle_matches_reference(oracle_libs, name):
+    """H == NULL, f == NULL (the LDP min |x|^2 itself, utils.c:103-110): the oracle -- which walks it with an identity
+    Hessian -- reproduces the reference's exit flags, iteration counts and working sets, x / lam to 1e-9 of the default
+    build's, and is BIT-identical to the live strict build (with H = NULL, and with H = I: the substitution is exact)."""
+    b, d = load_ldp_golden(name)
+    use_sense = bool(d["use_sense"])
+    o = oracle_libs.OracleLib().solve(b, use_sense=use_sense, null_H=True)
+    np.testing.assert_array_equal(o.exitflag, d["exitflag"])
+    np.testing.assert_array_equal(o.iter, d["iter"])
+    ok = d["exitflag"] > 0
+    assert ok.any()
+    np.testing.assert_allclose(o.x[ok], d["x"][ok], atol=1e-9)
+    np.testing.assert_allclose(o.lam[ok], d["lam"][ok], atol=1e-7)
+    for p in range(b.N):
+        assert list(o.ws[p]) == list(d["ws"][p, :d["n_active"][p]]), f"{name}[{p}]: working set"
+    if oracle_libs.have_ref("libdaqp_ref_strict.so"):
+        ref = oracle_libs.RefLib("libdaqp_ref_strict.so")
+        for null_H in (True, False):
+            r = ref.solve(b, use_sense=use_sense, null_H=null_H)
+            np.testing.assert_array_equal(r.exitflag, o.exitflag)
+            np.testing.assert_array_equal(r.iter, o.iter)
+            np.testing.assert_array_equal(r.x[ok], o.x[ok])
+            np.testing.assert_array_equal(r.lam[ok], o.lam[ok])
 
 
 @pytest.mark.parametrize("name", bnb_golden_names())
