@@ -703,9 +703,11 @@ extern "C" int daqp_b200_solve_device_f32(DAQPB200Handle* h, int N, int n, int m
 // ---- batched minimal representation (reference daqp_minrep: src/api.c:531-556, src/utils.c:808-835) ---------------
 // Device arrays in, device array out: P polyhedra x m constraints = P m LDPs, solved concurrently by the solve kernel in
 // shared-matrix mode (minrep_kernel.cuh). Chunked over polyhedra when the scratch limit asks for it.
+// (`single` switches to ONE raw LDP per polyhedron with the caller's lower bounds and sense bits: daqp_b200_ldp_batch)
+struct LdpSingle { const c_float* dbl; const int* dsense; c_float *dx, *dlam, *dfval; int *dnact, *dws; unsigned char* dsense_out; };
 static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA, const c_float* db,
                               const DAQPSettings* settings, int* dred, int* dflag_out, int* diter_out,
-                              cudaStream_t stream, const unsigned char* ddropped = nullptr) {
+                              cudaStream_t stream, const unsigned char* ddropped = nullptr, const LdpSingle* single = nullptr) {
     if (P <= 0 || m <= 0) return 0;
     if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid polyhedron dimensions"; return -2; }
     typedef c_float T;
@@ -722,7 +724,8 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
     const size_t ntri = (size_t)n * (n + 1) / 2;
     const size_t per_poly = ((size_t)n * ldm + (size_t)m * ldn + ldm + ntri) * sizeof(T) + 4 * 256;
     const size_t per_ldp = ((size_t)2 * ldm + n + 1) * sizeof(T) + ldm + 3 * sizeof(int);
-    const size_t per = per_poly + (size_t)m * per_ldp;
+    const int K = single ? 1 : m; // LDPs per polyhedron
+    const size_t per = per_poly + (size_t)K * per_ldp + (single ? (size_t)n * sizeof(T) : 0);
     int chunk = (int)std::min<long long>(P, std::max<long long>(1, (h->scratch_limit - (8 << 20)) / (long long)per));
     chunk = (int)std::min<long long>(chunk, (long long)(INT_MAX / 2) / m); // LDP indices are ints
     const int grid_max = h->num_sms;
@@ -734,7 +737,7 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
     const DevSettings<T> st = to_dev_settings<T>(settings);
     for (int q0 = 0; q0 < P; q0 += chunk) {
         const int Q = std::min(chunk, P - q0);
-        const size_t NL = (size_t)Q * m;
+        const size_t NL = (size_t)Q * K;
         Carver cv(h->arena);
         int* counters = cv.take<int>(64);
         MinrepArgs ma;
@@ -746,10 +749,11 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
         ma.dupper = cv.take<T>(NL * ldm); ma.dlower = cv.take<T>(NL * ldm);
         ma.sense = cv.take<unsigned char>(NL * ldm);
         ma.setup_flag = cv.take<int>(NL);
-        ma.exitflag = dflag_out ? dflag_out + (size_t)q0 * m : cv.take<int>(NL);
-        ma.iter = diter_out ? diter_out + (size_t)q0 * m : cv.take<int>(NL);
-        T* xs = cv.take<T>(NL * n);
-        T* fv = cv.take<T>(NL);
+        ma.exitflag = dflag_out ? dflag_out + (size_t)q0 * K : cv.take<int>(NL);
+        ma.iter = diter_out ? diter_out + (size_t)q0 * K : cv.take<int>(NL);
+        T* xs = (single && single->dx) ? single->dx + (size_t)q0 * n : cv.take<T>(NL * n);
+        T* fv = (single && single->dfval) ? single->dfval + q0 : cv.take<T>(NL);
+        T* vzero = single ? cv.take<T>((size_t)Q * n) : nullptr;
         int* pst_id = cv.take<int>((size_t)grid_max * 16 * cap);
         T* pst_lam = cv.take<T>((size_t)grid_max * 16 * cap);
 
@@ -758,15 +762,23 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
         if (rc) return rc;
         CK(cudaMemsetAsync(counters, 0, 64 * sizeof(int), stream));
         CK(cudaEventRecord(ev.e0, stream));
-        minrep_prep_kernel<<<std::min(Q, 8 * grid_max), 256, 0, stream>>>(ma);
+        if (single) ldp_prep_kernel<<<std::min(Q, 8 * grid_max), 256, 0, stream>>>(ma, single->dbl + (size_t)q0 * m,
+                                                                                 single->dsense ? single->dsense + (size_t)q0 * m : nullptr, vzero);
+        else minrep_prep_kernel<<<std::min(Q, 8 * grid_max), 256, 0, stream>>>(ma);
         CK(cudaGetLastError());
         h->stats.setup_launches++;
         CK(cudaEventRecord(ev.e1, stream));
 
-        la.P = (int)NL; la.grp = m;
-        la.Mt = ma.Mt; la.Mr = ma.Mr; la.Mt32 = nullptr; la.scaling = ma.scaling; la.Rinv = ma.Rinv; la.v = nullptr;
+        la.P = (int)NL; la.grp = K;
+        la.Mt = ma.Mt; la.Mr = ma.Mr; la.Mt32 = nullptr; la.scaling = ma.scaling; la.Rinv = ma.Rinv; la.v = vzero;
         la.dupper = ma.dupper; la.dlower = ma.dlower; la.sense = ma.sense; la.setup_flag = ma.setup_flag;
-        la.x = xs; la.lam = nullptr; la.fval = fv; la.exitflag = ma.exitflag; la.iter = ma.iter;
+        la.x = xs; la.lam = (single && single->dlam) ? single->dlam + (size_t)q0 * m : nullptr; la.fval = fv;
+        la.exitflag = ma.exitflag; la.iter = ma.iter;
+        if (single) {
+            la.nact_out = single->dnact ? single->dnact + q0 : nullptr;
+            la.ws_out = single->dws ? single->dws + (size_t)q0 * cap : nullptr;
+            la.sense_out = single->dsense_out ? single->dsense_out + (size_t)q0 * ldm : nullptr;
+        }
         la.work_counter = counters + 32; la.pst_id = pst_id; la.pst_lam = pst_lam; la.st = st;
         const int grid = (int)std::min<size_t>(grid_max, (NL + w_solve - 1) / w_solve);
         const size_t smem = smem_w * w_solve;
@@ -787,8 +799,10 @@ static int minrep_device_impl(DAQPB200Handle* h, int P, int n, int m, int ms, co
         }
         if (e != cudaSuccess) return fail("ldp_solve_kernel launch (minrep)", e, __LINE__);
         h->stats.solve_launches++;
-        minrep_finish_kernel<<<(int)std::min<size_t>(1024, (NL + 255) / 256), 256, 0, stream>>>(ma.exitflag, dred + (size_t)q0 * m, NL);
-        CK(cudaGetLastError());
+        if (!single) {
+            minrep_finish_kernel<<<(int)std::min<size_t>(1024, (NL + 255) / 256), 256, 0, stream>>>(ma.exitflag, dred + (size_t)q0 * m, NL);
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(ev.e2, stream));
         h->pending.push_back(ev);
         if (q0 + chunk < P) CK(cudaStreamSynchronize(stream)); // the next chunk reuses the scratch
@@ -804,6 +818,60 @@ extern "C" int daqp_b200_minrep_device(DAQPB200Handle* h, int P, int n, int m, i
     CK(cudaSetDevice(h->device));
     return minrep_device_impl(h, P, n, m, ms, dA, db, settings, dis_redundant, dexitflag, diter,
                               stream ? (cudaStream_t)stream : h->compute);
+}
+
+// ---- P raw LDPs in one call (batched form of daqp_ldp on hand-filled workspaces, api.jl:440-459) --------------------------
+extern "C" int daqp_b200_ldp_device(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA, const c_float* dbupper,
+                                    const c_float* dblower, const int* dsense, const DAQPSettings* settings, c_float* du,
+                                    c_float* dlam, c_float* dfval, int* dexitflag, int* diter, void* stream) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    LdpSingle sg{dblower, dsense, du, dlam, dfval, nullptr, nullptr, nullptr};
+    return minrep_device_impl(h, P, n, m, ms, dA, dbupper, settings, nullptr, dexitflag, diter,
+                              stream ? (cudaStream_t)stream : h->compute, nullptr, &sg);
+}
+
+extern "C" int daqp_b200_ldp_batch(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* A, const c_float* bupper,
+                                   const c_float* blower, const int* sense, const DAQPSettings* settings, c_float* u, c_float* lam,
+                                   c_float* fval, int* exitflag, int* iter, const DAQPB200Diag* diag) {
+    if (!h) { int rc = default_handle(&h); if (rc) return rc; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (P <= 0 || m <= 0) return 0;
+    if (n < 1 || m < ms || ms < 0 || ms > n) { g_last_error = "daqp_b200: invalid LDP dimensions"; return -2; }
+    const size_t mA = (size_t)(m - ms), nA = (size_t)P * mA * n, nb = (size_t)P * m, nx = (size_t)P * n;
+    const int ldm = round_up(m, 4), cap = n + 1;
+    int rc = ensure(&h->stage, &h->stage_bytes, (nA + 3 * nb + nx + P) * sizeof(c_float) + (nb + (size_t)P * (3 + cap)) * sizeof(int) +
+                                                    (size_t)P * ldm + 16 * 256);
+    if (rc) return rc;
+    Carver cv(h->stage);
+    int* dnact = cv.take<int>((size_t)P); int* dws = cv.take<int>((size_t)P * cap);
+    unsigned char* dso = cv.take<unsigned char>((size_t)P * ldm);
+    c_float* dA = cv.take<c_float>(nA); c_float* dbu = cv.take<c_float>(nb); c_float* dbl = cv.take<c_float>(nb);
+    c_float* dlam = cv.take<c_float>(nb); c_float* dx = cv.take<c_float>(nx); c_float* dfv = cv.take<c_float>((size_t)P);
+    int* dse = cv.take<int>(nb); int* dflag = cv.take<int>((size_t)P); int* dit = cv.take<int>((size_t)P);
+    cudaStream_t s = h->compute;
+    if (nA) CK(cudaMemcpyAsync(dA, A, nA * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dbu, bupper, nb * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dbl, blower, nb * sizeof(c_float), cudaMemcpyHostToDevice, s));
+    if (sense) CK(cudaMemcpyAsync(dse, sense, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(dfv, 0, (size_t)P * sizeof(c_float), s));
+    LdpSingle sg{dbl, sense ? dse : nullptr, dx, dlam, dfv, dnact, dws, dso};
+    rc = minrep_device_impl(h, P, n, m, ms, dA, dbu, settings, nullptr, dflag, dit, s, nullptr, &sg);
+    if (rc) return rc;
+    if (diag) { // working sets in factor order ([P][n + 1]), their sizes, final sense bytes ([P][ldm])
+        if (diag->n_active) CK(cudaMemcpyAsync(diag->n_active, dnact, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (diag->ws) CK(cudaMemcpyAsync(diag->ws, dws, (size_t)P * cap * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (diag->sense) CK(cudaMemcpyAsync(diag->sense, dso, (size_t)P * ldm, cudaMemcpyDeviceToHost, s));
+    }
+    if (u) CK(cudaMemcpyAsync(u, dx, nx * sizeof(c_float), cudaMemcpyDeviceToHost, s));
+    if (lam) CK(cudaMemcpyAsync(lam, dlam, nb * sizeof(c_float), cudaMemcpyDeviceToHost, s));
+    if (fval) CK(cudaMemcpyAsync(fval, dfv, (size_t)P * sizeof(c_float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(exitflag, dflag, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (iter) CK(cudaMemcpyAsync(iter, dit, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
 }
 
 // One round on host arrays: stage, run, copy back. `dropped` ([P][m] bytes) may be NULL.

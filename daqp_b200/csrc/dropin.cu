@@ -21,6 +21,8 @@ namespace {
 
 // host-side bookkeeping of one workspace (DAQPWorkspace::avi slot)
 struct DropinHost {
+    int raw = 0;             // allocate_daqp_workspace: the caller fills M / dupper / dlower / sense himself (daqp_ldp)
+    int cold_next = 0;       // reset_daqp_workspace was called: the next solve starts from an empty working set
     int one_shot = 0;        // init_mask carried DAQP_UPDATE_unconstrained: setup + solve are one daqp_quadprog call
     int ns = 0;              // soft constraints of the problem (sizes WS / lam like src/api.c:296-313)
     int have_result = 0;     // one-shot: the result computed at setup time is waiting for daqp_solve
@@ -202,7 +204,9 @@ extern "C" void daqp_solve(DAQPResult* res, DAQPWorkspace* work) { // src/api.c:
     daqp_b200_get_stats(nullptr, &before, 0);
     hs->fval = 0;
     // warm: continue from the factor and working set the previous solve left (what daqp_solve does on a kept workspace)
-    if (daqp_b200_workspace_solve(dw, 1, hs->x.data(), hs->lam.data(), &hs->fval, &hs->exitflag, &hs->iter, &dg) != 0) {
+    const int warm = hs->cold_next ? 0 : 1;
+    hs->cold_next = 0;
+    if (daqp_b200_workspace_solve(dw, warm, hs->x.data(), hs->lam.data(), &hs->fval, &hs->exitflag, &hs->iter, &dg) != 0) {
         res->exitflag = DAQP_EXIT_UNSUPPORTED;
         return;
     }
@@ -242,6 +246,83 @@ extern "C" int daqp_update_ldp(const int mask, DAQPWorkspace* work, DAQPProblem*
     int flag = 0;
     if (daqp_b200_workspace_flags(dw, &flag) != 0) return DAQP_EXIT_UNSUPPORTED;
     return flag < 0 ? flag : 0;
+}
+
+// ---- hand-filled workspaces and the pieces of daqp_solve -------------------------------------------------------------
+extern "C" void reset_daqp_workspace(DAQPWorkspace* work) { // src/daqp.c:142-146
+    work->sing_ind = -1; work->n_active = 0; work->reuse_ind = 0;
+    if (DropinHost* hs = host_of(work)) hs->cold_next = 1; // the device keeps the factor: tell the next solve not to use it
+}
+
+extern "C" void daqp_deactivate_constraints(DAQPWorkspace* work) { // src/auxiliary.c:482-488
+    if (!work->sense || !work->WS) return;
+    for (int i = 0; i < work->n_active; i++) {
+        const int id = work->WS[i];
+        if (id >= 0 && id < work->m && !(work->sense[id] & DAQP_IMMUTABLE)) work->sense[id] &= ~DAQP_ACTIVE;
+    }
+}
+
+extern "C" void allocate_daqp_workspace(DAQPWorkspace* work, int n, int ns) { // src/api.c:295-340
+    const int cap = n + ns + 1;
+    work->n = n;
+    work->Rinv = nullptr; work->RinvD = nullptr; work->v = nullptr; work->scaling = nullptr; work->Mu = nullptr;
+    work->lam = static_cast<c_float*>(calloc((size_t)cap, sizeof(c_float)));
+    work->lam_star = static_cast<c_float*>(calloc((size_t)cap, sizeof(c_float)));
+    work->WS = static_cast<int*>(calloc((size_t)cap, sizeof(int)));
+    work->x = static_cast<c_float*>(calloc((size_t)(n > 0 ? n : 1), sizeof(c_float)));
+    work->u = work->x; work->xold = nullptr;
+    work->L = nullptr; work->D = nullptr; work->xldl = nullptr; work->zldl = nullptr; // the factor lives on the device
+    work->prox_mask = nullptr; work->n_prox = 0;
+    work->bnb = nullptr; work->nh = 1; work->break_points = nullptr; work->eq = nullptr; work->timer = nullptr;
+    work->fval = 0; work->soft_slack = 0; work->iterations = 0;
+    DropinHost* hs = new DropinHost();
+    hs->raw = 1; hs->ns = ns;
+    work->avi = hs;
+    reset_daqp_workspace(work);
+    hs->cold_next = 0;
+}
+
+extern "C" int daqp_ldp(DAQPWorkspace* work) { // src/daqp.c:6-108
+    DropinHost* hs = host_of(work);
+    if (!hs) return DAQP_EXIT_UNSUPPORTED;
+    if (!hs->raw) { // a workspace from setup_daqp: the solve inside daqp_solve (work->x then holds the QP-space solution)
+        std::vector<c_float> x((size_t)(work->n > 0 ? work->n : 1)), lam((size_t)(work->m > 0 ? work->m : 1));
+        DAQPResult tmp{};
+        tmp.x = x.data(); tmp.lam = lam.data();
+        daqp_solve(&tmp, work);
+        return tmp.exitflag;
+    }
+    const int n = work->n, m = work->m, ms = work->ms, cap = n + 1, ldm = (m + 3) / 4 * 4;
+    if (n < 1 || m < 1 || ms < 0 || ms > n || m < ms || work->Rinv || work->RinvD || hs->ns > 0 || (m > ms && !work->M) || !work->dupper ||
+        !work->dlower)
+        return DAQP_EXIT_UNSUPPORTED;
+    hs->lam.assign((size_t)m, 0); hs->ws.assign((size_t)cap, 0); hs->sense8.assign((size_t)ldm, 0);
+    int nact = 0, flag = DAQP_EXIT_UNSUPPORTED, iter = 0;
+    c_float fv = 0;
+    DAQPB200Diag dg{};
+    dg.n_active = &nact; dg.ws = hs->ws.data(); dg.sense = hs->sense8.data();
+    if (daqp_b200_ldp_batch(nullptr, 1, n, m, ms, work->M, work->dupper, work->dlower, work->sense, work->settings, work->u,
+                            hs->lam.data(), &fv, &flag, &iter, &dg) != 0)
+        return DAQP_EXIT_UNSUPPORTED;
+    work->iterations = iter; work->n_active = nact; work->sing_ind = -1; work->reuse_ind = nact;
+    for (int i = 0; i < nact && i < cap; i++) { work->WS[i] = hs->ws[i]; work->lam_star[i] = hs->lam[hs->ws[i]]; work->lam[i] = work->lam_star[i]; }
+    if (work->sense) for (int i = 0; i < m; i++) work->sense[i] = hs->sense8[i];
+    if (flag > 0) work->fval = 2 * fv; // |u|^2 (daqp.c keeps the squared norm, auxiliary.c:85-87)
+    hs->exitflag = flag; hs->iter = iter; hs->fval = 0; hs->soft_slack = 0;
+    return flag;
+}
+
+extern "C" void daqp_extract_result(DAQPResult* res, DAQPWorkspace* work) { // src/api.c:455-495
+    DropinHost* hs = host_of(work);
+    for (int i = 0; i < work->n; i++) res->x[i] = work->x[i];
+    if (res->lam) {
+        for (int i = 0; i < work->m; i++) res->lam[i] = 0;
+        for (int i = 0; i < work->n_active; i++) res->lam[work->WS[i]] = work->lam_star[i];
+    }
+    if (hs && !hs->raw && work->qp && work->qp->f) res->fval = hs->fval; // (no linear term: fval is left as it is)
+    res->soft_slack = work->soft_slack;
+    res->iter = work->iterations;
+    res->nodes = 1;
 }
 
 extern "C" void daqp_set_primal_start(DAQPWorkspace* work, c_float* x) { // src/api.c:636-641

@@ -87,6 +87,50 @@ __global__ void __launch_bounds__(256) minrep_prep_kernel(const MinrepArgs a) {
     }
 }
 
+// ---- raw LDPs, one per polyhedron: what daqp_ldp runs on a hand-filled workspace (interfaces/daqp-julia/src/api.jl:
+// 440-459 -- M = A as given, no normalisation, Rinv == NULL, v == NULL). Same matrix layouts as above, then ONE problem
+// per polyhedron with the caller's bounds and sense bits; rows with the ACTIVE bit are activated first (a13). Soft and
+// binary bits are not part of this form: flagged -8.
+__global__ void __launch_bounds__(256) ldp_prep_kernel(const MinrepArgs a, const double* bl, const int* sense_in, double* vzero) {
+    const int n = a.n, m = a.m, ms = a.ms, mA = m - ms, ldm = a.ldm, ldn = a.ldn, ntri = n * (n + 1) / 2;
+    __shared__ int bad;
+    for (int q = blockIdx.x; q < a.P; q += gridDim.x) {
+        const double* A = a.A + (size_t)q * mA * n;
+        double* Mr = a.Mr + (size_t)q * m * ldn;
+        double* Mt = a.Mt + (size_t)q * n * ldm;
+        double* sc = a.scaling + (size_t)q * ldm;
+        double* Ri = a.Rinv + (size_t)q * ntri;
+        if (threadIdx.x == 0) bad = 0;
+        for (int idx = threadIdx.x; idx < m * ldn; idx += blockDim.x) {
+            const int r = idx / ldn, c = idx - r * ldn;
+            Mr[idx] = (c >= n) ? 0.0 : (r < ms ? (c == r ? 1.0 : 0.0) : A[(size_t)(r - ms) * n + c]);
+        }
+        for (int idx = threadIdx.x; idx < n * ldm; idx += blockDim.x) {
+            const int c = idx / ldm, r = idx - c * ldm;
+            Mt[idx] = (r >= m) ? 0.0 : (r < ms ? (c == r ? 1.0 : 0.0) : A[(size_t)(r - ms) * n + c]);
+        }
+        for (int idx = threadIdx.x; idx < ntri; idx += blockDim.x) Ri[idx] = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) vzero[(size_t)q * n + i] = 0.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) Ri[roff(i, n) + i] = 1.0;
+        for (int r = threadIdx.x; r < ldm; r += blockDim.x) {
+            sc[r] = 1.0;
+            const int sb = (r < m && sense_in) ? sense_in[(size_t)q * m + r] : 0;
+            if (sb & (B_SOFT | B_BINARY | ~63)) bad = 1;
+            a.dupper[(size_t)q * ldm + r] = r < m ? a.b[(size_t)q * m + r] : 0.0;
+            a.dlower[(size_t)q * ldm + r] = r < m ? bl[(size_t)q * m + r] : 0.0;
+            a.sense[(size_t)q * ldm + r] = (unsigned char)(sb & 63);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            a.setup_flag[q] = bad ? EXIT_UNSUPPORTED : SETUP_SOLVE_ACTIVATE;
+            a.exitflag[q] = bad ? EXIT_UNSUPPORTED : 0;
+            a.iter[q] = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // is_redundant = 1 iff the LDP ended DAQP_EXIT_INFEASIBLE (utils.c:821-824); anything else is 0 (utils.c:825-831)
 __global__ void minrep_finish_kernel(const int* exitflag, int* is_redundant, size_t count) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)

@@ -171,6 +171,17 @@ void allocate_daqp_settings(DAQPWorkspace* work);
 void free_daqp_workspace(DAQPWorkspace* work);
 void free_daqp_ldp(DAQPWorkspace* work);
 void daqp_set_primal_start(DAQPWorkspace* work, c_float* x);
+/* hand-filled workspaces (Julia: api.jl:428-459) and the pieces of daqp_solve the interfaces call one by one:
+ * allocate_daqp_workspace (src/api.c:295-340: host iterates only -- the factor lives on the device), daqp_ldp
+ * (src/daqp.c:6-108: on a workspace from setup_daqp the solve of daqp_solve; on a hand-filled one -- M, dupper, dlower,
+ * sense, m, ms set by the caller, Rinv == NULL -- a batch of one through daqp_b200_ldp_batch; work->u, lam_star, WS,
+ * n_active, fval, iterations, sense are filled in), reset_daqp_workspace + daqp_deactivate_constraints (src/daqp.c:142-146,
+ * src/auxiliary.c:482-488: the next solve starts cold), daqp_extract_result (src/api.c:455-495). */
+void allocate_daqp_workspace(DAQPWorkspace* work, int n, int ns);
+int daqp_ldp(DAQPWorkspace* work);
+void reset_daqp_workspace(DAQPWorkspace* work);
+void daqp_deactivate_constraints(DAQPWorkspace* work);
+void daqp_extract_result(DAQPResult* res, DAQPWorkspace* work);
 /* reference include/api.h:55 (src/api.c:562-574): index of the first constraint x violates by more than tol, or m */
 int daqp_first_violating(c_float* x, c_float* A, c_float* bu, c_float* bl, int n, int m, int ms, c_float tol);
 
@@ -346,6 +357,22 @@ int daqp_b200_first_violating_batch(DAQPB200Handle* h, int N, int n, int m, int 
  * res->iter count this walk (waves of the deepest open nodes, not strict depth first); res->lam holds the incumbent's
  * multipliers. daqp_quadprog / daqp_quadprog_batch route problems with binary constraints here. */
 int daqp_b200_bnb(DAQPB200Handle* h, const DAQPProblem* qp, const DAQPSettings* settings, DAQPResult* res, int wave_width);
+
+/* ---- raw LDPs (batched LDP consumer) -----------------------------------------------------------------------------------
+ * P problems  min |u|^2  s.t.  blower <= [I(ms); A] u <= bupper  solved as they stand: M = A as given (NO normalisation,
+ * scaling == NULL), Rinv == NULL, v == NULL -- what the reference's daqp_ldp (include/daqp.h, src/daqp.c:6-108) runs on a
+ * workspace whose LDP fields the caller filled in himself, the way Julia's polyhedral tools test feasibility
+ * (interfaces/daqp-julia/src/api.jl:428-459; settings->fval_bound = their max_radius). A[P][m-ms][n], bupper / blower
+ * [P][m], sense[P][m] or NULL (ACTIVE rows are activated first; SOFT / BINARY bits: -8). Outputs: u[P][n], lam[P][m]
+ * (scattered like DAQPResult.lam), fval[P] = |u|^2 / 2, exitflag[P], iter[P]; any of u / lam / fval / iter may be NULL.
+ * diag (optional): n_active[P], ws[P][n+1] in factor order, sense[P][ldm]. */
+int daqp_b200_ldp_batch(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* A, const c_float* bupper,
+                        const c_float* blower, const int* sense, const DAQPSettings* settings, c_float* u, c_float* lam,
+                        c_float* fval, int* exitflag, int* iter, const DAQPB200Diag* diag);
+/* the same on device arrays, asynchronous on `stream` (NULL = the engine's own) */
+int daqp_b200_ldp_device(DAQPB200Handle* h, int P, int n, int m, int ms, const c_float* dA, const c_float* dbupper,
+                         const c_float* dblower, const int* dsense, const DAQPSettings* settings, c_float* du, c_float* dlam,
+                         c_float* dfval, int* dexitflag, int* diter, void* stream);
 
 /* ---- minimal representation of polyhedra (batched LDP consumer) ---------------------------------------------
  * reference include/api.h:54 (src/api.c:531-556, src/utils.c:808-835): is_redundant[i] = 1 iff constraint i of

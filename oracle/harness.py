@@ -168,6 +168,37 @@ class RefLib:
         return Solution(x, lam, fval, flag, it, ws, sense_out, None, time.perf_counter() - t0, slack)
 
 
+def raw_ldp(lib, A, bupper, blower, sense=None, ms=0, fval_bound=None):
+    """daqp_ldp on a HAND-FILLED workspace, the way interfaces/daqp-julia/src/api.jl:428-459 does it: calloc a
+    DAQPWorkspace, allocate_daqp_workspace(n, 0) + allocate_daqp_settings, store the caller's M = A (row-major [m-ms][n],
+    NOT normalised), dupper, dlower, sense, m, ms in the struct, call daqp_ldp, read the struct back. `lib` is any CDLL
+    that exports those symbols (the reference, or the library under test). Returns a dict."""
+    _, Settings, _, Workspace, _ = _F64
+    A = np.ascontiguousarray(A, np.float64); bu = np.ascontiguousarray(bupper, np.float64)
+    bl = np.ascontiguousarray(blower, np.float64)
+    m = bu.shape[0]; n = A.shape[1]
+    se = np.zeros(m, np.int32) if sense is None else np.ascontiguousarray(sense, np.int32).copy()
+    lib.daqp_ldp.restype = C.c_int
+    for f in ("allocate_daqp_workspace", "allocate_daqp_settings", "free_daqp_workspace"):
+        getattr(lib, f).restype = None
+    work = Workspace()
+    lib.allocate_daqp_workspace(C.byref(work), C.c_int(n), C.c_int(0))
+    lib.allocate_daqp_settings(C.byref(work))
+    if fval_bound is not None:
+        C.cast(work.settings, C.POINTER(Settings)).contents.fval_bound = fval_bound
+    work.M = _ptr(A, C.c_double) if A.size else None
+    work.dupper = _ptr(bu, C.c_double); work.dlower = _ptr(bl, C.c_double)
+    work.sense = se.ctypes.data_as(C.POINTER(C.c_int))
+    work.m = m; work.ms = ms
+    flag = lib.daqp_ldp(C.byref(work))
+    k = work.n_active
+    out = {"exitflag": int(flag), "iter": int(work.iterations), "u": np.array([work.u[i] for i in range(n)]),
+           "ws": [int(work.WS[i]) for i in range(k)], "lam_star": np.array([work.lam_star[i] for i in range(k)]),
+           "fval": float(work.fval), "sense": se.copy()}
+    lib.free_daqp_workspace(C.byref(work))
+    return out
+
+
 def ref_solve_sequence(reflib, b, steps, settings=None, use_sense=None):
     """The reference's workspace flow on every problem of the batch: setup_daqp() + daqp_solve(), then per step
     daqp_update_ldp(DAQP_UPDATE_v + DAQP_UPDATE_d) with new (f, bupper, blower) + daqp_solve() on the KEPT workspace

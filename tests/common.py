@@ -18,12 +18,17 @@ X_TOL, F_TOL, L_TOL = 1e-9, 1e-9, 1e-7
 def golden_names():
     """Single-solve fixtures (the wsseq_* files hold workspace sequences: see test_workspace_sequence_matches_reference)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_", "rare_", "bnb_", "ldp_"))]
+    return [n for n in names if not n.startswith(("wsseq_", "wsshared_", "minrep_", "warmstart_", "rare_", "bnb_", "ldp_", "rawldp_"))]
 
 
 def bnb_golden_names():
     """MIQPs with the reference's own branch-and-bound output (tests/golden/make_golden_bnb.py)."""
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "bnb_*.npz")))
+
+
+def rawldp_golden_names():
+    """daqp_ldp on hand-filled workspaces (no normalisation), the reference's own output (make_golden_ldp.py)."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "rawldp_*.npz")))
 
 
 def ldp_golden_names():

@@ -75,5 +75,46 @@ def main():
               f"iters {sol.iter[keep].min()}..{sol.iter[keep].max()}")
 
 
+def raw_cases():
+    """daqp_ldp on hand-filled workspaces (no normalisation: the rows keep their norms, spread over two decades on
+    purpose so that a normalising implementation would take another path), with simple bounds, infeasible polyhedra and a
+    max-radius bound (settings.fval_bound, api.jl:441-445)."""
+    out = {}
+    for name, (N, n, m, ms, seed, fvb) in {"rawldp_n8_m24": (20, 8, 24, 0, 911, None), "rawldp_n12_m36_ms4": (20, 12, 36, 4, 912, None),
+                                           "rawldp_n30_m90_radius": (12, 30, 90, 0, 913, 5.5), "rawldp_n70_m160": (6, 70, 160, 0, 914, None)}.items():
+        b = make(N, n, m, ms, seed, shift=0.7, infeasible_every=5)
+        rng = np.random.Generator(np.random.Philox(key=seed + 50))
+        scale = 10.0 ** rng.uniform(-1, 1, (N, m - ms))
+        b.A *= scale[:, :, None]; b.bupper[:, ms:] *= scale
+        fin = b.blower[:, ms:] > -1e29
+        b.blower[:, ms:][fin] = (b.blower[:, ms:] * scale)[fin]
+        out[name] = (b, fvb)
+    return out
+
+
+def main_raw():
+    import ctypes as C
+    libs = [C.CDLL(os.path.join(harness.REF_DIR, nm)) for nm in ("libdaqp_ref.so", "libdaqp_ref_strict.so")]
+    for name, (b, fvb) in raw_cases().items():
+        rows = []
+        for p in range(b.N):
+            r = [harness.raw_ldp(L, b.A[p], b.bupper[p], b.blower[p], None, b.ms, fvb) for L in libs]
+            if r[0]["exitflag"] == r[1]["exitflag"] and r[0]["iter"] == r[1]["iter"] and r[0]["ws"] == r[1]["ws"]:
+                rows.append((p, r[0]))
+        keep = [p for p, _ in rows]
+        ws = np.full((len(rows), b.n + 1), -1, np.int32)
+        for q, (_, r) in enumerate(rows):
+            ws[q, :len(r["ws"])] = r["ws"]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), n=b.n, m=b.m, ms=b.ms, A=b.A[keep], bupper=b.bupper[keep],
+                            blower=b.blower[keep], fval_bound=-1.0 if fvb is None else fvb,
+                            exitflag=np.array([r["exitflag"] for _, r in rows], np.int32),
+                            iter=np.array([r["iter"] for _, r in rows], np.int32), u=np.array([r["u"] for _, r in rows]),
+                            fval=np.array([r["fval"] for _, r in rows]), ws=ws,
+                            n_active=np.array([len(r["ws"]) for _, r in rows], np.int32))
+        fl = np.array([r["exitflag"] for _, r in rows])
+        print(f"{name:24s} N={len(rows)} (dropped {b.N - len(rows)}) flags={dict(zip(*[v.tolist() for v in np.unique(fl, return_counts=True)]))}")
+
+
 if __name__ == "__main__":
     main()
+    main_raw()

@@ -6,8 +6,8 @@ final working sets and per-problem operation counts must be EQUAL.
 import numpy as np
 import pytest
 
-from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, ldp_golden_names, load_golden,
-                    load_ldp_golden, rare_golden_names, rare_settings, ws_sets)
+from common import (GOLDEN_DIR, RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, ldp_golden_names,
+                    load_golden, load_ldp_golden, rare_golden_names, rare_settings, rawldp_golden_names, ws_sets)
 from daqp_b200.problems import generate_config, generate_g0, generate_g1, soften
 
 pytestmark = pytest.mark.gpu
@@ -596,6 +596,47 @@ def test_pure_ldp_inputs_match_reference(cuda_lib, name):
     assert fl == d["exitflag"][0] and info["iterations"] == d["iter"][0]
     # a linear term without a Hessian is an LP: the reference's proximal driver, flagged out of scope here
     assert daqp_b200.quadprog_batch([{"f": np.ones(b.n), "A": b.A[0], "bupper": b.bupper[0], "blower": b.blower[0]}])[0][2] == -8
+
+
+@pytest.mark.parametrize("name", rawldp_golden_names())
+def test_raw_ldp_batch_and_hand_filled_workspace(cuda_lib, name):
+    """Raw LDPs (M = A as given, no normalisation, Rinv == NULL): (1) daqp_b200_ldp_batch, all polyhedra of the fixture in one
+    call, (2) the reference's own flow on a hand-filled DAQPWorkspace -- allocate_daqp_workspace, allocate_daqp_settings,
+    fields stored by the caller, daqp_ldp, free_daqp_workspace (interfaces/daqp-julia/src/api.jl:428-459) -- one polyhedron
+    at a time. Exit flags (the max-radius bound included), iteration counts and working sets in factor order equal to the
+    reference's; u within 1e-9, fval = |u|^2."""
+    import ctypes as C
+    import os
+    import daqp_b200 as dq
+    from oracle import harness
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, m, ms, P = int(d["n"]), int(d["m"]), int(d["ms"]), d["exitflag"].shape[0]
+    fvb = None if d["fval_bound"] < 0 else float(d["fval_bound"])
+    L = dq.lib()
+    L.daqp_b200_ldp_batch.restype = C.c_int
+    A = np.ascontiguousarray(d["A"]); bu = np.ascontiguousarray(d["bupper"]); bl = np.ascontiguousarray(d["blower"])
+    u = np.zeros((P, n)); lam = np.zeros((P, m)); fv = np.zeros(P); flag = np.zeros(P, np.intc); it = np.zeros(P, np.intc)
+    nact = np.zeros(P, np.intc); ws = np.zeros((P, n + 1), np.intc)
+    dg = dq.DAQPB200Diag(nact.ctypes.data_as(C.POINTER(C.c_int)), ws.ctypes.data_as(C.POINTER(C.c_int)), None, None, None)
+    st = dq.default_settings(**({"fval_bound": fvb} if fvb is not None else {}))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    assert L.daqp_b200_ldp_batch(None, P, n, m, ms, dp(A), dp(bu), dp(bl), None, C.byref(st), dp(u), dp(lam), dp(fv), ip(flag),
+                                 ip(it), C.byref(dg)) == 0, L.daqp_b200_last_error().decode()
+    np.testing.assert_array_equal(flag, d["exitflag"])
+    np.testing.assert_array_equal(it, d["iter"])
+    for p in range(P):
+        assert ws[p, :nact[p]].tolist() == d["ws"][p, :d["n_active"][p]].tolist(), f"{name}[{p}]: working set"
+    ok = d["exitflag"] > 0
+    np.testing.assert_allclose(u[ok], d["u"][ok], atol=1e-9 * (1 + np.abs(d["u"][ok]).max()))
+    np.testing.assert_allclose(2 * fv[ok], d["fval"][ok], rtol=1e-9)
+    for p in range(min(P, 6)):
+        r = harness.raw_ldp(L, A[p], bu[p], bl[p], None, ms, fvb)
+        assert r["exitflag"] == d["exitflag"][p] and r["iter"] == d["iter"][p], f"{name}[{p}] via daqp_ldp"
+        assert r["ws"] == d["ws"][p, :d["n_active"][p]].tolist()
+        if r["exitflag"] > 0:
+            np.testing.assert_allclose(r["u"], d["u"][p], atol=1e-9 * (1 + np.abs(d["u"][p]).max()))
+            assert abs(r["fval"] - d["fval"][p]) <= 1e-9 * (1 + d["fval"][p])
 
 
 @pytest.mark.parametrize("name", bnb_golden_names())

@@ -3,9 +3,8 @@
 import numpy as np
 import pytest
 
-from common import (RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, ldp_golden_names, load_golden,
-                    load_ldp_golden, rare_golden_names,
-                    rare_settings, ws_sets)
+from common import (GOLDEN_DIR, RARE_MUST_HIT, assert_parity, bnb_golden_names, golden_names, kkt_residuals, ldp_golden_names,
+                    load_golden, load_ldp_golden, rare_golden_names, rare_settings, rawldp_golden_names, ws_sets)
 from daqp_b200.problems import generate_g0, generate_g1
 
 
@@ -210,6 +209,30 @@ def test_pure_ldp_oracle_matches_reference(oracle_libs, name):
             np.testing.assert_array_equal(r.iter, o.iter)
             np.testing.assert_array_equal(r.x[ok], o.x[ok])
             np.testing.assert_array_equal(r.lam[ok], o.lam[ok])
+
+
+@pytest.mark.parametrize("name", rawldp_golden_names())
+def test_raw_ldp_fixtures_are_what_the_reference_gives(oracle_libs, name):
+    """daqp_ldp on hand-filled workspaces (api.jl:428-459): where the reference is compiled here, its live output equals
+    the file; every optimal u satisfies the polyhedron it was projected onto, and the radius fixture has both outcomes."""
+    import ctypes as C
+    import os
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, m, ms = int(d["n"]), int(d["m"]), int(d["ms"])
+    fvb = None if d["fval_bound"] < 0 else float(d["fval_bound"])
+    assert (d["exitflag"] == 1).any() and (d["exitflag"] == -1).any()
+    for p in np.nonzero(d["exitflag"] == 1)[0]:
+        Ax = np.concatenate([d["u"][p, :ms], d["A"][p] @ d["u"][p]])
+        scale = np.concatenate([np.ones(ms), np.linalg.norm(d["A"][p], axis=1)])
+        assert (Ax <= d["bupper"][p] + 1e-5 * scale).all() and (Ax >= d["blower"][p] - 1e-5 * scale).all()
+        assert abs(d["fval"][p] - d["u"][p] @ d["u"][p]) < 1e-9 * (1 + d["fval"][p])
+    if oracle_libs.have_ref():
+        L = C.CDLL(os.path.join(oracle_libs.REF_DIR, "libdaqp_ref.so"))
+        for p in range(d["exitflag"].shape[0]):
+            r = oracle_libs.raw_ldp(L, d["A"][p], d["bupper"][p], d["blower"][p], None, ms, fvb)
+            assert r["exitflag"] == d["exitflag"][p] and r["iter"] == d["iter"][p]
+            assert r["ws"] == list(d["ws"][p, :d["n_active"][p]])
+            np.testing.assert_array_equal(r["u"], d["u"][p])
 
 
 @pytest.mark.parametrize("name", bnb_golden_names())
