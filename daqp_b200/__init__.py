@@ -619,6 +619,28 @@ def minrep_batch(A, b, **kw):
     return _default_engine.minrep_batch(A, b, **kw)
 
 
+def ldp_batch(A, bupper, blower=None, sense=None, **settings) -> BatchResult:
+    """P raw LDPs  min |u|^2  s.t.  blower <= [I(ms); A] u <= bupper  in one call (``daqp_b200_ldp_batch``): A[P, m-ms, n]
+    as given (no normalisation), bupper / blower [P, m] (ms = m - A.shape[1] leading simple bounds), sense [P, m] or None.
+    The batched form of the feasibility checks Julia's polyhedral tools run through ``daqp_ldp`` on a hand-filled
+    workspace (api.jl:428-459): ``exitflag`` 1 = non-empty (``x`` = its point of least norm), -1 = empty or outside the
+    radius ``fval_bound``. ``fval`` = |u|^2 / 2; ``ws`` / ``n_active`` = working sets in factor order."""
+    A = _f64(A); bupper = _f64(bupper)
+    P, m = bupper.shape
+    mA, n = A.shape[1], A.shape[2]
+    blower = np.full((P, m), -DAQP_INF) if blower is None else _f64(blower)
+    se = None if sense is None else np.ascontiguousarray(sense, dtype=np.intc)
+    r = BatchResult(x=np.zeros((P, n)), lam=np.zeros((P, m)), fval=np.zeros(P), exitflag=np.empty(P, np.intc),
+                    iter=np.empty(P, np.intc), n_active=np.zeros(P, np.intc), ws=np.zeros((P, n + 1), np.intc))
+    d = DAQPB200Diag(_p(r.n_active, _ip), _p(r.ws, _ip), None, None, None)
+    st = default_settings(**settings)
+    L = lib()
+    L.daqp_b200_ldp_batch.restype = C.c_int
+    _check(L.daqp_b200_ldp_batch(None, P, n, m, m - mA, _p(A) if A.size else None, _p(bupper), _p(blower), _p(se, _ip),
+                                 C.byref(st), _p(r.x), _p(r.lam), _p(r.fval), _p(r.exitflag, _ip), _p(r.iter, _ip), C.byref(d)))
+    return r
+
+
 def quadprog_batch(problems: list[dict], **settings):
     """Array-of-struct batch through ``daqp_quadprog_batch``: a list of dicts with keys H, f, A, bupper, blower,
     sense (the last three optional as in ``solve``); problems may differ in size. Returns a list of

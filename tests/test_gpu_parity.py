@@ -630,6 +630,9 @@ def test_raw_ldp_batch_and_hand_filled_workspace(cuda_lib, name):
     ok = d["exitflag"] > 0
     np.testing.assert_allclose(u[ok], d["u"][ok], atol=1e-9 * (1 + np.abs(d["u"][ok]).max()))
     np.testing.assert_allclose(2 * fv[ok], d["fval"][ok], rtol=1e-9)
+    rb = dq.ldp_batch(A, bu, bl, **({"fval_bound": fvb} if fvb is not None else {}))  # the Python wrapper of the same call
+    np.testing.assert_array_equal(rb.exitflag, flag); np.testing.assert_array_equal(rb.iter, it)
+    np.testing.assert_array_equal(rb.x, u)
     for p in range(min(P, 6)):
         r = harness.raw_ldp(L, A[p], bu[p], bl[p], None, ms, fvb)
         assert r["exitflag"] == d["exitflag"][p] and r["iter"] == d["iter"][p], f"{name}[{p}] via daqp_ldp"
