@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(TW > 1 ? 32 * TW : 32 * FACTOR_MAX_WARPS, 1) q
                 if (j > i && (h > st.zero_tol || h < -st.zero_tol)) nd = 1;
                 if (j >= i) R[roff(i, n) + j] = (j == i) ? h : (T)0.5 * (h + H[(size_t)j * n + i]);
             }
-            is_diag = !any(nd); // (also orders the writes of R before the reads below)
+            is_diag = !any(nd);
+            sync(); // the writes of R are ordered before the reads below (a vote alone is not a memory barrier)
             for (int i = lane; i < n; i += 32) hscale = fmax(hscale, fabs(R[roff(i, n) + i])); // every warp: the whole diagonal
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) hscale = fmax(hscale, __shfl_xor_sync(FULL, hscale, o));

@@ -50,7 +50,23 @@ constexpr int TEAM_GRAM_MIN = 8; // warm starts with fewer rows than this are ac
     extern __shared__ __align__(16) unsigned char smem_raw[];       \
     TeamBox* const box = reinterpret_cast<TeamBox*>(smem_raw)
 
-template <int TW> __device__ __forceinline__ void team_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TW) : "memory"); }
+// (bar.sync is an ALIGNED barrier: every lane of a warp must execute it together. The phases end in lane-predicated
+// stores -- `if (lane == 0) box->... = ...`, `if (mine) tmp[i] = x` -- after which the hardware does not promise
+// reconvergence, so the warp is converged explicitly first; compute-sanitizer's synccheck flags the barrier otherwise.)
+// Leader and helpers reach the barrier from DIFFERENT instructions (the leader inside a phase wrapper, the helpers in
+// their command loop). PTX identifies a barrier by its number, not by the instruction, so that is well defined; synccheck,
+// however, only accepts a barrier all threads of the block reach at the same address. -DDAQP_B200_SYNCCHECK makes the
+// barrier one out-of-line instruction for that tool (0 errors: profiles/sanitizer_r02.txt); the inlined form is 2-4 %
+// faster on C4 and is what ships.
+#ifdef DAQP_B200_SYNCCHECK
+#define TEAM_BAR_INLINE __noinline__
+#else
+#define TEAM_BAR_INLINE __forceinline__
+#endif
+template <int TW> __device__ TEAM_BAR_INLINE void team_bar() {
+    __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * TW) : "memory");
+}
 
 // loads that stay in program order (asm volatile): a batch of them is issued back to back before the first use
 __device__ __forceinline__ double ldg_ordered(const double* p) {
