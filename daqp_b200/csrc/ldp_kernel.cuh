@@ -1256,13 +1256,124 @@ struct Warp {
     }
 
     // ---- a13: warm start / equality activation (auxiliary.c:399-479)
+    // ---- a13 at once, single-warp form (see activate_constraints and team_ops.cuh: team_gram / team_ldl)
+    // g_ij = row(WS[i]) . row(WS[j]) for all j <= i < K: two rows i in registers, the rows j streamed past them four at a time
+    __device__ __forceinline__ void gram_rows(int K) {
+        constexpr int IB = 2, JB = 4;
+        const T* M = reinterpret_cast<const T*>(Mr()) + V * lane;
+        const int* ws = WS();
+        T* Lp = L();
+        T* Dp = D();
+        bool okg[NG];
+#pragma unroll
+        for (int g = 0; g < NG; g++) okg[g] = V * (lane + 32 * g) < a.ldn;
+        for (int i0 = 0; i0 < K; i0 += IB) {
+            const int jend = min(i0 + IB, K);
+            T mi[IB][NG][V];
+#pragma unroll
+            for (int r = 0; r < IB; r++) {
+                const T* row = M + (size_t)(unsigned)(ws[min(i0 + r, K - 1)] * a.ldn);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+#pragma unroll
+                    for (int e = 0; e < V; e++) mi[r][g][e] = 0;
+                    if (okg[g]) ldg_vec<T>(row + 32 * V * g, mi[r][g]);
+                }
+            }
+            for (int j0 = 0; j0 < jend; j0 += JB) {
+                T t[JB][NG][V];
+#pragma unroll
+                for (int rr = 0; rr < JB; rr++) {
+                    const T* row = M + (size_t)(unsigned)(ws[min(j0 + rr, K - 1)] * a.ldn);
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+#pragma unroll
+                        for (int e = 0; e < V; e++) t[rr][g][e] = 0;
+                        if (okg[g]) ldg_vec<T>(row + 32 * V * g, t[rr][g]);
+                    }
+                }
+                T pj[IB * JB];
+#pragma unroll
+                for (int r = 0; r < IB; r++)
+#pragma unroll
+                    for (int rr = 0; rr < JB; rr++) {
+                        T acc = 0;
+#pragma unroll
+                        for (int g = 0; g < NG; g++)
+#pragma unroll
+                            for (int e = 0; e < V; e++) acc += t[rr][g][e] * mi[r][g][e];
+                        pj[r * JB + rr] = acc;
+                    }
+                const T total = warp_sum_multi<IB * JB>(pj, lane);
+                const int idx = multi_index<IB * JB>(lane), i = i0 + idx / JB, j = j0 + idx % JB;
+                if ((lane & (32 / (IB * JB) - 1)) == 0 && i < K && j <= i) {
+                    if (j == i) Dp[i] = total; else Lp[loff(i) + j] = total;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // in-place right-looking LDL' of that Gram matrix; lane owns rows lane + 32 q. Returns K, or the index of the first row
+    // the row-by-row path treats specially (singular pivot, pivot swap). The published columns alternate between xldl and
+    // zldl, which hold nothing before the first CSP.
+    __device__ __forceinline__ int ldl_rows(int K) {
+        T* Lp = L();
+        T* Dp = D();
+        T acc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) acc[q] = 0;
+        int stop = uni((int)(Dp[0] < a.st.sing_tol)) ? 0 : K;
+        for (int j = 0; j + 1 < K && stop > j; j++) {
+            T* col = (j & 1) ? zl() : xl();
+            const T dj = Dp[j];
+            T x[NV];
+            int bad = 0;
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                x[q] = 0;
+                if (q > 0 && 32 * q >= K) break; // uniform: no rows in this register segment
+                const int i = lane + 32 * q;
+                const bool below = i > j && i < K;
+                if (below) x[q] = Lp[loff(i) + j];
+                const T l = fdiv(x[q], dj); // unconditional call: no divergence around the division
+                if (below) {
+                    acc[q] += x[q] * l;
+                    Lp[loff(i) + j] = l;
+                    col[i] = l;
+                    if (i == j + 1) {
+                        const T d = Dp[i] - acc[q];
+                        Dp[i] = d;
+                        bad = d < a.st.sing_tol || (dj < a.st.pivot_tol && dj < d);
+                    }
+                }
+            }
+            if (uni(bad)) stop = j + 1; // (uni = warp-wide max; it also orders the column before the reads below)
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                if (q > 0 && 32 * q >= K) break;
+                const int i = lane + 32 * q;
+                if (i > j + 1 && i < K) {
+                    T* Li = Lp + loff(i);
+                    const T xq = x[q];
+#pragma unroll 4
+                    for (int t = j + 1; t < i; t++) Li[t] -= col[t] * xq;
+                }
+            }
+        }
+        __syncwarp();
+        return stop;
+    }
+
     __device__ __forceinline__ int activate_constraints() {
         unsigned char* se = sense();
-        if constexpr (TW > 1) {
-            // A team activates a whole warm start at once: one pass for every dot product the K row-by-row updates would
-            // compute (team_gram), one right-looking pass for the K forward substitutions (team_ldl) -- the same products
-            // in the same order, without K x (row fetch + dependent sweep). Anything the row-by-row path treats
-            // specially (singular pivot, pivot swap, more rows than dimensions) sends the activation back to it.
+        // A whole warm start is activated at once: one pass for every dot product the K row-by-row updates would compute,
+        // one right-looking pass for the K forward substitutions -- the same products in the same order, without
+        // K x (row fetch + dependent sweep). Anything the row-by-row path treats specially (singular pivot, pivot swap,
+        // more rows than dimensions, soft rows) sends the activation back to it. A team splits both passes over its warps
+        // (team_gram / team_ldl); a single warp runs them itself (gram_rows / ldl_rows; fp64, n <= 127).
+        constexpr bool WARP_FAST = TW <= 1 && sizeof(T) == 8 && NG <= 2 && NV <= 4;
+        if constexpr (TW > 1 || WARP_FAST) {
             if (uni(k == 0) && !(EXT && a.ns_max > 0)) {
                 int K = 0;
                 int* wsp = WS();
@@ -1277,10 +1388,16 @@ struct Warp {
                 K = uni(K);
                 __syncwarp();
                 if (K >= TEAM_GRAM_MIN && K <= a.n) {
-                    if (lane == 0) tbox()->rk[0] = K;
-                    team_run(TC_GRAM, K, 0);
-                    team_run(TC_LDL, K, 0);
-                    const int done = uni((int)reinterpret_cast<volatile TeamBox*>(tbox())->rk[0]);
+                    int done;
+                    if constexpr (TW > 1) {
+                        if (lane == 0) tbox()->rk[0] = K;
+                        team_run(TC_GRAM, K, 0);
+                        team_run(TC_LDL, K, 0);
+                        done = uni((int)reinterpret_cast<volatile TeamBox*>(tbox())->rk[0]);
+                    } else {
+                        gram_rows(K);
+                        done = ldl_rows(K);
+                    }
                     if (done >= K) {
                         LANE_LOOP(j, 0, K) {
                             const int id = wsp[j], sb = se[id];
