@@ -295,7 +295,7 @@ inline size_t product_smem(int n) {
     const int S = (n + 3) >> 2, nct = (n + 8) >> 3;
     size_t nfrag = 0;
     for (int t = 0; t < nct; t++) nfrag += (size_t)std::min(S, 2 * t + 2);
-    return nfrag * 256 + 2 * (size_t)(8 * nct) * sizeof(double) + 32;
+    return nfrag * 256 + 2 * (size_t)(8 * nct) * sizeof(double) + 32 + (nfrag * 4 + 15) / 16 * 16;
 }
 
 template <int NCT>
@@ -312,10 +312,19 @@ __global__ void __launch_bounds__(128, NCT <= 9 ? 4 : 3) qp_product_kernel(const
     T* vs = Bf + (size_t)nfrag * 32;                  // v, zero padded to 8 nct
     T* xus = vs + 8 * nct;                            // x_unc, zero padded
     int* sh = reinterpret_cast<int*>(xus + 8 * nct);  // [0] problem index
+    short2* fts = reinterpret_cast<short2*>(sh + 8);  // [nfrag] (column tile, k-step) of every B fragment
     const DevSettings<T>& st = a.st;
     const int g4 = lane >> 2, q4 = lane & 3;          // row within a block, column pair within a tile
     const int tx = n >> 3, jx = n & 7;                // tile / column of the x_unc column
 
+    {
+        int fb = 0;
+        for (int t = 0; t < nct; t++) {
+            const int ns_t = min(S, 2 * t + 2);
+            for (int s = tid; s < ns_t; s += 128) fts[fb + s] = make_short2((short)t, (short)s);
+            fb += ns_t;
+        }
+    }
     for (;;) {
         __syncthreads(); // the previous problem's fragments are no longer read
         if (tid == 0) sh[0] = atomicAdd(a.work_counter + 1, 1);
@@ -342,20 +351,29 @@ __global__ void __launch_bounds__(128, NCT <= 9 ? 4 : 3) qp_product_kernel(const
         const T* xug = a.xu + (size_t)p * n;
 
         for (int i = tid; i < 8 * nct; i += 128) { vs[i] = i < n ? vg[i] : (T)0; xus[i] = (unc && i < n) ? xug[i] : (T)0; }
-        { // B fragments: element (k, c) of [R^-1 | x_unc], k = 4 s + lane % 4, c = 8 t + lane / 4; zero below the diagonal
-            int fb = 0;
-            for (int t = 0; t < nct; t++) {
-                const int ns_t = min(S, 2 * t + 2), c = 8 * t + g4;
-                for (int s = wid; s < ns_t; s += 4) {
-                    const int k = 4 * s + q4;
-                    T val = 0;
-                    if (k < n) {
-                        if (c < n) { if (k <= c) val = Rg[roff(k, n) + c]; }
-                        else if (c == n && unc) val = xug[k];
+        { // B fragments: element (k, c) of [R^-1 | x_unc], k = 4 s + lane % 4, c = 8 t + lane / 4; zero below the diagonal.
+          // Four fragments per warp and trip: four independent gathers in flight per thread (one at a time left the
+          // global-load latency of this phase exposed: 19 % of the kernel's stall samples).
+            for (int f0 = wid; f0 < nfrag; f0 += 16) {
+                T val[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int f = f0 + 4 * q;
+                    val[q] = 0;
+                    if (f < nfrag) {
+                        const short2 ts = fts[f];
+                        const int k = 4 * ts.y + q4, c = 8 * ts.x + g4;
+                        if (k < n) {
+                            if (c < n) { if (k <= c) val[q] = Rg[roff(k, n) + c]; }
+                            else if (c == n && unc) val[q] = xug[k];
+                        }
                     }
-                    Bf[(size_t)(fb + s) * 32 + lane] = val;
                 }
-                fb += ns_t;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int f = f0 + 4 * q;
+                    if (f < nfrag) Bf[(size_t)f * 32 + lane] = val[q];
+                }
             }
         }
         __syncthreads();
@@ -367,6 +385,10 @@ __global__ void __launch_bounds__(128, NCT <= 9 ? 4 : 3) qp_product_kernel(const
             const int row = 8 * (simple ? blk - nbg : blk) + g4; // row within its group (simple bounds / general rows)
             const bool rvalid = row < (simple ? ms : mA);
             const int ci = simple ? row : ms + row;               // constraint index
+            // (bounds and sense of the row, asked for before the product so that the epilogue does not wait for them)
+            const bool owner = q4 == 0 && rvalid;
+            const T bub = owner ? bu[ci] : (T)0, blb = owner ? bl[ci] : (T)0;
+            int sb = owner ? so[ci] : 0;
             T C[NCT][2];
 #pragma unroll
             for (int t = 0; t < NCT; t++) { C[t][0] = 0; C[t][1] = 0; }
@@ -431,15 +453,13 @@ __global__ void __launch_bounds__(128, NCT <= 9 ? 4 : 3) qp_product_kernel(const
             }
             dotv += __shfl_xor_sync(FULL, dotv, 1);
             dotv += __shfl_xor_sync(FULL, dotv, 2);
-            if (q4 == 0 && rvalid) { // one lane per row: bounds, scaling, sense
-                int sb = so[ci];
+            if (owner) { // one lane per row: bounds, scaling, sense
                 if (!simple && nrm < st.zero_tol) {
-                    const T bub = bu[ci], blb = bl[ci];
                     if ((bub < -st.zero_tol || blb > st.zero_tol) && !(sb & B_IMMUTABLE) && !(sb & B_SOFT)) zero_row_infeasible = 1;
                     sb = B_IMMUTABLE;
                     if (a.sense_static) a.sense_static[(size_t)p * ldm + ci] = (unsigned char)B_IMMUTABLE;
                 }
-                T u_ = bu[ci], l_ = bl[ci];
+                T u_ = bub, l_ = blb;
                 if (unc) {
                     u_ -= dotx; l_ -= dotx;
                     if (u_ < -st.primal_tol || l_ > st.primal_tol) infeasible_pt = 1;
