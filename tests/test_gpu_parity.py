@@ -534,6 +534,54 @@ def test_drop_in_entry_points(cuda_lib, oracle):
         np.testing.assert_allclose(info["lam"], o.lam[0], rtol=0, atol=1e-7 * (1 + np.abs(o.lam[0]).max()))
 
 
+def test_workspace_pieces_reset_deactivate_extract_and_ldp(cuda_lib, oracle):
+    """The pieces of daqp_solve the interfaces call one by one on a workspace from setup_daqp (Julia: reset(model) =
+    daqp_deactivate_constraints + reset_daqp_workspace, api.jl:384-387; Simulink: daqp_ldp + daqp_extract_result,
+    DAQP_sfunc.c:567-571): a second daqp_solve continues warm (one iteration), after the reset the solve is the cold one
+    again (the reference's iteration count), daqp_ldp + daqp_extract_result give what daqp_solve gives."""
+    import ctypes as C
+    import daqp_b200 as dq
+    from oracle import harness
+    Problem, Settings, Result, Workspace, _ = harness._F64
+    L = dq.lib()
+    for f in ("daqp_solve", "reset_daqp_workspace", "daqp_deactivate_constraints", "daqp_extract_result", "free_daqp_workspace",
+              "free_daqp_ldp"):
+        getattr(L, f).restype = None
+    L.setup_daqp.restype = C.c_int; L.daqp_ldp.restype = C.c_int
+    b = generate_g1(1, 12, 36, 4, 9, seed=88)
+    o = oracle.solve(b)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    se = np.zeros(b.m, np.intc)
+    qp = Problem(b.n, b.m, b.ms, dp(b.H[0]), dp(b.f[0]), dp(b.A[0]), dp(b.bupper[0]), dp(b.blower[0]),
+                 se.ctypes.data_as(C.POINTER(C.c_int)), None, 0, 0)
+    work = Workspace()
+    t = C.c_double(0)
+    assert L.setup_daqp(C.byref(qp), C.byref(work), C.byref(t)) == 1
+    def solve():
+        x = np.zeros(b.n); lam = np.zeros(b.m)
+        res = Result(dp(x), dp(lam), 0, 0, 0, 0, 0, 0, 0)
+        L.daqp_solve(C.byref(res), C.byref(work))
+        return x, lam, res
+    x1, lam1, r1 = solve()
+    assert r1.exitflag == 1 and r1.iter == o.iter[0]
+    np.testing.assert_allclose(x1, o.x[0], atol=1e-9)
+    x2, _, r2 = solve()                      # kept factor and working set: nothing to do
+    assert r2.exitflag == 1 and r2.iter == 1
+    L.daqp_deactivate_constraints(C.byref(work)); L.reset_daqp_workspace(C.byref(work))
+    assert work.n_active == 0 and all((work.sense[i] & 1) == 0 for i in range(b.m))
+    x3, lam3, r3 = solve()                   # cold again
+    assert r3.exitflag == 1 and r3.iter == o.iter[0]
+    np.testing.assert_array_equal(x3, x1)
+    L.daqp_deactivate_constraints(C.byref(work)); L.reset_daqp_workspace(C.byref(work))
+    assert L.daqp_ldp(C.byref(work)) == 1 and work.iterations == o.iter[0]
+    x4 = np.zeros(b.n); lam4 = np.zeros(b.m)
+    res4 = Result(dp(x4), dp(lam4), 0, 0, 0, 0, 0, 0, 0)
+    L.daqp_extract_result(C.byref(res4), C.byref(work))
+    np.testing.assert_array_equal(x4, x1); np.testing.assert_array_equal(lam4, lam1)
+    assert res4.iter == o.iter[0] and abs(res4.fval - o.fval[0]) <= 1e-9 * (1 + abs(o.fval[0]))
+    L.free_daqp_workspace(C.byref(work)); L.free_daqp_ldp(C.byref(work))
+
+
 def test_device_entry_point_and_chunking(engine, oracle):
     """Device-pointer entry on the torch stream; a tiny scratch limit forces the multi-chunk path."""
     import torch
