@@ -239,7 +239,11 @@ struct Warp {
     __device__ __forceinline__ const T* du() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.dupper) + (size_t)p * a.sVec); }
     __device__ __forceinline__ const T* dl() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.dlower) + (size_t)p * a.sVec); }
     __device__ __forceinline__ const T* sc() const { return reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.scaling) + (size_t)pmat() * a.sVec); }
+#ifdef DAQP_B200_PHASE_CLOCKS
+    __device__ __forceinline__ void count(int) {}
+#else
     __device__ __forceinline__ void count(int which) { if (lane == 0) cnt()[which]++; }
+#endif
     // decision log (only when the caller asked for it: the cursor lives in the log itself, no register or shared memory)
     // (the decision log and the time limit are compiled into the extended and the team instantiations only: the plain
     // warp-per-problem kernel is bound by its instruction-cache footprint, and even dead code between hot blocks costs)
@@ -1540,6 +1544,15 @@ struct Warp {
     // the top of every iteration (see ldp_solve_kernel). Control flow is arranged so that the direction solve, the
     // ratio test, the scan and the working-set modification each appear once.
     static constexpr int RUNNING = 0x7fffffff;
+    // -DDAQP_B200_PHASE_CLOCKS (profiling build only): the eight path counters are replaced by the leader's clock cycles
+    // / 16 per phase -- 0 CSP or singular direction, 1 ratio test, 2 primal, 3 scan, 4 LDL add, 5 LDL remove, 7 activation
+#ifdef DAQP_B200_PHASE_CLOCKS
+#define PHASE_T0 const long long ph_t0 = clock64()
+#define PHASE_T1(w) do { if (lane == 0) cnt()[w] += (int)((clock64() - ph_t0) >> 4); } while (0)
+#else
+#define PHASE_T0 do { } while (0)
+#define PHASE_T1(w) do { } while (0)
+#endif
     __device__ __forceinline__ void begin(bool activate_first) {
         iter = 0; tried_repair = 0; cycle_counter = 0; best_fval = -1; do_activate = activate_first;
     }
@@ -1550,7 +1563,8 @@ struct Warp {
         if (uni(do_activate)) { // end of the previous iteration's refactor / cycle repair, or the warm start
             do_activate = false;
             if (iter > 0) reset();
-            const int aflag = uni(activate_constraints());
+            int aflag;
+            { PHASE_T0; aflag = uni(activate_constraints()); PHASE_T1(7); }
             if (iter == 0 && aflag < 0) return aflag;
         }
         iter = uni(iter + 1);
@@ -1568,18 +1582,20 @@ struct Warp {
             }
         }
         const bool was_singular = uni(sing != EMPTY_IND);
-        if (!was_singular) compute_csp(); else singular_direction();
-        int op = OP_REMOVE, arg = find_blocking();
+        { PHASE_T0; if (!was_singular) compute_csp(); else singular_direction(); PHASE_T1(0); }
+        int op = OP_REMOVE, arg;
+        { PHASE_T0; arg = find_blocking(); PHASE_T1(1); }
         T lamval = 0;
         bool refined = false;
         if (arg < 0) { // no blocking constraint: dual feasible (or, in singular mode, primal infeasible)
             if (was_singular) return EXIT_INFEASIBLE; // daqp.c:88-93
-            compute_primal();
+            { PHASE_T0; compute_primal(); PHASE_T1(2); }
             if (fval > fval_bound) return EXIT_INFEASIBLE;
             bool again = true;
             while (again) { // at most two passes: the scan is repeated once after a refinement (daqp.c:52-56)
                 again = false;
-                const int key = uni(scan_infeasible());
+                int key;
+                { PHASE_T0; key = uni(scan_infeasible()); PHASE_T1(3); }
                 if (key >= 0) {
                     arg = key >> 1;
                     const int lower = key & 1;
@@ -1619,7 +1635,7 @@ struct Warp {
             }
         }
         if (AUX && a.trace_out != nullptr) trace(op == OP_ADD ? 1 : 2, op == OP_ADD ? 2 * arg + (lamval < 0 ? 1 : 0) : uni(WS()[arg]));
-        modify(op, arg, lamval); // the ONE place where the working set changes inside the loop
+        { PHASE_T0; modify(op, arg, lamval); PHASE_T1(op == OP_ADD ? 4 : 5); } // the ONE place where the working set changes inside the loop
         if (op == OP_ADD && !refined) { // cycle guard, daqp.c:67-85 (skipped on the refine path, daqp.c:54-55)
             if (AUX && a.trace_out != nullptr) { // the objective the guard compares, bit for bit (8 = high word, 9 = low word)
                 const long long fb = __double_as_longlong((double)fval);
