@@ -165,6 +165,41 @@ def test_warm_start_and_equalities(engine, oracle):
     check_vs_oracle(engine, oracle, b, "equalities via bl == bu", use_sense=False)
 
 
+@pytest.mark.parametrize("n", [9, 31, 32, 33, 63, 64, 65, 100, 127])
+def test_warm_start_activation_across_shapes(engine, oracle, n):
+    """The two-pass activation (Gram pass + right-looking LDL', single-warp kernel for n <= 63, team kernel above) against
+    the oracle's row-by-row daqp_activate_constraints on both sides of every register-segment / team boundary: warm starts
+    from a perturbed neighbour's active set (wrong rows in, right rows missing), from the exact set, with equality rows,
+    with simple bounds, with fewer rows than the two-pass threshold, and with more rows than dimensions (falls back to the
+    row-by-row path and its drop rules). Flags, iterations, working sets in factor order, path counters equal."""
+    m, ms, na = 3 * n, (n // 3 if n % 2 else 0), max(4, (7 * n) // 10)
+    b = generate_g1(16, n, m, ms, na, seed=1200 + n)
+    nb = generate_g1(16, n, m, ms, na, seed=1200 + n)
+    rng = np.random.default_rng(n)
+    nb.f = b.f * (1 + 0.05 * rng.standard_normal(b.f.shape))
+    on = oracle.solve(nb)
+    b.sense[on.lam > 1e-12] = 1
+    b.sense[on.lam < -1e-12] = 3
+    check_vs_oracle(engine, oracle, b, f"n={n}: neighbour's active set", use_sense=True)
+    o = oracle.solve(generate_g1(16, n, m, ms, na, seed=1200 + n))
+    b.sense[:] = 0
+    b.sense[o.lam > 1e-12] = 1
+    b.sense[o.lam < -1e-12] = 3
+    _, r = check_vs_oracle(engine, oracle, b, f"n={n}: exact active set", use_sense=True)
+    assert (r.iter == 1).all()
+    for p in range(b.N):  # two of the active rows as equalities, the others as warm-start bits
+        for i in np.nonzero(b.sense[p])[0][:2]:
+            b.sense[p, i] |= 4
+    check_vs_oracle(engine, oracle, b, f"n={n}: with equalities", use_sense=True)
+    b.sense[:] = 0
+    for p in range(b.N):  # five rows only: below the two-pass threshold
+        act = np.nonzero(o.lam[p])[0][:5]
+        b.sense[p, act] = np.where(o.lam[p, act] > 0, 1, 3)
+    check_vs_oracle(engine, oracle, b, f"n={n}: five rows", use_sense=True)
+    b.sense[:] = np.where(rng.random(b.sense.shape) < 0.5, rng.choice([1, 3], b.sense.shape), 0)  # ~1.5 n rows
+    check_vs_oracle(engine, oracle, b, f"n={n}: more rows than dimensions", use_sense=True)
+
+
 def test_soft_constraints(engine, oracle):
     """sense & 8 (reference factorization.c:48-52, auxiliary.c:69-84,534-535, daqp.c:59-62): the working set grows past
     n (up to n + ns rows of the factor), exit flag 2, soft_slack reported."""
