@@ -1245,6 +1245,9 @@ struct Warp {
                 if (ok) return wk;
             }
         }
+#ifdef DAQP_B200_PHASE_CLOCKS
+        if (lane == 0) cnt()[6]++; // exact scans (the screening was absent or could not name the row)
+#endif
         team_run(TC_SCAN64, 0, 0);
         T wb = 0;
         int wk = INT_MAX;

@@ -28,6 +28,8 @@ for warm in (False, True):
     c = diag["counts"].double().mean(dim=0) * 16
     it = r["iter"].double().mean().item()
     names = ["csp", "ratio", "primal", "scan", "add", "remove", "-", "activate"]
+    c[6] = 0
     tot = c.sum().item()
     print(("warm" if warm else "cold"), f"mean iterations {it:.1f}; leader cycles per problem {tot:.0f} ({tot / it:.0f} per iteration)")
     print("   " + ", ".join(f"{n} {100 * v / tot:.1f}%" for n, v in zip(names, c.tolist()) if n != "-"))
+    print(f"   exact scans per problem (team mode only): {diag['counts'][:, 6].double().mean().item():.1f}")
