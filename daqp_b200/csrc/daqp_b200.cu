@@ -1640,10 +1640,9 @@ template <> struct Aos<float> { typedef DAQPProblemF32 Problem; typedef DAQPResu
 
 // one shape group on one lane: pack into the lane's pinned buffer, solve, scatter the results to the caller's structs
 template <typename T>
-int run_group(Lane& L, const ShapeKey& k, const std::vector<int>& ids, typename Aos<T>::Problem* qps, typename Aos<T>::Result* res,
+int run_group(Lane& L, const ShapeKey& k, const int* ids, size_t G, typename Aos<T>::Problem* qps, typename Aos<T>::Result* res,
               DAQPSettings* settings) {
     const int n = k.n, m = k.m, ms = k.ms, mA = m - ms;
-    const size_t G = ids.size();
     const size_t nH = G * n * n, nf = k.has_f ? G * n : 0, nA = G * (size_t)mA * n, nb = G * m, nx = G * n;
     const size_t bytes = (nH + nf + nA + 2 * nb + nx + nb + 2 * G) * sizeof(T) + (k.has_s ? nb : 0) * sizeof(int) + 2 * G * sizeof(int) + 16 * 64;
     cudaSetDevice(L.h->device);
@@ -1729,15 +1728,28 @@ int quadprog_batch_impl(int N, typename Aos<T>::Problem* qps, typename Aos<T>::R
     std::vector<Lane>* lanes = nullptr;
     int rc = get_lanes(&lanes);
     if (rc) return rc;
-    // largest estimated cost first (n^2 m per problem); a lane takes the next group as soon as it is free
-    std::vector<std::pair<double, const std::pair<const Key, std::vector<int>>*>> order;
+    // largest estimated cost first (n^2 m per problem); a lane takes the next piece as soon as it is free. A
+    // large group is cut into pieces so that a homogeneous batch -- one group -- still fills all lanes: while one lane's
+    // piece is being copied and solved, the others pack theirs out of the caller's pageable structs.
+    struct Piece { double cost; ShapeKey key; const int* ids; size_t count; };
+    std::vector<Piece> order;
     for (auto& kv : groups) {
         const double n = std::get<0>(kv.first), m = std::get<1>(kv.first);
-        order.push_back({n * n * std::max(m, 1.0) * (double)kv.second.size(), &kv});
+        const ShapeKey key{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first), std::get<3>(kv.first), std::get<4>(kv.first)};
+        const size_t G = kv.second.size();
+        const size_t per_problem = (size_t)(n * n + n + std::max(m - std::get<2>(kv.first), 0.0) * n + 2 * m) * sizeof(T);
+        // pieces of ~128 MB of input, at least 1024 problems; small groups stay whole
+        size_t piece_mb = 128;
+        if (const char* penv = getenv("DAQP_B200_AOS_PIECE_MB")) piece_mb = (size_t)std::max(1, atoi(penv)); // tuning knob
+        const size_t piece = std::max<size_t>(1024, (piece_mb << 20) / std::max<size_t>(per_problem, 1));
+        const size_t np = G > 2 * piece ? (G + piece - 1) / piece : 1;
+        for (size_t q = 0; q < np; q++) {
+            const size_t lo = G * q / np, hi = G * (q + 1) / np;
+            order.push_back({n * n * std::max(m, 1.0) * (double)(hi - lo), key, kv.second.data() + lo, hi - lo});
+        }
     }
-    std::sort(order.begin(), order.end(), [](auto& a, auto& b) { return a.first > b.first; });
-    auto key_of = [](const Key& t) { return ShapeKey{std::get<0>(t), std::get<1>(t), std::get<2>(t), std::get<3>(t), std::get<4>(t)}; };
-    if (order.size() == 1) return run_group<T>((*lanes)[0], key_of(order[0].second->first), order[0].second->second, qps, res, settings);
+    std::stable_sort(order.begin(), order.end(), [](const Piece& a, const Piece& b) { return a.cost > b.cost; });
+    if (order.size() == 1) return run_group<T>((*lanes)[0], order[0].key, order[0].ids, order[0].count, qps, res, settings);
     const int nl = (int)std::min<size_t>(lanes->size(), order.size());
     std::vector<int> rcs((size_t)nl, 0);
     std::vector<std::string> errs((size_t)nl);
@@ -1748,7 +1760,7 @@ int quadprog_batch_impl(int N, typename Aos<T>::Problem* qps, typename Aos<T>::R
             for (;;) {
                 const size_t gi = next.fetch_add(1);
                 if (gi >= order.size() || rcs[l]) break;
-                rcs[l] = run_group<T>((*lanes)[l], key_of(order[gi].second->first), order[gi].second->second, qps, res, settings);
+                rcs[l] = run_group<T>((*lanes)[l], order[gi].key, order[gi].ids, order[gi].count, qps, res, settings);
                 if (rcs[l]) errs[l] = g_last_error;
             }
         });
