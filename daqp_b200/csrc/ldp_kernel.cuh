@@ -245,6 +245,15 @@ struct Warp {
     __device__ __forceinline__ void count(int which) { if (lane == 0) cnt()[which]++; }
 #endif
     // decision log (only when the caller asked for it: the cursor lives in the log itself, no register or shared memory)
+    // -DDAQP_B200_PHASE_CLOCKS (profiling build only): the eight path counters are replaced by the leader's clock cycles
+    // / 16 per phase -- 0 CSP or singular direction, 1 ratio test, 2 primal, 3 scan, 4 LDL add, 5 LDL remove, 7 activation
+#ifdef DAQP_B200_PHASE_CLOCKS
+#define PHASE_T0 const long long ph_t0 = clock64()
+#define PHASE_T1(w) do { if (lane == 0) cnt()[w] += (int)((clock64() - ph_t0) >> 4); } while (0)
+#else
+#define PHASE_T0 do { } while (0)
+#define PHASE_T1(w) do { } while (0)
+#endif
     // (the decision log and the time limit are compiled into the extended and the team instantiations only: the plain
     // warp-per-problem kernel is bound by its instruction-cache footprint, and even dead code between hot blocks costs)
     static constexpr bool AUX = EXT || TW > 1;
@@ -1245,7 +1254,7 @@ struct Warp {
                 if (ok) return wk;
             }
         }
-#ifdef DAQP_B200_PHASE_CLOCKS
+#if defined(DAQP_B200_PHASE_CLOCKS) && DAQP_B200_PHASE_CLOCKS != 2
         if (lane == 0) cnt()[6]++; // exact scans (the screening was absent or could not name the row)
 #endif
         team_run(TC_SCAN64, 0, 0);
@@ -1398,8 +1407,13 @@ struct Warp {
                     int done;
                     if constexpr (TW > 1) {
                         if (lane == 0) tbox()->rk[0] = K;
+#if defined(DAQP_B200_PHASE_CLOCKS) && DAQP_B200_PHASE_CLOCKS == 2 // (slot 6: cycles of the Gram pass, slot 5: of the LDL' pass)
+                        { PHASE_T0; team_run(TC_GRAM, K, 0); PHASE_T1(6); }
+                        { PHASE_T0; team_run(TC_LDL, K, 0); PHASE_T1(5); }
+#else
                         team_run(TC_GRAM, K, 0);
                         team_run(TC_LDL, K, 0);
+#endif
                         done = uni((int)reinterpret_cast<volatile TeamBox*>(tbox())->rk[0]);
                     } else {
                         gram_rows(K);
@@ -1547,15 +1561,6 @@ struct Warp {
     // the top of every iteration (see ldp_solve_kernel). Control flow is arranged so that the direction solve, the
     // ratio test, the scan and the working-set modification each appear once.
     static constexpr int RUNNING = 0x7fffffff;
-    // -DDAQP_B200_PHASE_CLOCKS (profiling build only): the eight path counters are replaced by the leader's clock cycles
-    // / 16 per phase -- 0 CSP or singular direction, 1 ratio test, 2 primal, 3 scan, 4 LDL add, 5 LDL remove, 7 activation
-#ifdef DAQP_B200_PHASE_CLOCKS
-#define PHASE_T0 const long long ph_t0 = clock64()
-#define PHASE_T1(w) do { if (lane == 0) cnt()[w] += (int)((clock64() - ph_t0) >> 4); } while (0)
-#else
-#define PHASE_T0 do { } while (0)
-#define PHASE_T1(w) do { } while (0)
-#endif
     __device__ __forceinline__ void begin(bool activate_first) {
         iter = 0; tried_repair = 0; cycle_counter = 0; best_fval = -1; do_activate = activate_first;
     }

@@ -341,28 +341,29 @@ __device__ __noinline__ void team_gram(int lane, int wid, int K) {
 }
 
 // a13 for a team, second half: the LDL' factor of the Gram matrix team_gram left in L / D, in place and right-looking --
-// thread i owns row i. Step j: every row below scales its entry (l_ij = x_ij / d_j, factorization.c:96-99), publishes it,
-// and after the barrier subtracts l_tj x_ij from its entries t = j+1 .. i-1: the products and their (ascending pivot)
-// order are those of the forward substitutions of K successive daqp_update_LDL_add calls (factorization.c:86-92), and
+// step j: thread i scales the entry of row i (l_ij = x_ij / d_j, factorization.c:96-99) and publishes l_ij and x_ij; after
+// the barrier the rows below are dealt to the warps, which subtract l_tj x_rj from the entries t = j+1 .. r-1 of their
+// rows: the products and their (ascending pivot) order are those of the forward substitutions of K successive daqp_update_LDL_add calls (factorization.c:86-92), and
 // d_i = g_ii - sum_j x_ij l_ij (:100-103). The pass stops at the first row the one-by-one path treats specially -- a
 // singular pivot (factorization.c:106-110) or a daqp_pivot_last swap (auxiliary.c:379-396) -- and reports its index in
 // box->rk[0] (K = none); the leader then redoes the activation row by row.
 template <typename T, int TW>
 __device__ __noinline__ void team_ldl(int lane, int wid, int K) {
     TEAM_SMEM;
-    T* const colA = reinterpret_cast<T*>(smem_raw + box->otmp);
-    T* const colB = reinterpret_cast<T*>(smem_raw + box->opv);
+    T* const col = reinterpret_cast<T*>(smem_raw + box->otmp);  // l_ij of the step, by row
+    T* const xcol = reinterpret_cast<T*>(smem_raw + box->opv);  // x_ij of the step, by row
+    T* const Lp = reinterpret_cast<T*>(smem_raw + box->oL);
     T* Dp = reinterpret_cast<T*>(smem_raw + box->oD);
     volatile int* stop = box->rk;
     const int i = 32 * wid + lane;
-    T* Li = reinterpret_cast<T*>(smem_raw + box->oL) + loff(min(i, box->cap - 1));
+    T* Li = Lp + loff(min(i, box->cap - 1));
     const T sing_tol = (T)box->sing_tol, pivot_tol = (T)box->pivot_tol;
     if (i == 0 && Dp[0] < sing_tol) stop[0] = 0;
     team_bar<TW>();
     T acc = 0;
     for (int j = 0; j + 1 < K; j++) {
         if (stop[0] <= j) break; // (written before the barrier that ended the previous step: the whole team sees it)
-        T* col = (j & 1) ? colB : colA;
+        // scale column j: thread = row
         const bool below = i > j && i < K;
         const T dj = Dp[j];
         const T x = below ? Li[j] : (T)0;
@@ -371,6 +372,7 @@ __device__ __noinline__ void team_ldl(int lane, int wid, int K) {
             acc += x * l;
             Li[j] = l;
             col[i] = l;
+            xcol[i] = x;
             if (i == j + 1) {
                 const T d = Dp[i] - acc;
                 Dp[i] = d;
@@ -378,10 +380,31 @@ __device__ __noinline__ void team_ldl(int lane, int wid, int K) {
             }
         }
         team_bar<TW>();
-        if (below) {
-#pragma unroll 4
-            for (int t = j + 1; t < i; t++) Li[t] -= col[t] * x;
+        // trailing update L[r][t] -= l_tj x_rj for j < t < r: a WARP per row, lanes across its columns (contiguous, no bank
+        // conflicts, and the rows -- of very different lengths -- are dealt round-robin; a thread per row left the team
+        // waiting for the thread with the longest one: 3.6 k cycles per step, two thirds of a C4 activation)
+        // (four rows per trip: their chains are independent, and with three teams on an SM there is little else to hide
+        // the shared-memory round trips behind)
+        for (int r0 = j + 2 + wid; r0 < K; r0 += 4 * TW) {
+            T xr[4];
+            T* Lr[4];
+            int rr[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                rr[q] = r0 + q * TW;
+                const int rc = min(rr[q], K - 1);
+                xr[q] = xcol[rc];
+                Lr[q] = Lp + loff(rc);
+                if (rr[q] >= K) rr[q] = 0; // no columns: j + 1 + lane >= 1 > 0
+            }
+            for (int t = j + 1 + lane; t < rr[3] || t < rr[2] || t < rr[1] || t < rr[0]; t += 32) {
+                const T ct = col[min(t, K - 1)];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (t < rr[q]) Lr[q][t] -= ct * xr[q];
+            }
         }
+        team_bar<TW>();
     }
 }
 
