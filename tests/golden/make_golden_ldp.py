@@ -89,6 +89,12 @@ def raw_cases():
         fin = b.blower[:, ms:] > -1e29
         b.blower[:, ms:][fin] = (b.blower[:, ms:] * scale)[fin]
         out[name] = (b, fvb)
+    # rows the caller has switched off (sense = IMMUTABLE without ACTIVE: every scan skips them, daqp.c / auxiliary.c:110)
+    b, _ = out["rawldp_n8_m24"]
+    b2 = QPBatch(b.n, b.m, b.ms, b.H.copy(), None, b.A.copy(), b.bupper.copy(), b.blower.copy(), b.sense.copy())
+    rng = np.random.Generator(np.random.Philox(key=931))
+    b2.sense[rng.uniform(size=b2.sense.shape) < 0.25] = 4
+    out["rawldp_n8_m24_switched_off"] = (b2, None)
     return out
 
 
@@ -98,7 +104,7 @@ def main_raw():
     for name, (b, fvb) in raw_cases().items():
         rows = []
         for p in range(b.N):
-            r = [harness.raw_ldp(L, b.A[p], b.bupper[p], b.blower[p], None, b.ms, fvb) for L in libs]
+            r = [harness.raw_ldp(L, b.A[p], b.bupper[p], b.blower[p], b.sense[p] if b.sense.any() else None, b.ms, fvb) for L in libs]
             if r[0]["exitflag"] == r[1]["exitflag"] and r[0]["iter"] == r[1]["iter"] and r[0]["ws"] == r[1]["ws"]:
                 rows.append((p, r[0]))
         keep = [p for p, _ in rows]
@@ -106,7 +112,7 @@ def main_raw():
         for q, (_, r) in enumerate(rows):
             ws[q, :len(r["ws"])] = r["ws"]
         np.savez_compressed(os.path.join(OUT, name + ".npz"), n=b.n, m=b.m, ms=b.ms, A=b.A[keep], bupper=b.bupper[keep],
-                            blower=b.blower[keep], fval_bound=-1.0 if fvb is None else fvb,
+                            blower=b.blower[keep], sense=b.sense[keep], fval_bound=-1.0 if fvb is None else fvb,
                             exitflag=np.array([r["exitflag"] for _, r in rows], np.int32),
                             iter=np.array([r["iter"] for _, r in rows], np.int32), u=np.array([r["u"] for _, r in rows]),
                             fval=np.array([r["fval"] for _, r in rows]), ws=ws,

@@ -3,6 +3,8 @@
 fp64 tolerances are stated in tests/common.py (x 1e-9, fval 1e-9, lam 1e-7, relative); exit flags, iteration counts,
 final working sets and per-problem operation counts must be EQUAL.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -704,7 +706,8 @@ def test_raw_ldp_batch_and_hand_filled_workspace(cuda_lib, name):
     st = dq.default_settings(**({"fval_bound": fvb} if fvb is not None else {}))
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
-    assert L.daqp_b200_ldp_batch(None, P, n, m, ms, dp(A), dp(bu), dp(bl), None, C.byref(st), dp(u), dp(lam), dp(fv), ip(flag),
+    sense = np.ascontiguousarray(d["sense"], np.intc) if d["sense"].any() else None
+    assert L.daqp_b200_ldp_batch(None, P, n, m, ms, dp(A), dp(bu), dp(bl), ip(sense) if sense is not None else None, C.byref(st), dp(u), dp(lam), dp(fv), ip(flag),
                                  ip(it), C.byref(dg)) == 0, L.daqp_b200_last_error().decode()
     np.testing.assert_array_equal(flag, d["exitflag"])
     np.testing.assert_array_equal(it, d["iter"])
@@ -713,16 +716,44 @@ def test_raw_ldp_batch_and_hand_filled_workspace(cuda_lib, name):
     ok = d["exitflag"] > 0
     np.testing.assert_allclose(u[ok], d["u"][ok], atol=1e-9 * (1 + np.abs(d["u"][ok]).max()))
     np.testing.assert_allclose(2 * fv[ok], d["fval"][ok], rtol=1e-9)
-    rb = dq.ldp_batch(A, bu, bl, **({"fval_bound": fvb} if fvb is not None else {}))  # the Python wrapper of the same call
+    rb = dq.ldp_batch(A, bu, bl, sense, **({"fval_bound": fvb} if fvb is not None else {}))  # the Python wrapper of the same call
     np.testing.assert_array_equal(rb.exitflag, flag); np.testing.assert_array_equal(rb.iter, it)
     np.testing.assert_array_equal(rb.x, u)
     for p in range(min(P, 6)):
-        r = harness.raw_ldp(L, A[p], bu[p], bl[p], None, ms, fvb)
+        r = harness.raw_ldp(L, A[p], bu[p], bl[p], sense[p] if sense is not None else None, ms, fvb)
         assert r["exitflag"] == d["exitflag"][p] and r["iter"] == d["iter"][p], f"{name}[{p}] via daqp_ldp"
         assert r["ws"] == d["ws"][p, :d["n_active"][p]].tolist()
         if r["exitflag"] > 0:
             np.testing.assert_allclose(r["u"], d["u"][p], atol=1e-9 * (1 + np.abs(d["u"][p]).max()))
             assert abs(r["fval"] - d["fval"][p]) <= 1e-9 * (1 + d["fval"][p])
+
+
+def test_raw_ldp_device_entry(cuda_lib):
+    """daqp_b200_ldp_device (device arrays, asynchronous on the caller's stream) gives what the host entry gives."""
+    import ctypes as C
+    import torch
+    import daqp_b200 as dq
+    d = np.load(os.path.join(GOLDEN_DIR, "rawldp_n12_m36_ms4.npz"))
+    n, m, ms, P = int(d["n"]), int(d["m"]), int(d["ms"]), d["exitflag"].shape[0]
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev).contiguous()
+    A, bu, bl = t(d["A"]), t(d["bupper"]), t(d["blower"])
+    u = torch.zeros((P, n), dtype=torch.float64, device=dev); lam = torch.zeros((P, m), dtype=torch.float64, device=dev)
+    fv = torch.zeros(P, dtype=torch.float64, device=dev)
+    flag = torch.zeros(P, dtype=torch.int32, device=dev); it = torch.zeros(P, dtype=torch.int32, device=dev)
+    L = dq.lib()
+    L.daqp_b200_ldp_device.restype = C.c_int
+    p = lambda x: C.c_void_p(x.data_ptr())
+    st = dq.default_settings()
+    stream = torch.cuda.current_stream(dev).cuda_stream or 1
+    assert L.daqp_b200_ldp_device(None, P, n, m, ms, p(A), p(bu), p(bl), None, C.byref(st), p(u), p(lam), p(fv), p(flag), p(it),
+                                  C.c_void_p(stream)) == 0, L.daqp_b200_last_error().decode()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(flag.cpu().numpy(), d["exitflag"])
+    np.testing.assert_array_equal(it.cpu().numpy(), d["iter"])
+    ok = d["exitflag"] > 0
+    np.testing.assert_allclose(u.cpu().numpy()[ok], d["u"][ok], atol=1e-9 * (1 + np.abs(d["u"][ok]).max()))
+    np.testing.assert_allclose(2 * fv.cpu().numpy()[ok], d["fval"][ok], rtol=1e-9)
 
 
 @pytest.mark.parametrize("name", bnb_golden_names())

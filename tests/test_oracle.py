@@ -224,12 +224,14 @@ def test_raw_ldp_fixtures_are_what_the_reference_gives(oracle_libs, name):
     for p in np.nonzero(d["exitflag"] == 1)[0]:
         Ax = np.concatenate([d["u"][p, :ms], d["A"][p] @ d["u"][p]])
         scale = np.concatenate([np.ones(ms), np.linalg.norm(d["A"][p], axis=1)])
-        assert (Ax <= d["bupper"][p] + 1e-5 * scale).all() and (Ax >= d["blower"][p] - 1e-5 * scale).all()
+        on = (d["sense"][p] & 4) == 0  # rows the caller switched off (IMMUTABLE without ACTIVE) do not constrain u
+        assert (Ax <= d["bupper"][p] + 1e-5 * scale)[on].all() and (Ax >= d["blower"][p] - 1e-5 * scale)[on].all()
         assert abs(d["fval"][p] - d["u"][p] @ d["u"][p]) < 1e-9 * (1 + d["fval"][p])
     if oracle_libs.have_ref():
         L = C.CDLL(os.path.join(oracle_libs.REF_DIR, "libdaqp_ref.so"))
         for p in range(d["exitflag"].shape[0]):
-            r = oracle_libs.raw_ldp(L, d["A"][p], d["bupper"][p], d["blower"][p], None, ms, fvb)
+            se = d["sense"][p] if d["sense"].any() else None
+            r = oracle_libs.raw_ldp(L, d["A"][p], d["bupper"][p], d["blower"][p], se, ms, fvb)
             assert r["exitflag"] == d["exitflag"][p] and r["iter"] == d["iter"][p]
             assert r["ws"] == list(d["ws"][p, :d["n_active"][p]])
             np.testing.assert_array_equal(r["u"], d["u"][p])
