@@ -167,13 +167,16 @@ def test_warm_start_and_equalities(engine, oracle):
     check_vs_oracle(engine, oracle, b, "equalities via bl == bu", use_sense=False)
 
 
-@pytest.mark.parametrize("n", [9, 31, 32, 33, 63, 64, 65, 100, 127])
-def test_warm_start_activation_across_shapes(engine, oracle, n):
+@pytest.mark.parametrize("n,mode", [(9, None), (31, None), (32, None), (33, None), (63, None), (64, "0"), (64, "4"), (65, "0"),
+                                    (65, "4"), (100, "0"), (100, "4"), (127, "0"), (127, "4")])
+def test_warm_start_activation_across_shapes(engine, oracle, n, mode, monkeypatch):
     """The two-pass activation (Gram pass + right-looking LDL', single-warp kernel for n <= 63, team kernel above) against
     the oracle's row-by-row daqp_activate_constraints on both sides of every register-segment / team boundary: warm starts
     from a perturbed neighbour's active set (wrong rows in, right rows missing), from the exact set, with equality rows,
     with simple bounds, with fewer rows than the two-pass threshold, and with more rows than dimensions (falls back to the
     row-by-row path and its drop rules). Flags, iterations, working sets in factor order, path counters equal."""
+    if mode is not None:  # n + 1 > 64: the single-warp kernel ("0") and the team kernel ("4")
+        monkeypatch.setenv("DAQP_B200_TEAM", mode)
     m, ms, na = 3 * n, (n // 3 if n % 2 else 0), max(4, (7 * n) // 10)
     b = generate_g1(16, n, m, ms, na, seed=1200 + n)
     nb = generate_g1(16, n, m, ms, na, seed=1200 + n)
@@ -263,14 +266,20 @@ def test_c4_at_scale_cold_and_warm(engine, oracle):
 
 @pytest.mark.parametrize("shape", [(66, 140, 0, 50), (95, 300, 40, 70), (96, 200, 96, 80), (127, 260, 3, 100),
                                    (100, 600, 0, 75)])
-def test_team_mode_shapes(engine, oracle, shape):
-    """Sizes on both sides of the team kernel's three / four row segments (n + 1 = 67 .. 128), with m beyond 512."""
+@pytest.mark.parametrize("mode", ["4", "0"])
+def test_team_mode_shapes(engine, oracle, shape, mode, monkeypatch):
+    """Sizes on both sides of the team kernel's three / four row segments (n + 1 = 67 .. 128), with m beyond 512 -- through
+    the team kernel (DAQP_B200_TEAM=4: wherever it can run) and through the single-warp kernel (=0); the library's own
+    choice between the two is by measured speed (daqp_b200.cu) and takes one or the other of these paths."""
+    monkeypatch.setenv("DAQP_B200_TEAM", mode)
     n, m, ms, na = shape
-    check_vs_oracle(engine, oracle, generate_g1(120, n, m, ms, na, seed=7000 + n + ms), f"team G1{shape}")
+    check_vs_oracle(engine, oracle, generate_g1(120, n, m, ms, na, seed=7000 + n + ms), f"team={mode} G1{shape}")
 
 
-def test_team_mode_rare_paths(engine, oracle):
-    """Singular steps, infeasibility, warm starts (incl. over-determined ones) and equalities at n > 64."""
+@pytest.mark.parametrize("mode", ["4", "0"])
+def test_team_mode_rare_paths(engine, oracle, mode, monkeypatch):
+    """Singular steps, infeasibility, warm starts (incl. over-determined ones) and equalities at n > 64, in both kernels."""
+    monkeypatch.setenv("DAQP_B200_TEAM", mode)
     b = generate_g1(100, 70, 160, 0, 50, seed=7101)
     b.A[:, 80:160] = b.A[:, 0:80]; b.bupper[:, 80:160] = b.bupper[:, 0:80]; b.blower[:, 80:160] = b.blower[:, 0:80]
     check_vs_oracle(engine, oracle, b, "team: duplicate rows")
