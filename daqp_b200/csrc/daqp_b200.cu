@@ -342,7 +342,8 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     // cp.async-staged kernel with 12 -- a third more resident warps buys nothing, so it stays opt-in.
     // the decision log and settings.time_limit live in the extended and the team instantiations of the solve kernel
     const DevSettings<T> st = to_dev_settings<T>(settings);
-    const bool aux = sizeof(T) == 8 && ((diag && diag->trace && diag->trace_cap > 0) || st.time_limit_ns != 0);
+    // (... and so does the screening scan in row blocks for m > 256: see scan_infeasible)
+    const bool aux = sizeof(T) == 8 && ((diag && diag->trace && diag->trace_cap > 0) || st.time_limit_ns != 0 || (m > 256 && m <= 768));
     la.aux = aux ? 1 : 0;
     bool regstage = false;
     if (const char* renv = getenv("DAQP_B200_REGSTAGE")) regstage = atoi(renv) != 0 && sizeof(T) == 8 && ns_max == 0 && !ps && team == 0 && nv <= 2 && !aux;
@@ -366,7 +367,7 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     if (rc) return rc;
     int tune = 0; // experiment knob: 1 = bulk L2 prefetch before the scan, 2 = no fp32 screening, 4 = stream policy for Mt32
     if (const char* tenv = getenv("DAQP_B200_TUNE")) tune = atoi(tenv);
-    const bool screening = sizeof(T) == 8 && !(tune & 2) && (team ? (m + 31) / 32 <= TEAM_SCREEN_MAX_GROUPS * team : m <= 256);
+    const bool screening = sizeof(T) == 8 && !(tune & 2) && (team ? (m + 31) / 32 <= TEAM_SCREEN_MAX_GROUPS * team : m <= (regstage ? 256 : 768));
     for (int p0 = 0; p0 < N; p0 += chunk) {
         const int P = std::min(chunk, N - p0);
         Carver cv(h->arena);
@@ -1159,7 +1160,7 @@ static int workspace_setup_impl(DAQPB200Handle* h, int N, int K, int n, int m, i
     // the matrix arrays hold G sets, everything else N problems
     WS_TRY(ws_alloc(w, &ps.Mt, (size_t)G * n * ldm));
     WS_TRY(ws_alloc(w, &ps.Mr, (size_t)G * m * ldn));
-    if (m <= 256) WS_TRY(ws_alloc(w, &ps.Mt32, (size_t)G * ((n + 3) / 4) * m * 4));
+    if (m <= 768) WS_TRY(ws_alloc(w, &ps.Mt32, (size_t)G * ((n + 3) / 4) * m * 4));
     WS_TRY(ws_alloc(w, &ps.du, (size_t)N * ldm)); WS_TRY(ws_alloc(w, &ps.dl, (size_t)N * ldm));
     WS_TRY(ws_alloc(w, &ps.sc, (size_t)G * ldm)); WS_TRY(ws_alloc(w, &ps.Ri, (size_t)G * n * (n + 1) / 2));
     WS_TRY(ws_alloc(w, &ps.vv, (size_t)N * n)); WS_TRY(ws_alloc(w, &ps.sense8, (size_t)N * ldm));

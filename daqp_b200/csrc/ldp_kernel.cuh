@@ -144,7 +144,7 @@ inline size_t ldp_layout(LdpArgs<T>& a, int team = 0) {
     a.oarena = (int)bytes;
     const size_t slab = (size_t)a.m * 16, rowb = (size_t)a.ldn * sizeof(T);
     a.rowbuf = (unsigned)std::max<size_t>(RB * rowb, (size_t)RB * SCR_PITCH * sizeof(T));
-    if (team == 0 || team == 1) bytes += (a.m <= 256) ? std::max<size_t>(QRING * slab, 2 * (size_t)a.rowbuf) : 2 * (size_t)a.rowbuf;
+    if (team == 0 || team == 1) bytes += std::max<size_t>(QRING * (a.m <= 256 ? slab : (size_t)2048), 2 * (size_t)a.rowbuf); // (m > 256: blocks of 128 rows)
     bytes = (bytes + 15) / 16 * 16; // (a team stages through registers: no arena)
     a.per_warp_bytes = (unsigned)bytes;
     a.sMt = (unsigned)((size_t)a.n * a.ldm * sizeof(T));
@@ -949,6 +949,97 @@ struct Warp {
         return -2; // ambiguous: decide in fp64
     }
 
+    // The same screening for m > 256: the rows go through the ring in BLOCKS of 128 (four row groups per lane, 2 KB per ring
+    // slot -- the arena a single warp has anyway), the per-lane candidate record is carried across the blocks and the warp
+    // decides once at the end. Same error bound, same decision rule, same fallback.
+    __device__ __forceinline__ int scan_screen_blocks() {
+        constexpr int NR = 4, BR = 32 * NR;
+        const unsigned slab = (unsigned)a.m * 16u; // bytes of one quad of columns in global memory
+        const int nq = (a.n + 3) >> 2;
+        const unsigned ub = smem_u32(u32());
+        const double unorm = (double)sqrtf((float)fval) * 1.0001 + 1e-22;
+        const double delta = 1.01 * (double)(a.n + 3) * 5.9604644775390625e-8 * unorm;
+        const double ep = -(double)a.st.primal_tol;
+        const unsigned char* se = sense();
+        double best = 1e300, second = 1e300;
+        int key = INT_MAX;
+        bool best_sure = false;
+        for (int row0 = 0; row0 < a.m; row0 += BR) {
+            float acc[NR];
+            bool own[NR];
+            double bu[NR], bl[NR], bs[NR];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                const int row = row0 + lane + 32 * r;
+                acc[r] = 0.f;
+                own[r] = row < a.m;
+                bu[r] = bl[r] = bs[r] = 0;
+                if (own[r]) {
+                    bu[r] = __ldg(reinterpret_cast<const double*>(du()) + row);
+                    bl[r] = __ldg(reinterpret_cast<const double*>(dl()) + row);
+                    bs[r] = __ldg(reinterpret_cast<const double*>(sc()) + row);
+                }
+            }
+            const char* src = reinterpret_cast<const char*>(a.Mt32) + (size_t)pmat() * a.sMt32 + 16 * (size_t)(row0 + lane);
+            const unsigned ring0 = smem_u32(S) + a.oarena + 16 * lane;
+            for (int q0 = -QRING; q0 < nq; q0 += QRING) {
+#pragma unroll
+                for (int sl = 0; sl < QRING; sl++) {
+                    const int q = q0 + sl;
+                    if (q >= 0 && q < nq) {
+                        cp_async_wait<QRING - 1>();
+                        float uq[4];
+                        lds_vec<float>(ub + 16 * q, uq);
+#pragma unroll
+                        for (int r = 0; r < NR; r++) {
+                            if (own[r]) {
+                                float t[4];
+                                lds_vec<float>(ring0 + sl * (16u * BR) + 512 * r, t);
+#pragma unroll
+                                for (int e = 0; e < 4; e++) acc[r] += t[e] * uq[e];
+                            }
+                        }
+                    }
+                    if (q + QRING < nq) {
+#pragma unroll
+                        for (int r = 0; r < NR; r++) cp_async16_if(own[r], ring0 + sl * (16u * BR) + 512 * r, src + 512 * r);
+                        src += slab;
+                    }
+                    cp_async_commit();
+                }
+            }
+            cp_async_wait<0>();
+#pragma unroll
+            for (int r = 0; r < NR; r++) { // ascending rows per lane across the blocks: strict '<' keeps the first of equal candidates
+                const int row = row0 + lane + 32 * r;
+                const double mu = (double)acc[r];
+                const double cu = bu[r] - mu, cl = mu - bl[r];
+                const bool lower = cl < cu;
+                const double cand = lower ? cl : cu;
+                const double bound = ep * bs[r];
+                const bool possible = own[r] && !(se[min(row, a.m - 1)] & (B_ACTIVE + B_IMMUTABLE)) && cand - delta < bound;
+                const bool nb = possible && cand < best;
+                second = nb ? best : ((possible && cand < second) ? cand : second);
+                best_sure = nb ? (cand + delta < bound) : best_sure;
+                key = nb ? 2 * row + (int)lower : key;
+                best = nb ? cand : best;
+            }
+            __syncwarp(); // the ring is refilled by the next block
+        }
+        double wbest = best;
+        int wkey = key;
+        warp_argmin(wbest, wkey);
+        wkey = uni(wkey);
+        if (wkey == INT_MAX) return -1;
+        wbest = uni(wbest);
+        double other = (key == wkey) ? second : best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) other = fmin(other, __shfl_xor_sync(FULL, other, o));
+        const bool sure = __any_sync(FULL, key == wkey && best_sure);
+        if (sure && uni(other - wbest > 2.0 * delta)) return wkey;
+        return -2;
+    }
+
     // ---- a8: Mu = M u for all rows, most-violated inactive row (auxiliary.c:89-152).
     // Returns 2*row + (1 if violated at the lower bound), or -1 when every inactive row is feasible.
     __device__ __forceinline__ int scan_infeasible() {
@@ -971,9 +1062,14 @@ struct Warp {
             }
         } else
         if constexpr (sizeof(T) == 8) {
-            if (a.Mt32 != nullptr) { // screening in fp32 (host enables it for m <= 256)
+            if (a.Mt32 != nullptr) { // screening in fp32 (the host enables it up to m = 768; beyond 256 rows in blocks of 128)
                 int r;
-                switch ((a.m + 31) >> 5) {
+                // (the block form is compiled into the EXTENDED instantiation only -- the host sends m > 256 there: inlined
+                // into the plain kernel it cost the C3 headline 2 % in instruction-cache misses without ever running)
+                bool blocks = false;
+                if constexpr (EXT) blocks = a.m > 256;
+                if (blocks) r = scan_screen_blocks();
+                else switch ((a.m + 31) >> 5) {
                     case 1: r = scan_screen<1>(); break;
                     case 2: r = scan_screen<2>(); break;
                     case 3: r = scan_screen<3>(); break;

@@ -122,6 +122,15 @@ def test_shapes_vs_oracle(engine, oracle, shape):
     check_vs_oracle(engine, oracle, generate_g1(N, n, m, ms, na, seed=2000 + n + ms), f"G1{shape}")
 
 
+@pytest.mark.parametrize("shape", [(50, 300, 0, 40), (20, 520, 5, 14), (33, 700, 0, 20), (63, 257, 10, 50), (40, 768, 0, 30),
+                                   (30, 800, 0, 20)])
+def test_many_rows_screening_in_blocks(engine, oracle, shape):
+    """m > 256 in the single-warp kernel: the fp32 screening scan takes the rows through its ring in blocks of 128 (up to
+    m = 768; beyond that the exact scan), same decisions as the oracle."""
+    n, m, ms, na = shape
+    check_vs_oracle(engine, oracle, generate_g1(150, n, m, ms, na, seed=8100 + m), f"G1{shape}")
+
+
 def test_g0_distribution(engine, oracle):
     check_vs_oracle(engine, oracle, generate_g0(800, 50, 150), "G0 n50 m150")
 
