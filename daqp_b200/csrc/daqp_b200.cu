@@ -326,11 +326,11 @@ static int solve_device_impl(DAQPB200Handle* h, int N, int n, int m, int ms, con
     // problem instead (plain fp64 path; soft constraints / workspaces / shared matrices stay on the warp kernel)
     // Where the switch sits (measured per shape, scripts/bench_warm.py, 12 500 problems, cold solve ms team / warp): a warp per
     // problem keeps its fp32 screening ring up to m = 256 and wins there until n ~ 100 (n = 66: 70 / 31, 72: 81 / 39, 80: 101 /
-    // 65, 96: 131 / 110, 112: 157 / 171); without the ring the team wins from n ~ 80 on (n = 72, m = 288: 99 / 95; 80, 320:
-    // 125 / 160; 96, 288: 148 / 247; 104, 312: 175 / 382; C4: 3x).
+    // 65, 96: 131 / 110, 112: 157 / 171); beyond m = 256, where the warp streams the copy through its ring in row blocks, the
+    // team wins from n ~ 88 on (n = 80, m = 320: 125 / 101; 88, 400: 169 / 180; 96, 288: 149 / 152; 104, 312: 175 / 227; C4: 3x).
     int team = 0;
     const bool team_ok = sizeof(T) == 8 && ns_max == 0 && !ps && nv >= 3 && cap <= 128;
-    if (team_ok && (m > 256 ? n > 72 : n >= 104)) team = 4;
+    if (team_ok && (m > 256 ? n >= 88 : n >= 104)) team = 4;
     if (const char* tenv = getenv("DAQP_B200_TEAM")) { // experiment knob: 0 = a warp per problem everywhere; 4 = a team wherever it
         const int tv = atoi(tenv);                        // can run; 2 = two-warp teams for 32 < n + 1 <= 64 as well (measured on C3:
         if (tv == 0) team = 0;                            // 220 ms against 105 ms for a warp per problem -- the iteration is bound by
