@@ -543,6 +543,33 @@ def test_settings_and_limits(engine, oracle):
     assert (run_gpu(engine, b).exitflag == -8).all()  # singular H needs the proximal driver: flagged
 
 
+@pytest.mark.parametrize("shape,mode", [((12, 36, 4, 9), None), ((70, 150, 0, 40), "4")])
+def test_decision_trace_matches_oracle(engine, oracle, shape, mode, monkeypatch):
+    """DAQPB200Diag.trace (extended / team instantiations): the kernel's log of working-set decisions -- add with side,
+    remove, exit flag -- equals the oracle's log entry for entry (the objective words differ in the last bits)."""
+    import torch
+    import daqp_b200
+    if mode is not None:
+        monkeypatch.setenv("DAQP_B200_TEAM", mode)
+    n, m, ms, na = shape
+    b = generate_g1(24, n, m, ms, na, seed=9100 + n)
+    cap = 1024
+    o = oracle.solve(b, log_cap=cap)
+    dev = torch.device("cuda:0")
+    t = lambda a, ty=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=ty, device=dev).contiguous()
+    diag = daqp_b200.Engine.alloc_diag(b.N, n, m, dev)
+    diag["trace"] = torch.zeros((b.N, 1 + 2 * cap), dtype=torch.int32, device=dev)
+    out = engine.solve_batch_device(t(b.H), t(b.f), t(b.A), t(b.bupper), t(b.blower), None, ms=ms, diag=diag)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out["iter"].cpu().numpy(), o.iter)
+    tr = diag["trace"].cpu().numpy()
+    for p in range(b.N):
+        g = tr[p, 1:1 + 2 * int(tr[p, 0])].reshape(-1, 2)
+        keep = lambda log: [(int(c), int(v)) for c, v in log if c not in (8, 9)]
+        assert keep(g) == keep(o.oplog[p]), f"problem {p}"
+        assert (g[:, 0] == 8).sum() == (o.oplog[p][:, 0] == 8).sum()
+
+
 def test_time_limit(engine, oracle):
     """settings.time_limit (daqp.c:95-103): the clock is read every 32nd iteration, so with a limit no solve can meet a
     problem either ends before its 32nd iteration, untouched, or leaves there with EXIT_TIMELIMIT (-7) and iter = 32; a

@@ -185,6 +185,27 @@ def test_fp32_oracle_vs_live_fp32_reference(oracle_libs):
         assert np.abs(r.x - o.x).max() <= 1e-4 * (1 + np.abs(r.x).max())
 
 
+def test_oracle_decision_log(oracle_libs):
+    """OracleLib.solve(log_cap=...) records every working-set decision (the log tests/trace_diff.py compares with the
+    kernel's DAQPB200Diag.trace): as many adds / removes as the path counters say, one objective value per add made by the
+    feasibility scan, the exit flag last."""
+    b = generate_g1(20, 12, 36, 4, 9, seed=77)
+    o = oracle_libs.OracleLib().solve(b, log_cap=4096)
+    for p in range(b.N):
+        log = o.oplog[p]
+        codes = log[:, 0]
+        assert codes[-1] == 7 and log[-1, 1] == o.exitflag[p]
+        assert (codes == 1).sum() == o.counts[p, 1] and (codes == 2).sum() == o.counts[p, 2]
+        assert (codes == 8).sum() == (codes == 9).sum() == (codes == 1).sum()  # no warm start: every add comes from a scan
+        adds = log[codes == 1, 1] >> 1
+        assert ((adds >= 0) & (adds < b.m)).all()
+        live = set()
+        for c, v in log:  # the log replays to the final working set
+            if c == 1: live.add(int(v) >> 1)
+            elif c == 2: live.discard(int(v))
+        assert live == set(o.ws[p])
+
+
 @pytest.mark.parametrize("name", ldp_golden_names())
 def test_pure_ldp_oracle_matches_reference(oracle_libs, name):
     """H == NULL, f == NULL (the LDP min |x|^2 itself, utils.c:103-110): the oracle -- which walks it with an identity
